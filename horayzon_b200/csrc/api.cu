@@ -1,0 +1,350 @@
+// api.cu -- the C ABI of libhorayzon_b200.so (see include/horayzon_b200.h).
+//
+// Host-side drivers standing where horizon_gridded_comp / horizon_locations_comp
+// (horizon_comp.cpp:629-822, 828-1094) and shapes::CppTerrain
+// (shadow_comp.cpp:304-605) stand in the reference.  No CPU fallback: every
+// compute entry point needs a CUDA device and fails with a status otherwise.
+#include "hzb_common.cuh"
+#include <math.h>
+#include <string.h>
+#include <chrono>
+#include <limits>
+
+namespace hzb {
+
+static thread_local std::string g_error;
+static thread_local hzb_stats g_stats;
+
+void set_error(const std::string& msg) { g_error = msg; }
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+        cached = prop.multiProcessorCount; cached_dev = dev;
+    }
+    return cached;
+}
+int parse_algorithm(const char* s) {
+    if (!s) return -1;
+    if (!strcmp(s, "discrete_sampling")) return 0;
+    if (!strcmp(s, "binary_search")) return 1;
+    if (!strcmp(s, "guess_constant")) return 2;
+    return -1;
+}
+int parse_geom_type(const char* s) {
+    if (!s) return -1;
+    if (!strcmp(s, "triangle")) return 0;
+    if (!strcmp(s, "quad")) return 1;
+    if (!strcmp(s, "grid")) return 2;
+    return -1;
+}
+
+static int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        set_error(std::string("no CUDA device available (libhorayzon_b200 has no CPU fallback): ") +
+                  (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+        cudaGetLastError();
+        return 1;
+    }
+    return 0;
+}
+
+static int read_counters(const Scene& s, hzb_stats& st) {
+    Counters c;
+    HZB_CUDA(cudaMemcpy(&c, s.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+    st.rays = c.rays; st.node_visits = c.node_visits; st.prim_tests = c.prim_tests; st.units = c.units;
+    st.warp_node_visits = c.warp_node_visits;
+    st.num_prims = s.num_prims; st.num_nodes = s.num_nodes8; st.bvh_bytes = s.bvh_bytes;
+    st.t_h2d = s.t_h2d; st.t_build = s.t_build;
+    if (c.stack_overflow) { set_error("BVH traversal stack overflow (results invalid)"); return 1; }
+    return 0;
+}
+
+template <typename T>
+struct DevBuf {  // RAII device buffer
+    T* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { HZB_CUDA(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T))); return 0; }
+    int upload(const T* h, size_t n) {
+        HZB_TRY(alloc(n));
+        HZB_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+        return 0;
+    }
+};
+
+}  // namespace hzb
+
+using namespace hzb;
+
+struct hzb_scene { Scene s; };
+struct hzb_terrain {
+    Scene s; bool ready = false; TerrainParams tp{};
+    float *d_tilt = nullptr, *d_norm = nullptr, *d_enl = nullptr, *d_elev = nullptr; uint8_t* d_mask = nullptr;
+    void* d_out = nullptr; size_t out_cap = 0;
+    void release() {
+        cudaFree(d_tilt); cudaFree(d_norm); cudaFree(d_enl); cudaFree(d_elev); cudaFree(d_mask); cudaFree(d_out);
+        d_tilt = d_norm = d_enl = d_elev = nullptr; d_mask = nullptr; d_out = nullptr; out_cap = 0;
+        scene_free(s); ready = false;
+    }
+};
+
+extern "C" {
+
+const char* hzb_last_error(void) { return g_error.c_str(); }
+const char* hzb_version(void) { return "horayzon_b200 0.1 (sm_100a)"; }
+int hzb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int hzb_get_stats(hzb_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
+
+// ------------------------------------------------------------------ scene
+hzb_scene* hzb_scene_create(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vert_simp,
+                            int num_vert_simp, const int32_t* tri_ind_simp, int num_tri_simp, int device) {
+    if (require_device()) return nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); cudaGetLastError(); return nullptr; }
+    hzb_scene* h = new hzb_scene();
+    h->s.device = device;
+    if (scene_upload_and_build(h->s, vert_grid, dem_dim_0, dem_dim_1, vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp)) {
+        scene_free(h->s); delete h; return nullptr;
+    }
+    return h;
+}
+void hzb_scene_destroy(hzb_scene* h) { if (h) { cudaSetDevice(h->s.device); scene_free(h->s); delete h; } }
+int hzb_scene_stats(const hzb_scene* h, hzb_stats* out) {
+    if (!h || !out) { set_error("null argument"); return 1; }
+    memset(out, 0, sizeof(*out));
+    return read_counters(h->s, *out);
+}
+
+int hzb_horizon_gridded_dev(hzb_scene* h, const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                            int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
+                            int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                            float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
+                            void* stream) {
+    if (!h) { set_error("null scene"); return 1; }
+    const int alg = parse_algorithm(ray_algorithm);
+    if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
+    if (azim_num < 1 || dim_in_0 < 0 || dim_in_1 < 0 || row_begin < 0 || row_end > dim_in_0) { set_error("invalid dimensions"); return 1; }
+    if (offset_0 < 0 || offset_1 < 0 || offset_0 + dim_in_0 > h->s.H || offset_1 + dim_in_1 > h->s.W) {
+        set_error("inner domain exceeds DEM dimensions"); return 1;
+    }
+    if (!(hori_acc > 0.f)) { set_error("hori_acc must be positive"); return 1; }
+    HZB_CUDA(cudaSetDevice(h->s.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    if (T.elev_num < 2) { set_error("elevation table too small"); return 1; }
+    HorizonParams p{};
+    HZB_TRY(upload_tables(h->s, T, p, st));
+    p.algorithm = alg; p.vec_norm = d_vec_norm; p.vec_north = d_vec_north; p.mask = d_mask;
+    p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1;
+    p.row_begin = row_begin; p.row_end = row_end; p.hori_fill = hori_fill; p.ray_org_elev = ray_org_elev;
+    p.hori = d_hori_buffer;
+    return launch_horizon_gridded(h->s, p, st);
+}
+
+// -------------------------------------------------------------- host tier
+int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
+                        const float* vec_north, int offset_0, int offset_1, float* hori_buffer, int dim_in_0,
+                        int dim_in_1, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                        const char* geom_type, const float* vert_simp, int num_vert_simp,
+                        const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
+                        float hori_fill, float ray_org_elev) {
+    memset(&g_stats, 0, sizeof(g_stats));
+    const double t_start = now_s();
+    if (require_device()) return 1;
+    if (parse_geom_type(geom_type) < 0) { set_error("invalid input argument for geom_type"); return 1; }
+    if (!vert_grid || !vec_norm || !vec_north || !hori_buffer || !mask) { set_error("null pointer argument"); return 1; }
+    int dev = 0; cudaGetDevice(&dev);
+    hzb_scene* h = hzb_scene_create(vert_grid, dem_dim_0, dem_dim_1, vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp, dev);
+    if (!h) return 1;
+    struct Guard { hzb_scene* h; ~Guard() { hzb_scene_destroy(h); } } guard{h};
+    const size_t nc = (size_t)dim_in_0 * dim_in_1;
+    double t0 = now_s();
+    DevBuf<float> d_norm, d_north, d_hori; DevBuf<uint8_t> d_mask;
+    HZB_TRY(d_norm.upload(vec_norm, nc * 3)); HZB_TRY(d_north.upload(vec_north, nc * 3)); HZB_TRY(d_mask.upload(mask, nc));
+    HZB_TRY(d_hori.alloc(nc * (size_t)azim_num));
+    const double t_h2d_extra = now_s() - t0;
+    t0 = now_s();
+    HZB_TRY(hzb_horizon_gridded_dev(h, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
+                                    azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
+                                    ray_org_elev, d_hori.p, nullptr));
+    HZB_CUDA(cudaDeviceSynchronize());
+    const double t_trace = now_s() - t0;
+    t0 = now_s();
+    HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
+    const double t_d2h = now_s() - t0;
+    HZB_TRY(read_counters(h->s, g_stats));
+    g_stats.t_h2d += t_h2d_extra; g_stats.t_trace = t_trace; g_stats.t_d2h = t_d2h; g_stats.t_total = now_s() - t_start;
+    return 0;
+}
+
+int hzb_horizon_locations(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* coords,
+                          const float* vec_norm, const float* vec_north, float* hori_buffer, float* hori_dist_buffer,
+                          int num_loc, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                          const char* geom_type, float elev_ang_low_lim, const float* ray_org_elev, int hori_dist_out) {
+    memset(&g_stats, 0, sizeof(g_stats));
+    const double t_start = now_s();
+    if (require_device()) return 1;
+    const int alg = parse_algorithm(ray_algorithm);
+    if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
+    if (parse_geom_type(geom_type) < 0) { set_error("invalid input argument for geom_type"); return 1; }
+    if (hori_dist_out && alg == 2) { set_error("horizon detection algorithm 'guess_constant' not implemented for horizon distance computation"); return 1; }
+    if (num_loc < 0 || azim_num < 1 || !(hori_acc > 0.f)) { set_error("invalid dimensions"); return 1; }
+    int dev = 0; cudaGetDevice(&dev);
+    hzb_scene* h = hzb_scene_create(vert_grid, dem_dim_0, dem_dim_1, nullptr, 0, nullptr, 0, dev);  // no TIN (:848-852)
+    if (!h) return 1;
+    struct Guard { hzb_scene* h; ~Guard() { hzb_scene_destroy(h); } } guard{h};
+    if (num_loc == 0) return 0;
+    const size_t n = (size_t)num_loc, no = n * (size_t)azim_num;
+    DevBuf<float> d_coords, d_norm, d_north, d_elev, d_hori, d_dist;
+    HZB_TRY(d_coords.upload(coords, n * 3)); HZB_TRY(d_norm.upload(vec_norm, n * 3)); HZB_TRY(d_north.upload(vec_north, n * 3));
+    HZB_TRY(d_elev.upload(ray_org_elev, n));
+    HZB_TRY(d_hori.upload(hori_buffer, no));  // keeps the caller's pre-fill for skipped locations
+    if (hori_dist_out) HZB_TRY(d_dist.upload(hori_dist_buffer, no));
+    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    HorizonParams p{};
+    HZB_TRY(upload_tables(h->s, T, p, nullptr));
+    p.algorithm = alg;
+    LocationParams lp{d_coords.p, d_norm.p, d_north.p, d_elev.p, d_hori.p, d_dist.p, num_loc, hori_dist_out};
+    double t0 = now_s();
+    HZB_TRY(launch_horizon_locations(h->s, p, lp, nullptr));
+    HZB_CUDA(cudaDeviceSynchronize());
+    const double t_trace = now_s() - t0;
+    HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, no * sizeof(float), cudaMemcpyDeviceToHost));
+    if (hori_dist_out) HZB_CUDA(cudaMemcpy(hori_dist_buffer, d_dist.p, no * sizeof(float), cudaMemcpyDeviceToHost));
+    HZB_TRY(read_counters(h->s, g_stats));
+    g_stats.t_trace = t_trace; g_stats.t_total = now_s() - t_start;
+    return 0;
+}
+
+// ---------------------------------------------------------------- terrain
+hzb_terrain* hzb_terrain_create(void) { return new hzb_terrain(); }
+void hzb_terrain_destroy(hzb_terrain* t) { if (t) { if (t->ready) cudaSetDevice(t->s.device); t->release(); delete t; } }
+
+int hzb_terrain_initialise(hzb_terrain* t, const float* vert_grid, int dem_dim_0, int dem_dim_1, int offset_0,
+                           int offset_1, const float* vec_tilt, const float* vec_norm, int dim_in_0, int dim_in_1,
+                           const float* surf_enl_fac, const float* elevation, const uint8_t* mask,
+                           const char* geom_type, float sw_dir_cor_fill, float ang_max, int refrac_cor) {
+    if (!t) { set_error("null terrain"); return 1; }
+    if (require_device()) return 1;
+    if (parse_geom_type(geom_type) < 0) { set_error("invalid input argument for geom_type"); return 1; }
+    if (offset_0 < 0 || offset_1 < 0 || offset_0 + dim_in_0 > dem_dim_0 || offset_1 + dim_in_1 > dem_dim_1) {
+        set_error("inner domain exceeds DEM dimensions"); return 1;
+    }
+    t->release();
+    int dev = 0; cudaGetDevice(&dev);
+    t->s.device = dev;
+    HZB_TRY(scene_upload_and_build(t->s, vert_grid, dem_dim_0, dem_dim_1, nullptr, 0, nullptr, 0));
+    const size_t nc = (size_t)dim_in_0 * dim_in_1;
+    auto up = [&](auto** d, const auto* h, size_t n) -> int {
+        HZB_CUDA(cudaMalloc((void**)d, (n ? n : 1) * sizeof(**d)));
+        HZB_CUDA(cudaMemcpy(*d, h, n * sizeof(**d), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    HZB_TRY(up(&t->d_tilt, vec_tilt, nc * 3)); HZB_TRY(up(&t->d_norm, vec_norm, nc * 3));
+    HZB_TRY(up(&t->d_enl, surf_enl_fac, nc)); HZB_TRY(up(&t->d_elev, elevation, nc)); HZB_TRY(up(&t->d_mask, mask, nc));
+    TerrainParams& tp = t->tp;
+    tp.vec_tilt = t->d_tilt; tp.vec_norm = t->d_norm; tp.surf_enl_fac = t->d_enl; tp.elevation = t->d_elev; tp.mask = t->d_mask;
+    tp.offset_0 = offset_0; tp.offset_1 = offset_1; tp.dim_in_0 = dim_in_0; tp.dim_in_1 = dim_in_1;
+    tp.sw_dir_cor_fill = sw_dir_cor_fill; tp.ang_max = ang_max; tp.refrac_cor = refrac_cor;
+    tp.dot_prod_min = cosf((float)(((double)ang_max / 180.0) * M_PI));  // shadow_comp.cpp:498
+    tp.t_ref = 283.15f; tp.p_ref = 101.0f; tp.lapse = 0.0065f;           // :349-354
+    const float g = 9.81f, R_d = 287.0f;
+    tp.expo = g / (R_d * tp.lapse);
+    t->ready = true;
+    return 0;
+}
+
+static int terrain_out(hzb_terrain* t, size_t bytes) {
+    if (t->out_cap < bytes) {
+        cudaFree(t->d_out); t->d_out = nullptr; t->out_cap = 0;
+        HZB_CUDA(cudaMalloc(&t->d_out, bytes));
+        t->out_cap = bytes;
+    }
+    return 0;
+}
+
+int hzb_terrain_shadow_dev(hzb_terrain* t, const float* sun, uint8_t* d_out, void* stream) {
+    if (!t || !t->ready) { set_error("terrain not initialised"); return 1; }
+    HZB_CUDA(cudaSetDevice(t->s.device));
+    return launch_shadow(t->s, t->tp, sun, d_out, (cudaStream_t)stream);
+}
+int hzb_terrain_sw_dir_cor_dev(hzb_terrain* t, const float* sun, float* d_out, void* stream) {
+    if (!t || !t->ready) { set_error("terrain not initialised"); return 1; }
+    HZB_CUDA(cudaSetDevice(t->s.device));
+    return launch_sw_dir_cor(t->s, t->tp, sun, d_out, (cudaStream_t)stream);
+}
+int hzb_terrain_shadow_batch(hzb_terrain* t, const float* suns, int n_sun, uint8_t* out) {
+    if (!t || !t->ready) { set_error("terrain not initialised"); return 1; }
+    if (n_sun <= 0) return 0;
+    const size_t nc = (size_t)t->tp.dim_in_0 * t->tp.dim_in_1;
+    HZB_CUDA(cudaSetDevice(t->s.device));
+    HZB_TRY(terrain_out(t, nc * (size_t)n_sun));
+    for (int k = 0; k < n_sun; ++k)
+        HZB_TRY(launch_shadow(t->s, t->tp, suns + 3 * k, (uint8_t*)t->d_out + nc * k, nullptr));
+    HZB_CUDA(cudaMemcpy(out, t->d_out, nc * (size_t)n_sun, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int hzb_terrain_sw_dir_cor_batch(hzb_terrain* t, const float* suns, int n_sun, float* out) {
+    if (!t || !t->ready) { set_error("terrain not initialised"); return 1; }
+    if (n_sun <= 0) return 0;
+    const size_t nc = (size_t)t->tp.dim_in_0 * t->tp.dim_in_1;
+    HZB_CUDA(cudaSetDevice(t->s.device));
+    HZB_TRY(terrain_out(t, nc * (size_t)n_sun * sizeof(float)));
+    for (int k = 0; k < n_sun; ++k)
+        HZB_TRY(launch_sw_dir_cor(t->s, t->tp, suns + 3 * k, (float*)t->d_out + nc * k, nullptr));
+    HZB_CUDA(cudaMemcpy(out, t->d_out, nc * (size_t)n_sun * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int hzb_terrain_shadow(hzb_terrain* t, const float* sun, uint8_t* out) { return hzb_terrain_shadow_batch(t, sun, 1, out); }
+int hzb_terrain_sw_dir_cor(hzb_terrain* t, const float* sun, float* out) { return hzb_terrain_sw_dir_cor_batch(t, sun, 1, out); }
+int hzb_terrain_stats(const hzb_terrain* t, hzb_stats* out) {
+    if (!t || !t->ready || !out) { set_error("terrain not initialised"); return 1; }
+    memset(out, 0, sizeof(*out));
+    return read_counters(t->s, *out);
+}
+
+// ------------------------------------------------------ azimuthal integrals
+int hzb_sky_view_factor_dev(const float* a, const float* h, const float* t, long long cells, int K, float* o, void* st) {
+    return launch_svf(0, a, h, t, cells, K, o, (cudaStream_t)st);
+}
+int hzb_visible_sky_fraction_dev(const float* a, const float* h, const float* t, long long cells, int K, float* o, void* st) {
+    return launch_svf(1, a, h, t, cells, K, o, (cudaStream_t)st);
+}
+int hzb_topographic_openness_dev(const float* a, const float* h, long long cells, int K, float* o, void* st) {
+    return launch_svf(2, a, h, nullptr, cells, K, o, (cudaStream_t)st);
+}
+static int integral_host(int kind, const float* azim, const float* hori, const float* tilt, int ny, int nx, int K, float* out) {
+    if (require_device()) return 1;
+    if (ny < 0 || nx < 0 || K < 1) { set_error("invalid dimensions"); return 1; }
+    const size_t nc = (size_t)ny * nx;
+    if (nc == 0) return 0;
+    DevBuf<float> d_a, d_h, d_t, d_o;
+    HZB_TRY(d_a.upload(azim, K)); HZB_TRY(d_h.upload(hori, nc * (size_t)K));
+    if (kind != 2) HZB_TRY(d_t.upload(tilt, nc * 3));
+    HZB_TRY(d_o.alloc(nc));
+    HZB_TRY(launch_svf(kind, d_a.p, d_h.p, d_t.p, (long long)nc, K, d_o.p, nullptr));
+    HZB_CUDA(cudaMemcpy(out, d_o.p, nc * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int hzb_sky_view_factor(const float* azim, const float* hori, const float* tilt, int ny, int nx, int K, float* out) {
+    return integral_host(0, azim, hori, tilt, ny, nx, K, out);
+}
+int hzb_visible_sky_fraction(const float* azim, const float* hori, const float* tilt, int ny, int nx, int K, float* out) {
+    return integral_host(1, azim, hori, tilt, ny, nx, K, out);
+}
+int hzb_topographic_openness(const float* azim, const float* hori, int ny, int nx, int K, float* out) {
+    return integral_host(2, azim, hori, nullptr, ny, nx, K, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+// horizon.cu -- horizon search kernels (B200, sm_100a).
+//
+// Replaces the TBB row loop and the three search algorithms of the reference
+// (horizon_comp.cpp:302-498, 519-612, 739-800, 926-1070).  One lane owns one
+// grid cell and walks its azimuth chain; warps pull 8x4-cell tiles from an
+// atomic queue (persistent CTAs, grid = SM count x resident CTAs).  All
+// arithmetic that decides a table index or a ray direction is written with
+// explicitly rounded intrinsics in the reference's float/double mix, so the
+// outputs are decision-exact against the CPU oracle.
+#include "hzb_geom.cuh"
+#include <math.h>
+#include <string.h>
+
+namespace hzb {
+
+// ------------------------------------------------------------ host tables
+static inline float deg2rad_f(float a) { return (float)(((double)a / 180.0) * M_PI); }  // horizon_comp.cpp:37-39
+
+void HorizonTables::make(int azim_n, float dist_km, float acc_deg, float low_deg) {
+    azim_num = azim_n;
+    acc = deg2rad_f(acc_deg);
+    low = deg2rad_f(low_deg);
+    up = deg2rad_f(89.98f);                      // horizon_comp.cpp:648
+    dist = (float)((double)dist_km * 1000.0);    // :670
+    step = (double)acc / 5.0;
+    azim_sin.resize(azim_n); azim_cos.resize(azim_n);
+    for (int i = 0; i < azim_n; ++i) {           // :714-718: float angle, float sin/cos overloads
+        const float ang = (float)((2 * M_PI) / azim_n * i);
+        azim_sin[i] = sinf(ang); azim_cos[i] = cosf(ang);
+    }
+    elev_num = (int)ceil((double)(up - low) / step) + 1;  // :721-722
+    elev_ang.resize(elev_num); elev_sin.resize(elev_num); elev_cos.resize(elev_num);
+    for (int i = 0; i < elev_num; ++i) {         // :726-731: anchored at the upper limit
+        const float ang = (float)((double)up - step * i);
+        elev_ang[elev_num - i - 1] = ang;
+        elev_sin[elev_num - i - 1] = sinf(ang);
+        elev_cos[elev_num - i - 1] = cosf(ang);
+    }
+}
+
+int upload_tables(Scene& s, const HorizonTables& T, HorizonParams& p, cudaStream_t st) {
+    const size_t need = (size_t)2 * T.azim_num + (size_t)3 * T.elev_num;
+    if (need > s.tables_cap) {
+        if (s.d_tables) cudaFree(s.d_tables);
+        s.d_tables = nullptr; s.tables_cap = 0;
+        HZB_CUDA(cudaMalloc((void**)&s.d_tables, need * sizeof(float)));
+        s.tables_cap = need;
+    }
+    std::vector<float> h(need);
+    float* q = h.data();
+    memcpy(q, T.azim_sin.data(), 4 * (size_t)T.azim_num); q += T.azim_num;
+    memcpy(q, T.azim_cos.data(), 4 * (size_t)T.azim_num); q += T.azim_num;
+    memcpy(q, T.elev_ang.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
+    memcpy(q, T.elev_sin.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
+    memcpy(q, T.elev_cos.data(), 4 * (size_t)T.elev_num);
+    // synchronous copy from pageable memory: the host vector may die afterwards
+    HZB_CUDA(cudaMemcpyAsync(s.d_tables, h.data(), need * sizeof(float), cudaMemcpyHostToDevice, st));
+    HZB_CUDA(cudaStreamSynchronize(st));
+    p.azim_sin = s.d_tables; p.azim_cos = p.azim_sin + T.azim_num;
+    p.elev_ang = p.azim_cos + T.azim_num; p.elev_sin = p.elev_ang + T.elev_num; p.elev_cos = p.elev_sin + T.elev_num;
+    p.azim_num = T.azim_num; p.elev_num = T.elev_num;
+    p.acc = T.acc; p.low = T.low; p.up = T.up; p.dist = T.dist; p.step = T.step;
+    return 0;
+}
+
+// ------------------------------------------------------------ device side
+namespace {
+
+struct Frame {  // per-cell local frame: columns east, north, norm (horizon_comp.cpp:773-779)
+    F3 org;
+    float m00, m01, m02, m10, m11, m12, m20, m21, m22;
+};
+
+__device__ __forceinline__ Frame make_frame(F3 vert, F3 norm, F3 north, float lift) {
+    Frame f;
+    f.org = f3(__fadd_rn(vert.x, __fmul_rn(norm.x, lift)), __fadd_rn(vert.y, __fmul_rn(norm.y, lift)),
+               __fadd_rn(vert.z, __fmul_rn(norm.z, lift)));
+    const float ex = __fsub_rn(__fmul_rn(north.y, norm.z), __fmul_rn(north.z, norm.y));
+    const float ey = __fsub_rn(__fmul_rn(north.z, norm.x), __fmul_rn(north.x, norm.z));
+    const float ez = __fsub_rn(__fmul_rn(north.x, norm.y), __fmul_rn(north.y, norm.x));
+    f.m00 = ex; f.m01 = north.x; f.m02 = norm.x;
+    f.m10 = ey; f.m11 = north.y; f.m12 = norm.y;
+    f.m20 = ez; f.m21 = north.z; f.m22 = norm.z;
+    return f;
+}
+
+struct Search {  // everything a lane needs to cast one ray of the search
+    SceneView sv;
+    const float* __restrict__ azim_sin; const float* __restrict__ azim_cos;
+    const float* __restrict__ elev_ang; const float* __restrict__ elev_sin; const float* __restrict__ elev_cos;
+    int azim_num, elev_num;
+    float acc, low, up, dist; double step;
+    unsigned int* overflow;
+};
+
+__device__ __forceinline__ Search make_search(const SceneView& sv, const HorizonParams& p, Counters* c) {
+    Search s;
+    s.sv = sv; s.azim_sin = p.azim_sin; s.azim_cos = p.azim_cos; s.elev_ang = p.elev_ang;
+    s.elev_sin = p.elev_sin; s.elev_cos = p.elev_cos; s.azim_num = p.azim_num; s.elev_num = p.elev_num;
+    s.acc = p.acc; s.low = p.low; s.up = p.up; s.dist = p.dist; s.step = p.step;
+    s.overflow = reinterpret_cast<unsigned int*>(&c->stack_overflow);
+    return s;
+}
+
+__device__ __forceinline__ F3 ray_dir(const Search& s, const Frame& f, int ie, int k) {
+    const float ec = __ldg(s.elev_cos + ie), es = __ldg(s.elev_sin + ie);
+    const float r0 = __fmul_rn(ec, __ldg(s.azim_sin + k)), r1 = __fmul_rn(ec, __ldg(s.azim_cos + k)), r2 = es;
+    return f3(__fadd_rn(__fadd_rn(__fmul_rn(f.m00, r0), __fmul_rn(f.m01, r1)), __fmul_rn(f.m02, r2)),
+              __fadd_rn(__fadd_rn(__fmul_rn(f.m10, r0), __fmul_rn(f.m11, r1)), __fmul_rn(f.m12, r2)),
+              __fadd_rn(__fadd_rn(__fmul_rn(f.m20, r0), __fmul_rn(f.m21, r1)), __fmul_rn(f.m22, r2)));
+}
+
+// any-hit cast (castRay_occluded1, horizon_comp.cpp:241-262)
+__device__ __forceinline__ bool cast_any(const Search& s, const Frame& f, int ie, int k, LaneCounters& cnt) {
+    cnt.rays++;
+    float tfar = s.dist;
+    return trace_bvh2<false>(s.sv, f.org, ray_dir(s, f, ie, k), tfar, cnt, s.overflow);
+}
+// closest-hit cast (castRay_intersect1, :268-292): dist = distance of the hit
+__device__ __forceinline__ bool cast_closest(const Search& s, const Frame& f, int ie, int k, LaneCounters& cnt, float& dist) {
+    cnt.rays++;
+    float tfar = s.dist;
+    const bool hit = trace_bvh2<true>(s.sv, f.org, ray_dir(s, f, ie, k), tfar, cnt, s.overflow);
+    dist = tfar;
+    return hit;
+}
+
+__device__ __forceinline__ int index_of(const Search& s, float elev) {  // (int)roundf((elev-low)/(acc/5.0))
+    const double q = __ddiv_rn((double)__fsub_rn(elev, s.low), s.step);
+    return (int)roundf(__double2float_rn(q));
+}
+__device__ __forceinline__ float midpoint(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
+
+// bisection for one azimuth (horizon_comp.cpp:348-376); returns the final index
+template <bool WD>
+__device__ __forceinline__ int bisect(const Search& s, const Frame& f, int k, LaneCounters& cnt, float& mid, float& dist_hit) {
+    float lim_up = s.up, lim_low = s.low;
+    float samp = midpoint(lim_up, lim_low);
+    int ie = index_of(s, samp);
+    while (true) {
+        const float ea = __ldg(s.elev_ang + ie);
+        if (!(fmaxf(__fsub_rn(lim_up, ea), __fsub_rn(ea, lim_low)) > s.acc)) break;
+        bool hit;
+        if (WD) { float d; hit = cast_closest(s, f, ie, k, cnt, d); if (hit) dist_hit = d; }
+        else hit = cast_any(s, f, ie, k, cnt);
+        if (hit) lim_low = ea; else lim_up = ea;
+        samp = midpoint(lim_up, lim_low);
+        ie = index_of(s, samp);
+    }
+    mid = samp;
+    return ie;
+}
+
+// output staging: four consecutive azimuths per 16-byte store when aligned
+struct OutBuf {
+    float* out; bool vec; float b0, b1, b2, b3;
+    __device__ __forceinline__ void init(float* o, bool v) { out = o; vec = v; b0 = b1 = b2 = b3 = 0.f; }
+    __device__ __forceinline__ void put(int k, float v) {
+        if (!vec) { out[k] = v; return; }
+        b0 = b1; b1 = b2; b2 = b3; b3 = v;
+        if ((k & 3) == 3) *reinterpret_cast<float4*>(out + (k - 3)) = make_float4(b0, b1, b2, b3);
+    }
+};
+
+// One cell, all azimuths.  ALG 0 discrete_sampling (:302-333), 1 binary_search
+// (:339-381), 2 guess_constant (:387-498).  Termination rule: a hit
+// at the top index counts as a miss, a miss at index 0 as a hit.
+template <int ALG>
+__device__ void cell_search(const Search& s, const Frame& f, OutBuf& ob, LaneCounters& cnt) {
+    const int top = s.elev_num - 1;
+    if (ALG == 0) {
+        for (int k = 0; k < s.azim_num; ++k) {
+            int cur = 0, prev = 0; bool hit = true;
+            while (hit) {
+                prev = cur; cur = min(cur + 10, top);
+                hit = cast_any(s, f, cur, k, cnt);
+                if (cur == top) hit = false;
+            }
+            ob.put(k, midpoint(__ldg(s.elev_ang + prev), __ldg(s.elev_ang + cur)));
+        }
+    } else if (ALG == 1) {
+        for (int k = 0; k < s.azim_num; ++k) {
+            float mid, dh = 0.f;
+            bisect<false>(s, f, k, cnt, mid, dh);
+            ob.put(k, mid);
+        }
+    } else {
+        float mid, dh = 0.f;
+        int prev_az = bisect<false>(s, f, 0, cnt, mid, dh);
+        ob.put(0, mid);
+        for (int k = 1; k < s.azim_num; ++k) {
+            int cur = max(prev_az - 5, 0), prev = 0, count = 0; bool hit = true;
+            while (hit) {
+                prev = cur; cur = min(cur + 10, top);
+                hit = cast_any(s, f, cur, k, cnt); ++count;
+                if (cur == top) hit = false;
+            }
+            if (count <= 1) {
+                cur = min(prev_az + 5, top); hit = false;
+                while (!hit) {
+                    prev = cur; cur = max(cur - 10, 0);
+                    hit = cast_any(s, f, cur, k, cnt);
+                    if (cur == 0) hit = true;
+                }
+            }
+            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + prev), __ldg(s.elev_ang + cur)));
+            ob.put(k, __ldg(s.elev_ang + ie));
+            prev_az = ie;
+        }
+    }
+}
+
+__device__ __forceinline__ void flush_counters(LaneCounters& cnt, unsigned int units, Counters* c) {
+    unsigned int r = cnt.rays, n = cnt.nodes, p = cnt.prims, u = units;
+    for (int o = 16; o > 0; o >>= 1) {
+        r += __shfl_xor_sync(0xffffffffu, r, o); n += __shfl_xor_sync(0xffffffffu, n, o);
+        p += __shfl_xor_sync(0xffffffffu, p, o); u += __shfl_xor_sync(0xffffffffu, u, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&c->rays, (unsigned long long)r); atomicAdd(&c->node_visits, (unsigned long long)n);
+        atomicAdd(&c->prim_tests, (unsigned long long)p); atomicAdd(&c->units, (unsigned long long)u);
+    }
+    cnt.rays = cnt.nodes = cnt.prims = 0;
+}
+
+constexpr int HG_THREADS = 128;
+
+template <int ALG>
+__global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, HorizonParams p, Counters* counters,
+                                                                unsigned int* tile_counter) {
+    const Search s = make_search(sv, p, counters);
+    const int lane = threadIdx.x & 31;
+    const int rows = p.row_end - p.row_begin;
+    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    while (true) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= num_tiles) break;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int i = p.row_begin + ty * 4 + (lane >> 3), j = tx * 8 + (lane & 7);
+        unsigned int units = 0;
+        if (i < p.row_end && j < p.dim_in_1) {
+            const size_t c = (size_t)i * p.dim_in_1 + j;
+            float* out = p.hori + c * p.azim_num;
+            if (p.mask[c] == 1) {
+                const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
+                const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
+                const float4 v = sv.vert4[(size_t)(i + p.offset_0) * sv.W + (j + p.offset_1)];
+                const Frame f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+                OutBuf ob; ob.init(out, vec);
+                cell_search<ALG>(s, f, ob, cnt);
+                units = p.azim_num;
+            } else {
+                for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+            }
+        }
+        flush_counters(cnt, units, counters);
+    }
+}
+
+// ---- arbitrary locations (horizon_comp.cpp:828-1094)
+__global__ void k_loc_snap(SceneView sv, LocationParams lp, float4* org_valid, Counters* counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lp.num_loc) return;
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int* ovf = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
+    const F3 nrm = f3(lp.vec_norm[3 * i], lp.vec_norm[3 * i + 1], lp.vec_norm[3 * i + 2]);
+    const F3 ini = f3(lp.coords[3 * i], lp.coords[3 * i + 1], lp.coords[3 * i + 2]);
+    float dist = 100000.0f;                                           // :951-952
+    bool hit = trace_bvh2<true>(sv, ini, nrm, dist, cnt, ovf);
+    if (!hit) {                                                       // :953-957
+        dist = 100000.0f;
+        hit = trace_bvh2<true>(sv, ini, f3(-nrm.x, -nrm.y, -nrm.z), dist, cnt, ovf);
+        dist = -dist;
+    }
+    const float lift = __fadd_rn(dist, lp.ray_org_elev[i]);           // :961-963
+    org_valid[i] = make_float4(__fadd_rn(ini.x, __fmul_rn(nrm.x, lift)), __fadd_rn(ini.y, __fmul_rn(nrm.y, lift)),
+                               __fadd_rn(ini.z, __fmul_rn(nrm.z, lift)), hit ? 1.f : 0.f);
+}
+
+__device__ __forceinline__ Frame loc_frame(const LocationParams& lp, const float4* org_valid, int i) {
+    const F3 nrm = f3(lp.vec_norm[3 * i], lp.vec_norm[3 * i + 1], lp.vec_norm[3 * i + 2]);
+    const F3 nth = f3(lp.vec_north[3 * i], lp.vec_north[3 * i + 1], lp.vec_north[3 * i + 2]);
+    Frame f = make_frame(f3(0.f, 0.f, 0.f), nrm, nth, 0.f);
+    const float4 o = org_valid[i];
+    f.org = f3(o.x, o.y, o.z);
+    return f;
+}
+
+// chained search (guess_constant): one lane per location
+__global__ void k_loc_chain(SceneView sv, HorizonParams p, LocationParams lp, const float4* org_valid, Counters* counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int units = 0;
+    if (i < lp.num_loc && org_valid[i].w != 0.f) {
+        const Search s = make_search(sv, p, counters);
+        const Frame f = loc_frame(lp, org_valid, i);
+        OutBuf ob; ob.init(lp.hori + (size_t)i * p.azim_num, false);
+        cell_search<2>(s, f, ob, cnt);
+        units = p.azim_num;
+    }
+    flush_counters(cnt, units, counters);
+}
+
+// independent azimuths (discrete_sampling / binary_search): one lane per
+// (location, azimuth).  With distance output a miss-only azimuth writes -1 and
+// k_loc_dist_fix carries the previous azimuth's distance forward, which is what
+// the reference's function-scope dist_hit does (:526-527, :570-571).
+template <int ALG, bool WD>
+__global__ void k_loc_indep(SceneView sv, HorizonParams p, LocationParams lp, const float4* org_valid, Counters* counters) {
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int units = 0;
+    const long long total = (long long)lp.num_loc * p.azim_num;
+    if (g < total) {
+        const int i = (int)(g / p.azim_num), k = (int)(g - (long long)i * p.azim_num);
+        if (org_valid[i].w != 0.f) {
+            const Search s = make_search(sv, p, counters);
+            const Frame f = loc_frame(lp, org_valid, i);
+            const int top = s.elev_num - 1;
+            float res, dist_hit = -1.0f;
+            if (ALG == 0) {
+                int cur = 0, prev = 0; bool hit = true;
+                while (hit) {
+                    prev = cur; cur = min(cur + 10, top);
+                    if (WD) { float d; hit = cast_closest(s, f, cur, k, cnt, d); if (hit) dist_hit = d; }
+                    else hit = cast_any(s, f, cur, k, cnt);
+                    if (cur == top) hit = false;
+                }
+                res = midpoint(__ldg(s.elev_ang + prev), __ldg(s.elev_ang + cur));
+            } else {
+                bisect<WD>(s, f, k, cnt, res, dist_hit);
+            }
+            lp.hori[g] = res;
+            if (WD) lp.hori_dist[g] = dist_hit;
+            units = 1;
+        }
+    }
+    flush_counters(cnt, units, counters);
+}
+__global__ void k_loc_dist_fix(LocationParams lp, int azim_num, const float4* org_valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= lp.num_loc || org_valid[i].w == 0.f) return;
+    float carry = 0.0f;
+    float* d = lp.hori_dist + (size_t)i * azim_num;
+    for (int k = 0; k < azim_num; ++k) {
+        if (d[k] < 0.0f) d[k] = carry; else carry = d[k];
+    }
+}
+
+}  // namespace
+
+int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
+    if (p.row_end <= p.row_begin || p.dim_in_1 <= 0) return 0;
+    HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
+    const int grid = sm_count() * 8;
+    const SceneView sv = s.view();
+    switch (p.algorithm) {
+        case 0: k_horizon_gridded<0><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+        case 1: k_horizon_gridded<1><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+        default: k_horizon_gridded<2><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+    }
+    HZB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationParams& lp, cudaStream_t st) {
+    if (lp.num_loc <= 0) return 0;
+    float4* d_org = nullptr;
+    HZB_CUDA(cudaMalloc((void**)&d_org, (size_t)lp.num_loc * sizeof(float4)));
+    const SceneView sv = s.view();
+    const int nb_loc = (lp.num_loc + 63) / 64;
+    k_loc_snap<<<nb_loc, 64, 0, st>>>(sv, lp, d_org, s.d_counters);
+    if (p.algorithm == 2) {
+        k_loc_chain<<<(lp.num_loc + 31) / 32, 32, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+    } else {
+        const long long total = (long long)lp.num_loc * p.azim_num;
+        const int nb = (int)((total + 127) / 128);
+        if (p.algorithm == 0) {
+            if (lp.hori_dist_out) k_loc_indep<0, true><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+            else k_loc_indep<0, false><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+        } else {
+            if (lp.hori_dist_out) k_loc_indep<1, true><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+            else k_loc_indep<1, false><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+        }
+        if (lp.hori_dist_out) k_loc_dist_fix<<<nb_loc, 64, 0, st>>>(lp, p.azim_num, d_org);
+    }
+    HZB_CUDA(cudaGetLastError());
+    HZB_CUDA(cudaStreamSynchronize(st));
+    cudaFree(d_org);
+    return 0;
+}
+
+}  // namespace hzb

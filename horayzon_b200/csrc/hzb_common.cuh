@@ -1,0 +1,160 @@
+// hzb_common.cuh -- shared declarations of libhorayzon_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/horayzon_b200.h"
+
+namespace hzb {
+
+// ------------------------------------------------------------------ errors
+void set_error(const std::string& msg);
+#define HZB_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            ::hzb::set_error(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" +   \
+                             __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+            return 1;                                                                      \
+        }                                                                                  \
+    } while (0)
+#define HZB_TRY(expr)              \
+    do {                           \
+        if ((expr) != 0) return 1; \
+    } while (0)
+
+double now_s();
+
+// --------------------------------------------------------------- BVH nodes
+// Binary LBVH node (build-time structure; also the v1 traversal structure):
+// both children's boxes live in the parent.  64 B = four 16-byte loads.
+// child code: >= 0 internal node index; < 0 leaf holding primitive ~code.
+struct __align__(16) Bvh2Node {
+    float lo0[3], hi0[3], lo1[3], hi1[3];
+    int c0, c1;
+    int pad0, pad1;
+};
+static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be 64 bytes");
+
+// 8-wide BVH node with child boxes quantised to 8 bits relative to the node
+// origin (power-of-two scale per axis).  96 B = three 32-byte sectors.
+//   ref[k]: child k: 0xFFFFFFFF empty; bit31 set -> leaf range of sorted
+//           primitives: bits 0..27 first slot, bits 28..30 count-1; else
+//           internal node index.
+struct __align__(32) Bvh8Node {
+    float ox, oy, oz;          // node origin (box minimum)
+    uint8_t ex, ey, ez, nchild;  // biased exponents: scale = 2^(e-127) per axis
+    uint8_t qlo[3][8];         // [axis][child]
+    uint8_t qhi[3][8];
+    uint32_t ref[8];
+};
+static_assert(sizeof(Bvh8Node) == 96, "Bvh8Node must be 96 bytes");
+
+// Device view of a scene: DEM vertices, optional TIN, BVH.
+// Primitive p < num_quads is grid quad (i = p / (W-1), j = p % (W-1)), split
+// along the diagonal (i,j+1)-(i+1,j) into triangles ((i,j),(i,j+1),(i+1,j))
+// and ((i+1,j+1),(i+1,j),(i,j+1)) (reference horizon_comp.cpp:140-151,
+// 163-171, 178-183).  Primitive p >= num_quads is TIN triangle p - num_quads.
+struct SceneView {
+    const float4* vert4;   // [H*W] (x, y, z, 0)
+    const float4* tin4;    // [3*num_tin] (x, y, z, 0)
+    const Bvh2Node* nodes2;
+    const Bvh8Node* nodes8;
+    const uint32_t* prim_ids;  // sorted (Morton) order -> primitive id
+    int H, W;
+    uint32_t num_quads, num_tin, num_prims;
+    uint32_t num_nodes8;
+};
+
+struct Counters {  // device-side accumulators (one struct per scene / terrain)
+    unsigned long long rays, node_visits, prim_tests, units, warp_node_visits, stack_overflow;
+};
+
+// ------------------------------------------------------------------- scene
+struct Scene {
+    int device = 0;
+    int H = 0, W = 0;
+    uint32_t num_quads = 0, num_tin = 0, num_prims = 0, num_nodes8 = 0;
+    float4* d_vert4 = nullptr;
+    float4* d_tin4 = nullptr;
+    Bvh2Node* d_nodes2 = nullptr;
+    Bvh8Node* d_nodes8 = nullptr;
+    uint32_t* d_prim_ids = nullptr;
+    Counters* d_counters = nullptr;
+    unsigned int* d_tile_counter = nullptr;
+    float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, pad = 0.f;
+    double t_h2d = 0, t_build = 0;
+    size_t bvh_bytes = 0;
+    // cached per-call device tables (elevation / azimuth)
+    float* d_tables = nullptr;
+    size_t tables_cap = 0;
+    SceneView view() const {
+        SceneView v;
+        v.vert4 = d_vert4; v.tin4 = d_tin4; v.nodes2 = d_nodes2; v.nodes8 = d_nodes8;
+        v.prim_ids = d_prim_ids; v.H = H; v.W = W; v.num_quads = num_quads; v.num_tin = num_tin;
+        v.num_prims = num_prims; v.num_nodes8 = num_nodes8;
+        return v;
+    }
+};
+
+// bvh_build.cu
+int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const float* vert_simp,
+                           int num_vert_simp, const int32_t* tri_ind_simp, int num_tri_simp);
+void scene_free(Scene& s);
+
+// ------------------------------------------------------ horizon parameters
+struct HorizonTables {  // host copies; built exactly like horizon_comp.cpp:711-731
+    int azim_num = 0, elev_num = 0;
+    float acc = 0, low = 0, up = 0, dist = 0;
+    double step = 0;  // (double)acc / 5.0
+    std::vector<float> azim_sin, azim_cos, elev_ang, elev_sin, elev_cos;
+    void make(int azim_num, float dist_km, float acc_deg, float low_deg);
+};
+
+struct HorizonParams {
+    // tables (device)
+    const float* azim_sin; const float* azim_cos;
+    const float* elev_ang; const float* elev_sin; const float* elev_cos;
+    int azim_num, elev_num;
+    float acc, low, up, dist; double step;
+    int algorithm;  // 0 discrete_sampling, 1 binary_search, 2 guess_constant
+    // inner domain
+    const float* vec_norm; const float* vec_north; const uint8_t* mask;
+    int offset_0, offset_1, dim_in_0, dim_in_1, row_begin, row_end;
+    float hori_fill, ray_org_elev;
+    float* hori;
+};
+
+int parse_algorithm(const char* s);  // -1 if unknown
+int parse_geom_type(const char* s);  // -1 if unknown
+
+// horizon.cu
+int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st);
+struct LocationParams {
+    const float* coords; const float* vec_norm; const float* vec_north; const float* ray_org_elev;
+    float* hori; float* hori_dist; int num_loc; int hori_dist_out;
+};
+int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationParams& lp, cudaStream_t st);
+int upload_tables(Scene& s, const HorizonTables& T, HorizonParams& p, cudaStream_t st);
+
+// shadow.cu
+struct TerrainParams {
+    const float* vec_tilt; const float* vec_norm; const float* surf_enl_fac; const float* elevation;
+    const uint8_t* mask;
+    int offset_0, offset_1, dim_in_0, dim_in_1;
+    float sw_dir_cor_fill, ang_max; int refrac_cor;
+    float dot_prod_min;  // cosf(deg2rad(ang_max)) computed on the host
+    float t_ref, p_ref, lapse, expo;
+};
+int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun_xyz /*host*/, uint8_t* d_out, cudaStream_t st);
+int launch_sw_dir_cor(Scene& s, const TerrainParams& tp, const float* sun_xyz /*host*/, float* d_out, cudaStream_t st);
+
+// topo.cu
+int launch_svf(int kind, const float* d_azim, const float* d_hori, const float* d_tilt, long long cells,
+               int K, float* d_out, cudaStream_t st);
+
+// number of SMs of the current device (cached)
+int sm_count();
+
+}  // namespace hzb

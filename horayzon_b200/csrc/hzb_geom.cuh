@@ -1,0 +1,169 @@
+// hzb_geom.cuh -- ray/triangle and ray/box device code.
+//
+// tri_hit() implements the project's intersection specification (DESIGN.md,
+// "Ray/triangle test"): the Pluecker-coordinate edge test that Embree uses for
+// RTC_SCENE_FLAG_ROBUST scenes (the reference sets that flag at
+// horizon_comp.cpp:106), two-sided, eps = ulp*|U+V+W|, depth from the stable
+// geometric normal, accepted for 0 <= t <= tfar (tnear = 0 at
+// horizon_comp.cpp:252).  Every operation is an explicitly rounded intrinsic
+// (__fsub_rn, __fmul_rn, __fmaf_rn, __fdiv_rn) so that neither -fmad nor the
+// optimiser can change a hit/miss decision.
+#pragma once
+#include "hzb_common.cuh"
+#include <float.h>
+
+namespace hzb {
+
+struct F3 { float x, y, z; };
+
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 sub_rn(F3 a, F3 b) { return f3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ F3 add_rn(F3 a, F3 b) { return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+// cross = (fma(ay,bz,-(az*by)), fma(az,bx,-(ax*bz)), fma(ax,by,-(ay*bx)))
+__device__ __forceinline__ F3 cross_f(F3 a, F3 b) {
+    return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+              __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+// dot = fma(ax,bx, fma(ay,by, az*bz))
+__device__ __forceinline__ float dot_f(F3 a, F3 b) {
+    return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, __fmul_rn(a.z, b.z)));
+}
+
+// Pluecker edge function of edge (a -> b) style term: dot(cross(e, s), D)
+// with e, s prepared by the caller.
+
+// Depth part of the test, shared by both entry points below.
+__device__ __forceinline__ bool tri_depth(F3 v0, F3 e0, F3 e1, F3 e2, F3 D, float tfar, float& t_out) {
+    const float ab_x = __fmul_rn(e0.z, e1.y), ab_y = __fmul_rn(e0.x, e1.z), ab_z = __fmul_rn(e0.y, e1.x);
+    const float bc_x = __fmul_rn(e1.z, e2.y), bc_y = __fmul_rn(e1.x, e2.z), bc_z = __fmul_rn(e1.y, e2.x);
+    const float cab_x = __fmaf_rn(e0.y, e1.z, -ab_x), cab_y = __fmaf_rn(e0.z, e1.x, -ab_y), cab_z = __fmaf_rn(e0.x, e1.y, -ab_z);
+    const float cbc_x = __fmaf_rn(e1.y, e2.z, -bc_x), cbc_y = __fmaf_rn(e1.z, e2.x, -bc_y), cbc_z = __fmaf_rn(e1.x, e2.y, -bc_z);
+    const F3 Ng = f3(fabsf(ab_x) < fabsf(bc_x) ? cab_x : cbc_x, fabsf(ab_y) < fabsf(bc_y) ? cab_y : cbc_y,
+                     fabsf(ab_z) < fabsf(bc_z) ? cab_z : cbc_z);
+    const float dn = dot_f(Ng, D);
+    const float den = __fadd_rn(dn, dn);
+    if (den == 0.0f) return false;
+    const float tn = dot_f(v0, Ng);
+    const float t = __fdiv_rn(__fadd_rn(tn, tn), den);
+    if (!(t >= 0.0f && t <= tfar)) return false;
+    t_out = t;
+    return true;
+}
+
+__device__ __forceinline__ bool tri_hit(F3 p0, F3 p1, F3 p2, F3 O, F3 D, float tfar, float& t_out) {
+    const F3 v0 = sub_rn(p0, O), v1 = sub_rn(p1, O), v2 = sub_rn(p2, O);
+    const F3 e0 = sub_rn(v2, v0), e1 = sub_rn(v0, v1), e2 = sub_rn(v1, v2);
+    const float U = dot_f(cross_f(e0, add_rn(v2, v0)), D);
+    const float V = dot_f(cross_f(e1, add_rn(v0, v1)), D);
+    const float W = dot_f(cross_f(e2, add_rn(v1, v2)), D);
+    const float UVW = __fadd_rn(__fadd_rn(U, V), W);
+    const float eps = __fmul_rn(FLT_EPSILON, fabsf(UVW));
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    if (!((mn >= -eps) || (mx <= eps))) return false;
+    return tri_depth(v0, e0, e1, e2, D, tfar, t_out);
+}
+
+__device__ __forceinline__ F3 ld_vert(const float4* p) {
+    const float4 v = __ldg(p);
+    return f3(v.x, v.y, v.z);
+}
+
+// Test primitive `prim` (grid quad or TIN triangle).  ANY: return on first hit.
+// CLOSEST: shrink tfar to the smallest t.
+template <bool CLOSEST>
+__device__ __forceinline__ bool prim_hit(const SceneView& s, uint32_t prim, F3 O, F3 D, float& tfar) {
+    float t;
+    if (prim < s.num_quads) {
+        const uint32_t wq = (uint32_t)(s.W - 1);
+        const uint32_t i = prim / wq, j = prim - i * wq;
+        const float4* r0 = s.vert4 + (size_t)i * s.W + j;
+        const float4* r1 = r0 + s.W;
+        const F3 p00 = ld_vert(r0), p01 = ld_vert(r0 + 1), p10 = ld_vert(r1), p11 = ld_vert(r1 + 1);
+        bool hit = false;
+        if (tri_hit(p00, p01, p10, O, D, tfar, t)) {
+            if (!CLOSEST) return true;
+            tfar = t; hit = true;
+        }
+        if (tri_hit(p11, p10, p01, O, D, tfar, t)) {
+            if (!CLOSEST) return true;
+            tfar = t; hit = true;
+        }
+        return hit;
+    } else {
+        const float4* q = s.tin4 + 3 * (size_t)(prim - s.num_quads);
+        if (tri_hit(ld_vert(q), ld_vert(q + 1), ld_vert(q + 2), O, D, tfar, t)) { tfar = t; return true; }
+        return false;
+    }
+}
+
+// ------------------------------------------------------------------- boxes
+struct RayInv { float ix, iy, iz; };
+__device__ __forceinline__ float safe_rcp(float d) {
+    if (fabsf(d) < 1e-30f) d = copysignf(1e-30f, d);
+    return 1.0f / d;
+}
+__device__ __forceinline__ RayInv make_inv(F3 D) { RayInv r; r.ix = safe_rcp(D.x); r.iy = safe_rcp(D.y); r.iz = safe_rcp(D.z); return r; }
+
+// Conservative slab test over [0, tfar]: boxes are padded at build time and
+// the exit distance gets a relative slack, so a ray accepted by tri_hit can
+// never be culled by an ancestor box.
+__device__ __forceinline__ bool slab(const float* lo, const float* hi, F3 O, RayInv inv, float tfar, float& tnear) {
+    float ta = (lo[0] - O.x) * inv.ix, tb = (hi[0] - O.x) * inv.ix;
+    float t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+    ta = (lo[1] - O.y) * inv.iy; tb = (hi[1] - O.y) * inv.iy;
+    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+    ta = (lo[2] - O.z) * inv.iz; tb = (hi[2] - O.z) * inv.iz;
+    t0 = fmaxf(t0, fminf(ta, tb)); t1 = fminf(t1, fmaxf(ta, tb));
+    t0 = fmaxf(t0, 0.0f); t1 = fminf(t1, tfar);
+    tnear = t0;
+    return t0 <= t1 * 1.000001f;
+}
+
+struct LaneCounters { unsigned int rays, nodes, prims; };
+
+// --------------------------------------------------- BVH2 per-thread trace
+constexpr int HZB_STACK2 = 96;
+
+template <bool CLOSEST>
+__device__ bool trace_bvh2(const SceneView& s, F3 O, F3 D, float& tfar, LaneCounters& cnt, unsigned int* overflow) {
+    const RayInv inv = make_inv(D);
+    int stack[HZB_STACK2];
+    int sp = 0;
+    int node = 0;
+    bool any = false;
+    while (true) {
+        const float4* np = reinterpret_cast<const float4*>(s.nodes2 + node);
+        const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+        cnt.nodes++;
+        const float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
+        const float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
+        const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+        float tn0, tn1;
+        bool h0 = slab(lo0, hi0, O, inv, tfar, tn0);
+        bool h1 = slab(lo1, hi1, O, inv, tfar, tn1);
+        if (h0 && c0 < 0) {
+            cnt.prims++;
+            if (prim_hit<CLOSEST>(s, (uint32_t)(~c0), O, D, tfar)) { if (!CLOSEST) return true; any = true; }
+            h0 = false;
+        }
+        if (h1 && c1 < 0) {
+            cnt.prims++;
+            if (prim_hit<CLOSEST>(s, (uint32_t)(~c1), O, D, tfar)) { if (!CLOSEST) return true; any = true; }
+            h1 = false;
+        }
+        if (h0 && h1) {
+            int nearc = c0, farc = c1;
+            if (tn1 < tn0) { nearc = c1; farc = c0; }
+            if (sp < HZB_STACK2) stack[sp++] = farc; else atomicAdd(overflow, 1u);
+            node = nearc;
+        } else if (h0) node = c0;
+        else if (h1) node = c1;
+        else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    return any;
+}
+
+}  // namespace hzb

@@ -1,0 +1,255 @@
+# cython: language_level=3
+"""Horizon computation -- drop-in for ``horayzon.horizon``.
+
+Same Python signatures, defaults, validation and return values as the
+reference wrapper (``horayzon/horizon.pyx:29-197`` and ``:218-370``), but the
+work is done by the C-ABI CUDA library ``libhorayzon_b200.so``
+(``include/horayzon_b200.h``) instead of Embree/TBB
+(``horayzon/horizon_comp.cpp``).  There is no CPU fallback: without a CUDA
+device the calls raise ``RuntimeError``.
+"""
+cimport numpy as np
+import numpy as np
+from libc.stdint cimport int32_t, uint8_t
+
+np.import_array()
+
+cdef extern from "horayzon_b200.h":
+    const char* hzb_last_error()
+    int hzb_horizon_gridded(
+        const float* vert_grid, int dem_dim_0, int dem_dim_1,
+        const float* vec_norm, const float* vec_north,
+        int offset_0, int offset_1, float* hori_buffer,
+        int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+        float hori_acc, const char* ray_algorithm, const char* geom_type,
+        const float* vert_simp, int num_vert_simp,
+        const int32_t* tri_ind_simp, int num_tri_simp,
+        float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+        float ray_org_elev) nogil
+    int hzb_horizon_locations(
+        const float* vert_grid, int dem_dim_0, int dem_dim_1,
+        const float* coords, const float* vec_norm, const float* vec_north,
+        float* hori_buffer, float* hori_dist_buffer, int num_loc,
+        int azim_num, float dist_search, float hori_acc,
+        const char* ray_algorithm, const char* geom_type,
+        float elev_ang_low_lim, const float* ray_org_elev,
+        int hori_dist_out) nogil
+
+_ALGORITHMS = ("discrete_sampling", "binary_search", "guess_constant")
+_GEOM_TYPES = ("triangle", "quad", "grid")
+
+
+def _azimuth_axis(int azim_num):
+    # float32 azimuth of every sector, as horizon.pyx:190-195 rebuilds it
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] azim = np.empty(azim_num, dtype=np.float32)
+    cdef int i
+    for i in range(azim_num):
+        azim[i] = ((2 * np.pi) / azim_num * i)
+    return azim
+
+
+def _raise_native():
+    raise RuntimeError("horayzon_b200: " + hzb_last_error().decode("utf-8", "replace"))
+
+
+def horizon_gridded(
+        np.ndarray[np.float32_t, ndim = 1] vert_grid,
+        int dem_dim_0, int dem_dim_1,
+        np.ndarray[np.float32_t, ndim = 3] vec_norm,
+        np.ndarray[np.float32_t, ndim = 3] vec_north,
+        int offset_0, int offset_1,
+        float dist_search,
+        int azim_num=360,
+        float hori_acc=0.25,
+        str ray_algorithm="guess_constant",
+        str geom_type="grid",
+        np.ndarray[np.float32_t, ndim = 1]
+        vert_simp=np.array([0.0, 0.0, 0.0, 0.0], dtype=np.float32),
+        int num_vert_simp=1,
+        np.ndarray[np.int32_t, ndim = 1]
+        tri_ind_simp=np.array([0, 0, 0, 0], dtype=np.int32),
+        int num_tri_simp=1,
+        float elev_ang_low_lim = -15.0,
+        np.ndarray[np.uint8_t, ndim = 2] mask=None,
+        float hori_fill=0.0,
+        float ray_org_elev=0.01):
+    """Horizon of every unmasked cell of a gridded inner domain.
+
+    Arguments, units and defaults are those of ``horayzon.horizon.horizon_gridded``
+    (``horizon.pyx:29-106``): ``vert_grid`` flat float32 vertex buffer [m],
+    ``vec_norm`` / ``vec_north`` float32 (y, x, 3), ``dist_search`` [km],
+    ``hori_acc`` and ``elev_ang_low_lim`` [degree], ``hori_fill`` [radian],
+    ``ray_org_elev`` [m].  ``geom_type`` is accepted for compatibility; the three
+    Embree geometry types describe the same surface and share one GPU BVH.
+
+    Returns ``(hori_buffer, azim)``: float32 (y, x, azim_num) horizon [radian]
+    and float32 (azim_num,) azimuth [radian].
+    """
+    # argument checks, in the reference's order and wording (horizon.pyx:109-156)
+    if len(vert_grid) < (dem_dim_0 * dem_dim_1 * 3):
+        raise ValueError("inconsistency between input arguments vert_grid, "
+                         "dem_dim_0 and dem_dim_1")
+    if ((offset_0 + vec_norm.shape[0] > dem_dim_0)
+            or (offset_1 + vec_norm.shape[1] > dem_dim_1)):
+        raise ValueError("inconsistency between input arguments dem_dim_0, "
+                         "dem_dim_1, offset_0, offset_1 and vec_norm")
+    if ((vec_norm.ndim != 3) or (vec_north.ndim != 3)
+            or (vec_norm.shape[0] != vec_north.shape[0])
+            or (vec_norm.shape[1] != vec_north.shape[1])
+            or (vec_norm.shape[2] != vec_north.shape[2])):
+        raise ValueError("dimension (lengths) of vec_norm and/or vec_north "
+                         "is/are erroneous")
+    if ray_algorithm not in _ALGORITHMS:
+        raise ValueError("invalid input argument for ray_algorithm")
+    if geom_type not in _GEOM_TYPES:
+        raise ValueError("invalid input argument for geom_type")
+    if len(vert_simp) < (num_vert_simp * 3):
+        raise ValueError("inconsistency between input arguments vert_simp "
+                         "and num_vert_simp")
+    if len(tri_ind_simp) < (num_tri_simp * 3):
+        raise ValueError("inconsistency between input arguments tri_ind_simp "
+                         "and num_tri_simp")
+    if tri_ind_simp.max() > (num_vert_simp - 1):
+        raise ValueError("triangle indices of simplified outer domain exceed "
+                         "number of vertices")
+    if hori_acc > 10.0:
+        raise ValueError("limit of hori_acc (10 degree) is exceeded")
+    if mask is None:
+        mask = np.ones((vec_norm.shape[0], vec_norm.shape[1]), dtype=np.uint8)
+    if (mask.shape[0] != vec_norm.shape[0]) \
+            or (mask.shape[1] != vec_norm.shape[1]):
+        raise ValueError("shape of mask is inconsistent with other input")
+    if mask.dtype != "uint8":
+        raise TypeError("data type of mask must be 'uint8'")
+    if ray_org_elev < 0.005:
+        raise TypeError("minimal allowed value for 'ray_org_elev' is 0.005 m")
+    if (dem_dim_0 > 32767) or (dem_dim_1 > 32767):
+        raise ValueError("maximal allowed input length for dem_dim_0 and "
+                         "dem_dim_1 is 32'767")
+    if vert_simp.nbytes > (16.0 * 10 ** 9):
+        raise ValueError("vertex buffer vert_simp is larger than 16 GB")
+
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] vg = np.ascontiguousarray(vert_grid)
+    cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] vn = np.ascontiguousarray(vec_norm)
+    cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] vno = np.ascontiguousarray(vec_north)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] vs = np.ascontiguousarray(vert_simp)
+    cdef np.ndarray[np.int32_t, ndim = 1, mode = "c"] ti = np.ascontiguousarray(tri_ind_simp)
+    cdef np.ndarray[np.uint8_t, ndim = 2, mode = "c"] mk = np.ascontiguousarray(mask)
+    cdef bytes alg_b = ray_algorithm.encode("utf-8")
+    cdef bytes geom_b = geom_type.encode("utf-8")
+    cdef const char* alg_c = alg_b
+    cdef const char* geom_c = geom_b
+    cdef int ny = vn.shape[0], nx = vn.shape[1]
+
+    cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] hori_buffer = \
+        np.empty((ny, nx, azim_num), dtype=np.float32)
+    hori_buffer.fill(np.nan)  # horizon.pyx:170-173
+    cdef int rc = 0
+    if ny > 0 and nx > 0:
+        with nogil:
+            rc = hzb_horizon_gridded(
+                <const float*> vg.data, dem_dim_0, dem_dim_1,
+                <const float*> vn.data, <const float*> vno.data,
+                offset_0, offset_1, <float*> hori_buffer.data, ny, nx,
+                azim_num, dist_search, hori_acc, alg_c, geom_c,
+                <const float*> vs.data, num_vert_simp,
+                <const int32_t*> ti.data, num_tri_simp,
+                elev_ang_low_lim, <const uint8_t*> mk.data, hori_fill,
+                ray_org_elev)
+    if rc != 0:
+        _raise_native()
+    return hori_buffer, _azimuth_axis(azim_num)
+
+
+def horizon_locations(
+        np.ndarray[np.float32_t, ndim = 1] vert_grid,
+        int dem_dim_0, int dem_dim_1,
+        np.ndarray[np.float32_t, ndim = 2] coords,
+        np.ndarray[np.float32_t, ndim = 2] vec_norm,
+        np.ndarray[np.float32_t, ndim = 2] vec_north,
+        float dist_search,
+        int azim_num=360,
+        float hori_acc=0.25,
+        str ray_algorithm="binary_search",
+        str geom_type="grid",
+        float elev_ang_low_lim = -89.98,
+        np.ndarray[np.float32_t, ndim = 1] ray_org_elev \
+        = np.array([0.01], dtype=np.float32),
+        bint hori_dist_out=False):
+    """Horizon (and optionally distance to the horizon) at arbitrary locations.
+
+    Arguments, units and defaults are those of
+    ``horayzon.horizon.horizon_locations`` (``horizon.pyx:218-279``).  Locations
+    whose normal line does not meet the DEM surface within 100 km keep NaN.
+
+    Returns ``(hori_buffer, azim)`` or, with ``hori_dist_out=True``,
+    ``(hori_buffer, hori_dist_buffer, azim)``.
+    """
+    # argument checks, in the reference's order and wording (horizon.pyx:282-313)
+    if len(vert_grid) < (dem_dim_0 * dem_dim_1 * 3):
+        raise ValueError("inconsistency between input arguments vert_grid, "
+                         "dem_dim_0 and dem_dim_1")
+    if ((coords.ndim != 2) or (coords.shape[0] != vec_norm.shape[0])
+            or (coords.shape[1] !=3)):
+        raise ValueError("'number of dimensions and/or dimension "
+                         + "length(s) of 'coords' incorrect")
+    if ((vec_norm.ndim != 2) or (vec_north.ndim != 2)
+            or (vec_norm.shape[0] != vec_north.shape[0])
+            or (vec_norm.shape[1] != vec_north.shape[1])):
+        raise ValueError("dimension (lengths) of vec_norm and/or vec_north "
+                         "is/are erroneous")
+    if ray_algorithm not in _ALGORITHMS:
+        raise ValueError("invalid input argument for ray_algorithm")
+    if geom_type not in _GEOM_TYPES:
+        raise ValueError("invalid input argument for geom_type")
+    if hori_acc > 10.0:
+        raise ValueError("limit of hori_acc (10 degree) is exceeded")
+    if (len(ray_org_elev) != 1) and (len(ray_org_elev) != coords.shape[0]):
+        raise ValueError("length of array 'ray_org_elev' must be either "
+                         + "one or correspond to the number of locations")
+    if ray_org_elev.min() < 0.005:
+        raise TypeError("minimal allowed value for 'ray_org_elev' is 0.005 m")
+    if hori_dist_out and (ray_algorithm == "guess_constant"):
+        raise TypeError("horizon detection algorithm 'guess_constant' not "
+                        + "implemented for horizon distance computation")
+    if (dem_dim_0 > 32767) or (dem_dim_1 > 32767):
+        raise ValueError("maximal allowed input length for dem_dim_0 and "
+                         "dem_dim_1 is 32'767")
+
+    if len(ray_org_elev) != coords.shape[0]:
+        ray_org_elev = np.repeat(ray_org_elev, coords.shape[0])
+
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] vg = np.ascontiguousarray(vert_grid)
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] co = np.ascontiguousarray(coords)
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] vn = np.ascontiguousarray(vec_norm)
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] vno = np.ascontiguousarray(vec_north)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] roe = np.ascontiguousarray(ray_org_elev)
+    cdef bytes alg_b = ray_algorithm.encode("utf-8")
+    cdef bytes geom_b = geom_type.encode("utf-8")
+    cdef const char* alg_c = alg_b
+    cdef const char* geom_c = geom_b
+    cdef int num_loc = vn.shape[0]
+    cdef int dist_flag = 1 if hori_dist_out else 0
+
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] hori_buffer = \
+        np.empty((num_loc, azim_num), dtype=np.float32)
+    hori_buffer.fill(np.nan)
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] hori_dist_buffer = \
+        np.empty((num_loc if hori_dist_out else 1, azim_num), dtype=np.float32)
+    hori_dist_buffer.fill(np.nan)  # 'dummy length' 1 without distance output (horizon.pyx:336-344)
+
+    cdef int rc = 0
+    if num_loc > 0:
+        with nogil:
+            rc = hzb_horizon_locations(
+                <const float*> vg.data, dem_dim_0, dem_dim_1,
+                <const float*> co.data, <const float*> vn.data,
+                <const float*> vno.data, <float*> hori_buffer.data,
+                <float*> hori_dist_buffer.data, num_loc, azim_num,
+                dist_search, hori_acc, alg_c, geom_c, elev_ang_low_lim,
+                <const float*> roe.data, dist_flag)
+    if rc != 0:
+        _raise_native()
+    if hori_dist_out:
+        return hori_buffer, hori_dist_buffer, _azimuth_axis(azim_num)
+    return hori_buffer, _azimuth_axis(azim_num)

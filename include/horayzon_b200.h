@@ -1,0 +1,180 @@
+/* horayzon_b200.h -- C ABI of libhorayzon_b200.so
+ *
+ * The drop-in boundary for HORAYZON's horizon / shadow / sky-view hot path.
+ * Every entry point replaces one native interface of the reference (cited as
+ * file:line relative to the reference's horayzon/ directory) and keeps its
+ * argument order, units and meaning.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - All functions returning int return 0 on success; on failure the message
+ *     is available from hzb_last_error() (thread-local).  The reference's
+ *     native functions return void and print Embree errors with printf
+ *     (horizon_comp.cpp:74-76); status codes replace that.
+ *   - "host tier" functions take HOST pointers, exactly like the reference, and
+ *     perform H2D copy, on-device BVH build, kernels and D2H copy inside the
+ *     call.  Buffers are borrowed for the duration of the call only.
+ *   - "resident tier" functions (suffix _dev, and hzb_scene_*) are additive:
+ *     they take DEVICE pointers and a cudaStream_t (passed as void*) so that a
+ *     caller can keep DEM, BVH and outputs in HBM, shard rows over GPUs and
+ *     overlap work.  They have no counterpart in the reference.
+ *   - Units at the boundary are the reference's (horizon_comp.cpp:667-670):
+ *     dist_search [km], hori_acc / elev_ang_low_lim [degree], hori_fill
+ *     [radian], ray_org_elev [m]; outputs in radian.
+ *   - There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with a non-zero status.
+ */
+#ifndef HORAYZON_B200_H
+#define HORAYZON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ status */
+const char* hzb_last_error(void);
+int hzb_device_count(void);       /* number of visible CUDA devices (0 if none) */
+const char* hzb_version(void);
+
+/* Work counters and timings of the most recent host-tier call on this thread.
+ * rays = casts performed, the reference's own work counter "Number of rays
+ * shot" (horizon_comp.cpp:739,799-810).  Seconds are wall-clock around
+ * device-synchronised phases, mirroring the reference's prints "BVH build
+ * time" (:225-227), "Ray tracing time" (:805), "Total run time" (:818). */
+typedef struct hzb_stats {
+    unsigned long long rays;        /* ray casts                               */
+    unsigned long long node_visits; /* BVH nodes fetched (per ray; per packet for warp_node_visits) */
+    unsigned long long prim_tests;  /* leaf primitives (quads / TIN triangles) tested */
+    unsigned long long units;       /* unmasked cells x azimuths (or cells for shadow) */
+    unsigned long long warp_node_visits; /* packet traversal: nodes fetched per warp */
+    double t_h2d, t_build, t_trace, t_d2h, t_total;
+    unsigned long long num_prims;   /* BVH primitives (grid quads + TIN triangles) */
+    unsigned long long num_nodes;   /* wide-BVH nodes */
+    unsigned long long bvh_bytes;   /* bytes of the traversal structure in HBM */
+} hzb_stats;
+int hzb_get_stats(hzb_stats* out);
+
+/* --------------------------------------------------------------- host tier */
+
+/* Replaces horizon_gridded_comp (horizon_comp.h:8-20, horizon_comp.cpp:629-822).
+ * hori_buffer: float32 [dim_in_0][dim_in_1][azim_num], radians. */
+int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                        const float* vec_norm, const float* vec_north,
+                        int offset_0, int offset_1,
+                        float* hori_buffer,
+                        int dim_in_0, int dim_in_1,
+                        int azim_num, float dist_search,
+                        float hori_acc, const char* ray_algorithm, const char* geom_type,
+                        const float* vert_simp, int num_vert_simp,
+                        const int32_t* tri_ind_simp, int num_tri_simp,
+                        float elev_ang_low_lim,
+                        const uint8_t* mask, float hori_fill,
+                        float ray_org_elev);
+
+/* Replaces horizon_locations_comp (horizon_comp.h:23-34, horizon_comp.cpp:828-1094).
+ * hori_buffer / hori_dist_buffer: float32 [num_loc][azim_num]; locations whose
+ * normal line misses the surface are left untouched (the wrapper pre-fills NaN). */
+int hzb_horizon_locations(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                          const float* coords,
+                          const float* vec_norm, const float* vec_north,
+                          float* hori_buffer,
+                          float* hori_dist_buffer,
+                          int num_loc,
+                          int azim_num, float dist_search,
+                          float hori_acc, const char* ray_algorithm, const char* geom_type,
+                          float elev_ang_low_lim,
+                          const float* ray_org_elev,
+                          int hori_dist_out);
+
+/* Replaces class shapes::CppTerrain (shadow_comp.h:3-40, shadow_comp.cpp:304-605).
+ * Unlike the reference, initialise COPIES every input to the device, so the
+ * caller may free its arrays afterwards (shadow_comp.cpp:332-346 keeps raw
+ * pointers). */
+typedef struct hzb_terrain hzb_terrain;
+hzb_terrain* hzb_terrain_create(void);                       /* CppTerrain()  :304-308 */
+void hzb_terrain_destroy(hzb_terrain* t);                    /* ~CppTerrain() :310-316 */
+int hzb_terrain_initialise(hzb_terrain* t,                   /* ::initialise  :318-380 */
+                           const float* vert_grid,
+                           int dem_dim_0, int dem_dim_1,
+                           int offset_0, int offset_1,
+                           const float* vec_tilt,
+                           const float* vec_norm,
+                           int dim_in_0, int dim_in_1,
+                           const float* surf_enl_fac,
+                           const float* elevation,
+                           const uint8_t* mask,
+                           const char* geom_type,
+                           float sw_dir_cor_fill,
+                           float ang_max,
+                           int refrac_cor);
+/* ::shadow :386-491 -- codes 0 lit, 1 self-shaded, 2 terrain-shaded, 3 masked */
+int hzb_terrain_shadow(hzb_terrain* t, const float* sun_position, uint8_t* shadow_buffer);
+/* ::sw_dir_cor :495-605 */
+int hzb_terrain_sw_dir_cor(hzb_terrain* t, const float* sun_position, float* sw_dir_cor_buffer);
+/* additive: n_sun positions in one call; outputs [n_sun][dim_in_0][dim_in_1] */
+int hzb_terrain_shadow_batch(hzb_terrain* t, const float* sun_positions, int n_sun,
+                             uint8_t* shadow_buffer);
+int hzb_terrain_sw_dir_cor_batch(hzb_terrain* t, const float* sun_positions, int n_sun,
+                                 float* sw_dir_cor_buffer);
+
+/* Replace _sky_view_factor_cy / _visible_sky_fraction_cy / _topographic_openness_cy
+ * (topo_param.pyx:412-460, 499-543, 577-603).  hori: [ny][nx][K], vec_tilt:
+ * [ny][nx][3] (local frame), out: [ny][nx]. */
+int hzb_sky_view_factor(const float* azim, const float* hori, const float* vec_tilt,
+                        int ny, int nx, int K, float* out);
+int hzb_visible_sky_fraction(const float* azim, const float* hori, const float* vec_tilt,
+                             int ny, int nx, int K, float* out);
+int hzb_topographic_openness(const float* azim, const float* hori,
+                             int ny, int nx, int K, float* out);
+
+/* ----------------------------------------------------------- resident tier */
+
+/* A scene = DEM vertices (+ optional TIN) and their BVH, resident on `device`.
+ * Replaces initializeDevice + initializeScene (horizon_comp.cpp:79-86, 101-231):
+ * Morton codes + radix sort + LBVH + wide-BVH collapse, all on the device.
+ * vert_grid etc. are HOST pointers (copied). */
+typedef struct hzb_scene hzb_scene;
+hzb_scene* hzb_scene_create(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                            const float* vert_simp, int num_vert_simp,
+                            const int32_t* tri_ind_simp, int num_tri_simp,
+                            int device);
+void hzb_scene_destroy(hzb_scene* s);
+int hzb_scene_stats(const hzb_scene* s, hzb_stats* out);
+
+/* Horizon for rows [row_begin, row_end) of the inner domain.  d_* are DEVICE
+ * pointers to the FULL inner-domain arrays ([dim_in_0][dim_in_1][...]); only
+ * the selected rows are read / written.  stream is a cudaStream_t (NULL = the
+ * legacy default stream).  Asynchronous; counters accumulate into the scene
+ * and are read (after synchronising) with hzb_scene_stats. */
+int hzb_horizon_gridded_dev(hzb_scene* s,
+                            const float* d_vec_norm, const float* d_vec_north,
+                            const uint8_t* d_mask,
+                            int offset_0, int offset_1,
+                            int dim_in_0, int dim_in_1,
+                            int row_begin, int row_end,
+                            int azim_num, float dist_search, float hori_acc,
+                            const char* ray_algorithm, float elev_ang_low_lim,
+                            float hori_fill, float ray_org_elev,
+                            float* d_hori_buffer, void* stream);
+
+/* Device-pointer variants of the azimuthal integrals (same layouts). */
+int hzb_sky_view_factor_dev(const float* d_azim, const float* d_hori, const float* d_vec_tilt,
+                            long long num_cells, int K, float* d_out, void* stream);
+int hzb_visible_sky_fraction_dev(const float* d_azim, const float* d_hori,
+                                 const float* d_vec_tilt, long long num_cells, int K,
+                                 float* d_out, void* stream);
+int hzb_topographic_openness_dev(const float* d_azim, const float* d_hori,
+                                 long long num_cells, int K, float* d_out, void* stream);
+
+/* Shadow / sw_dir_cor with a DEVICE output buffer (terrain already resident). */
+int hzb_terrain_shadow_dev(hzb_terrain* t, const float* sun_position_host,
+                           uint8_t* d_shadow_buffer, void* stream);
+int hzb_terrain_sw_dir_cor_dev(hzb_terrain* t, const float* sun_position_host,
+                               float* d_sw_dir_cor_buffer, void* stream);
+int hzb_terrain_stats(const hzb_terrain* t, hzb_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HORAYZON_B200_H */

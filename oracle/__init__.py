@@ -1,0 +1,208 @@
+"""CPU oracle -- TEST INFRASTRUCTURE ONLY (see oracle/hzb_oracle.cpp header).
+
+ctypes front-end for ``oracle/libhzb_oracle.so`` with the call shapes of the
+reference's Python API (``horizon.pyx:29-197, 218-370``; ``shadow.pyx:17-200``;
+``topo_param.pyx:377-603``).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU-baseline legs may import this package; the product
+(``horayzon_b200``) never does.
+
+Parity status: ray path "parity unpinned" (Embree absent, reference has no
+golden vectors); SVF/VSF/openness pinned by ``tests/golden/`` vectors generated
+from the reference's own compiled ``topo_param.pyx``.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhzb_oracle.so")
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force=False):
+    """Compile the oracle (gcc) if the shared object is missing or stale."""
+    src = os.path.join(_HERE, "hzb_oracle.cpp")
+    if (force or not os.path.exists(_SO)
+            or os.path.getmtime(_SO) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "libhzb_oracle.so"],
+                              stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_SO)
+        _lib.orc_last_error.restype = ctypes.c_char_p
+        _lib.orc_terrain_create.restype = ctypes.c_void_p
+        _lib.orc_terrain_destroy.argtypes = [ctypes.c_void_p]
+    return _lib
+
+
+def _p(a, typ):
+    return a.ctypes.data_as(typ)
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def last_timing():
+    """(BVH build seconds, ray tracing seconds) of the last oracle call."""
+    b, t = ctypes.c_double(), ctypes.c_double()
+    lib().orc_last_timing(ctypes.byref(b), ctypes.byref(t))
+    return b.value, t.value
+
+
+def tables(azim_num, dist_search, hori_acc, elev_ang_low_lim):
+    """Elevation / azimuth tables as horizon_comp.cpp:711-731 builds them."""
+    L = lib()
+    n = L.orc_tables(int(azim_num), ctypes.c_float(dist_search), ctypes.c_float(hori_acc),
+                     ctypes.c_float(elev_ang_low_lim), 0, None, None, None, None, None)
+    ea, es, ec = (np.empty(n, np.float32) for _ in range(3))
+    asn, acs = (np.empty(azim_num, np.float32) for _ in range(2))
+    L.orc_tables(int(azim_num), ctypes.c_float(dist_search), ctypes.c_float(hori_acc),
+                 ctypes.c_float(elev_ang_low_lim), n, _p(ea, _f32p), _p(es, _f32p), _p(ec, _f32p),
+                 _p(asn, _f32p), _p(acs, _f32p))
+    return dict(elev_ang=ea, elev_sin=es, elev_cos=ec, azim_sin=asn, azim_cos=acs)
+
+
+def _azim(azim_num):
+    azim = np.empty(azim_num, dtype=np.float32)
+    for i in range(azim_num):
+        azim[i] = ((2 * np.pi) / azim_num * i)
+    return azim
+
+
+def horizon_gridded(vert_grid, dem_dim_0, dem_dim_1, vec_norm, vec_north, offset_0, offset_1,
+                    dist_search, azim_num=360, hori_acc=0.25, ray_algorithm="guess_constant",
+                    geom_type="grid", vert_simp=None, num_vert_simp=1, tri_ind_simp=None,
+                    num_tri_simp=1, elev_ang_low_lim=-15.0, mask=None, hori_fill=0.0,
+                    ray_org_elev=0.01, brute_force=False, return_rays=False):
+    """Oracle twin of ``horizon.horizon_gridded`` (horizon.pyx:29-197)."""
+    if vert_simp is None:
+        vert_simp = np.zeros(4, np.float32)
+    if tri_ind_simp is None:
+        tri_ind_simp = np.zeros(4, np.int32)
+    if mask is None:
+        mask = np.ones(vec_norm.shape[:2], np.uint8)
+    vert_grid = np.ascontiguousarray(vert_grid, np.float32)
+    vec_norm = np.ascontiguousarray(vec_norm, np.float32)
+    vec_north = np.ascontiguousarray(vec_north, np.float32)
+    vert_simp = np.ascontiguousarray(vert_simp, np.float32)
+    tri_ind_simp = np.ascontiguousarray(tri_ind_simp, np.int32)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    ny, nx = vec_norm.shape[:2]
+    hori = np.full((ny, nx, azim_num), np.nan, np.float32)
+    rays = ctypes.c_ulonglong(0)
+    _check(lib().orc_horizon_gridded(
+        _p(vert_grid, _f32p), int(dem_dim_0), int(dem_dim_1), _p(vec_norm, _f32p),
+        _p(vec_north, _f32p), int(offset_0), int(offset_1), _p(hori, _f32p), ny, nx,
+        int(azim_num), ctypes.c_float(dist_search), ctypes.c_float(hori_acc),
+        ray_algorithm.encode(), geom_type.encode(), _p(vert_simp, _f32p), int(num_vert_simp),
+        _p(tri_ind_simp, _i32p), int(num_tri_simp), ctypes.c_float(elev_ang_low_lim),
+        _p(mask, _u8p), ctypes.c_float(hori_fill), ctypes.c_float(ray_org_elev),
+        int(bool(brute_force)), ctypes.byref(rays)))
+    if return_rays:
+        return hori, _azim(azim_num), rays.value
+    return hori, _azim(azim_num)
+
+
+def horizon_locations(vert_grid, dem_dim_0, dem_dim_1, coords, vec_norm, vec_north, dist_search,
+                      azim_num=360, hori_acc=0.25, ray_algorithm="binary_search", geom_type="grid",
+                      elev_ang_low_lim=-89.98, ray_org_elev=None, hori_dist_out=False,
+                      brute_force=False):
+    """Oracle twin of ``horizon.horizon_locations`` (horizon.pyx:218-370)."""
+    if ray_org_elev is None:
+        ray_org_elev = np.array([0.01], np.float32)
+    n = coords.shape[0]
+    if len(ray_org_elev) != n:
+        ray_org_elev = np.repeat(ray_org_elev, n)
+    vert_grid = np.ascontiguousarray(vert_grid, np.float32)
+    coords = np.ascontiguousarray(coords, np.float32)
+    vec_norm = np.ascontiguousarray(vec_norm, np.float32)
+    vec_north = np.ascontiguousarray(vec_north, np.float32)
+    ray_org_elev = np.ascontiguousarray(ray_org_elev, np.float32)
+    hori = np.full((n, azim_num), np.nan, np.float32)
+    dist = np.full((n if hori_dist_out else 1, azim_num), np.nan, np.float32)
+    _check(lib().orc_horizon_locations(
+        _p(vert_grid, _f32p), int(dem_dim_0), int(dem_dim_1), _p(coords, _f32p),
+        _p(vec_norm, _f32p), _p(vec_north, _f32p), _p(hori, _f32p), _p(dist, _f32p), n,
+        int(azim_num), ctypes.c_float(dist_search), ctypes.c_float(hori_acc),
+        ray_algorithm.encode(), geom_type.encode(), ctypes.c_float(elev_ang_low_lim),
+        _p(ray_org_elev, _f32p), int(bool(hori_dist_out)), int(bool(brute_force)), None))
+    if hori_dist_out:
+        return hori, dist, _azim(azim_num)
+    return hori, _azim(azim_num)
+
+
+class Terrain:
+    """Oracle twin of ``shadow.Terrain`` (shadow.pyx:17-200)."""
+
+    def __init__(self):
+        self._h = ctypes.c_void_p(lib().orc_terrain_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_terrain_destroy(self._h)
+            self._h = None
+
+    def initialise(self, vert_grid, dem_dim_0, dem_dim_1, offset_0, offset_1, vec_tilt, vec_norm,
+                   surf_enl_fac, elevation, mask, geom_type="grid", sw_dir_cor_fill=np.nan,
+                   ang_max=89.0, refrac_cor=False, brute_force=False):
+        a = [np.ascontiguousarray(x, np.float32) for x in
+             (vert_grid, vec_tilt, vec_norm, surf_enl_fac, elevation)]
+        mask = np.ascontiguousarray(mask, np.uint8)
+        _check(lib().orc_terrain_initialise(
+            self._h, _p(a[0], _f32p), int(dem_dim_0), int(dem_dim_1), int(offset_0), int(offset_1),
+            _p(a[1], _f32p), _p(a[2], _f32p), vec_tilt.shape[0], vec_tilt.shape[1],
+            _p(a[3], _f32p), _p(a[4], _f32p), _p(mask, _u8p), geom_type.encode(),
+            ctypes.c_float(sw_dir_cor_fill), ctypes.c_float(ang_max), int(bool(refrac_cor)),
+            int(bool(brute_force))))
+
+    def shadow(self, sun_position, shadow_buffer):
+        sp = np.ascontiguousarray(sun_position, np.float32)
+        _check(lib().orc_terrain_shadow(self._h, _p(sp, _f32p), _p(shadow_buffer, _u8p)))
+
+    def sw_dir_cor(self, sun_position, sw_dir_cor_buffer):
+        sp = np.ascontiguousarray(sun_position, np.float32)
+        _check(lib().orc_terrain_sw_dir_cor(self._h, _p(sp, _f32p), _p(sw_dir_cor_buffer, _f32p)))
+
+
+def _integral(fn, azim, hori, vec_tilt):
+    azim = np.ascontiguousarray(azim, np.float32)
+    hori = np.ascontiguousarray(hori, np.float32)
+    ny, nx, K = hori.shape
+    out = np.empty((ny, nx), np.float32)
+    if vec_tilt is None:
+        _check(fn(_p(azim, _f32p), _p(hori, _f32p), ny, nx, K, _p(out, _f32p)))
+    else:
+        vec_tilt = np.ascontiguousarray(vec_tilt, np.float32)
+        _check(fn(_p(azim, _f32p), _p(hori, _f32p), _p(vec_tilt, _f32p), ny, nx, K, _p(out, _f32p)))
+    return out
+
+
+def sky_view_factor(azim, hori, vec_tilt):
+    return _integral(lib().orc_sky_view_factor, azim, hori, vec_tilt)
+
+
+def visible_sky_fraction(azim, hori, vec_tilt):
+    return _integral(lib().orc_visible_sky_fraction, azim, hori, vec_tilt)
+
+
+def topographic_openness(azim, hori):
+    return _integral(lib().orc_topographic_openness, azim, hori, None)

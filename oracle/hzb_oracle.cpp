@@ -1,0 +1,729 @@
+// hzb_oracle.cpp -- CPU ORACLE. TEST INFRASTRUCTURE ONLY.
+//
+// A CPU restatement (C++17 + OpenMP) of the algorithms on HORAYZON's horizon /
+// shadow / sky-view hot path.  It exists to CHECK the CUDA product in
+// horayzon_b200/csrc; nothing in the product may call, link or import it.  Only
+// tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs use it.
+//
+// PARITY STATUS: "parity unpinned" for the ray path.  The reference delegates
+// BVH construction, traversal and the ray/triangle test to Intel Embree 4
+// (un-vendored, minor version unpinned: reference setup.py:41,
+// horizon_comp.cpp:5) and ships no tests, golden vectors or recorded outputs.
+// Embree is not installable here, so the ray path below is pinned only by
+// analytic known-answer cases (tests/test_oracle_kat.py).  The SVF / VSF /
+// openness integrals ARE pinned: against golden vectors generated from the
+// reference's own compiled topo_param.pyx (tests/golden/, oracle/build_ref.py).
+//
+// What follows the reference (file:line, relative to /root/reference/horayzon):
+//   unit conversion, trig tables ........ horizon_comp.cpp:36-44, 667-670, 711-731
+//   per-cell frame, origin, driver ...... horizon_comp.cpp:739-800
+//   discrete_sampling ................... horizon_comp.cpp:302-333
+//   binary_search ....................... horizon_comp.cpp:339-381
+//   guess_constant ...................... horizon_comp.cpp:387-498
+//   *_hori_dist variants ................ horizon_comp.cpp:519-612
+//   horizon_locations ................... horizon_comp.cpp:828-1094
+//   mesh topology (triangle/quad/grid) .. horizon_comp.cpp:132-184, 199-218
+//   ray set-up / hit predicate .......... horizon_comp.cpp:241-292
+//   shadow helpers ...................... shadow_comp.cpp:96-159
+//   Terrain initialise/shadow/sw_dir_cor  shadow_comp.cpp:318-380, 386-491, 495-605
+//   SVF / VSF / openness ................ topo_param.pyx:412-460, 499-543, 577-603
+//
+// What replaces Embree (third-party, absent): any BVH gives the same any-hit
+// DECISION as long as its box test is conservative, so the oracle uses a plain
+// median-split BVH2 (or no BVH at all: brute_force=1 tests every triangle) and
+// a restatement of the published algorithm of Embree's robust-mode triangle
+// test (Pluecker-coordinate edge tests, eps = ulp*|U+V+W|, two-sided, depth
+// from the stable geometric normal).  Operation order and fused-multiply-add
+// placement are fixed in tri_hit() below and documented in DESIGN.md; the CUDA
+// product implements the same specification independently.
+//
+// Deviation shared by oracle and product: where the
+// reference would loop forever (still "hit" at the top table index, still
+// "miss" at index 0) the loop ends: a hit at index elev_num-1 counts as a miss,
+// a miss at index 0 counts as a hit.  Identical whenever the reference ends.
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// small vector helpers (explicit rounding points; compiled -ffp-contract=off)
+// ---------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+static inline V3 sub3(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline V3 add3(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+// fused forms: cross = (fma(ay,bz,-(az*by)), ...), dot = fma(ax,bx,fma(ay,by,az*bz))
+static inline V3 cross_f(V3 a, V3 b) {
+    return {fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)),
+            fmaf(a.x, b.y, -(a.y * b.x))};
+}
+static inline float dot_f(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+
+struct Tri { V3 p0, p1, p2; };
+
+// Robust two-sided ray/triangle test (restatement of the published Pluecker
+// test of Embree's RTC_SCENE_FLAG_ROBUST intersector).  Returns true when the
+// ray org + t*dir, 0 <= t <= tfar, meets the triangle; *t_out receives t.
+static inline bool tri_hit(const Tri& T, V3 O, V3 D, float tfar, float* t_out) {
+    const V3 v0 = sub3(T.p0, O), v1 = sub3(T.p1, O), v2 = sub3(T.p2, O);
+    const V3 e0 = sub3(v2, v0), e1 = sub3(v0, v1), e2 = sub3(v1, v2);
+    const float U = dot_f(cross_f(e0, add3(v2, v0)), D);
+    const float V = dot_f(cross_f(e1, add3(v0, v1)), D);
+    const float W = dot_f(cross_f(e2, add3(v1, v2)), D);
+    const float UVW = (U + V) + W;
+    const float eps = std::numeric_limits<float>::epsilon() * fabsf(UVW);
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    if (!((mn >= -eps) || (mx <= eps))) return false;
+    // stable geometric normal: per component, the cross product (e0 x e1 or
+    // e1 x e2) whose subtracted term is smaller in magnitude
+    const float ab_x = e0.z * e1.y, ab_y = e0.x * e1.z, ab_z = e0.y * e1.x;
+    const float bc_x = e1.z * e2.y, bc_y = e1.x * e2.z, bc_z = e1.y * e2.x;
+    const V3 cab = {fmaf(e0.y, e1.z, -ab_x), fmaf(e0.z, e1.x, -ab_y), fmaf(e0.x, e1.y, -ab_z)};
+    const V3 cbc = {fmaf(e1.y, e2.z, -bc_x), fmaf(e1.z, e2.x, -bc_y), fmaf(e1.x, e2.y, -bc_z)};
+    const V3 Ng = {fabsf(ab_x) < fabsf(bc_x) ? cab.x : cbc.x,
+                   fabsf(ab_y) < fabsf(bc_y) ? cab.y : cbc.y,
+                   fabsf(ab_z) < fabsf(bc_z) ? cab.z : cbc.z};
+    const float dn = dot_f(Ng, D);
+    const float den = dn + dn;
+    if (den == 0.0f) return false;
+    const float tn = dot_f(v0, Ng);
+    const float t = (tn + tn) / den;
+    if (!(t >= 0.0f && t <= tfar)) return false;
+    *t_out = t;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Scene: triangle soup + BVH2 (median split).  Grid cell (i,j) is split along
+// the diagonal (i,j+1)-(i+1,j): triangles ((i,j),(i,j+1),(i+1,j)) and
+// ((i+1,j+1),(i+1,j),(i,j+1)) -- the same surface for geom_type triangle, quad
+// and grid (horizon_comp.cpp:140-151, 163-171, 178-183).
+// ---------------------------------------------------------------------------
+struct BNode { float lo[3], hi[3]; int left, right, first, count; };
+
+struct Scene {
+    std::vector<Tri> tris;
+    std::vector<BNode> nodes;
+    std::vector<int> order;  // triangle permutation referenced by leaves
+    float pad = 0.f;
+    double build_s = 0.0;
+
+    void add_grid(const float* vg, int H, int W) {
+        auto P = [&](int i, int j) {
+            const float* p = vg + 3 * ((size_t)i * W + j);
+            return V3{p[0], p[1], p[2]};
+        };
+        tris.reserve(tris.size() + (size_t)2 * (H - 1) * (W - 1));
+        for (int i = 0; i + 1 < H; ++i)
+            for (int j = 0; j + 1 < W; ++j) {
+                tris.push_back({P(i, j), P(i, j + 1), P(i + 1, j)});
+                tris.push_back({P(i + 1, j + 1), P(i + 1, j), P(i, j + 1)});
+            }
+    }
+    void add_tin(const float* vs, int nv, const int32_t* idx, int nt) {
+        if (nv < 3) return;  // horizon_comp.cpp:199
+        for (int t = 0; t < nt; ++t) {
+            V3 p[3];
+            for (int c = 0; c < 3; ++c) {
+                const float* q = vs + 3 * (size_t)idx[3 * t + c];
+                p[c] = {q[0], q[1], q[2]};
+            }
+            tris.push_back({p[0], p[1], p[2]});
+        }
+    }
+    static void tri_box(const Tri& t, float* lo, float* hi) {
+        lo[0] = fminf(fminf(t.p0.x, t.p1.x), t.p2.x); hi[0] = fmaxf(fmaxf(t.p0.x, t.p1.x), t.p2.x);
+        lo[1] = fminf(fminf(t.p0.y, t.p1.y), t.p2.y); hi[1] = fmaxf(fmaxf(t.p0.y, t.p1.y), t.p2.y);
+        lo[2] = fminf(fminf(t.p0.z, t.p1.z), t.p2.z); hi[2] = fmaxf(fmaxf(t.p0.z, t.p1.z), t.p2.z);
+    }
+    int build_rec(int begin, int end, std::vector<float>& cen) {
+        BNode nd;
+        for (int a = 0; a < 3; ++a) { nd.lo[a] = INFINITY; nd.hi[a] = -INFINITY; }
+        float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = begin; k < end; ++k) {
+            float lo[3], hi[3];
+            tri_box(tris[order[k]], lo, hi);
+            for (int a = 0; a < 3; ++a) {
+                nd.lo[a] = fminf(nd.lo[a], lo[a]); nd.hi[a] = fmaxf(nd.hi[a], hi[a]);
+                const float c = cen[3 * (size_t)order[k] + a];
+                clo[a] = fminf(clo[a], c); chi[a] = fmaxf(chi[a], c);
+            }
+        }
+        for (int a = 0; a < 3; ++a) { nd.lo[a] -= pad; nd.hi[a] += pad; }
+        nd.left = nd.right = -1; nd.first = begin; nd.count = end - begin;
+        int self;
+#pragma omp critical(hzb_oracle_nodes)
+        { self = (int)nodes.size(); nodes.push_back(nd); }
+        if (end - begin <= 4) return self;
+        int ax = 0;
+        if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+        if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+        const int mid = (begin + end) / 2;
+        std::nth_element(order.begin() + begin, order.begin() + mid, order.begin() + end,
+                         [&](int a, int b) { return cen[3 * (size_t)a + ax] < cen[3 * (size_t)b + ax]; });
+        int l = -1, r = -1;
+        if (end - begin > (1 << 16)) {
+#pragma omp task shared(l, cen)
+            l = build_rec(begin, mid, cen);
+#pragma omp task shared(r, cen)
+            r = build_rec(mid, end, cen);
+#pragma omp taskwait
+        } else {
+            l = build_rec(begin, mid, cen);
+            r = build_rec(mid, end, cen);
+        }
+#pragma omp critical(hzb_oracle_nodes)
+        { nodes[self].left = l; nodes[self].right = r; nodes[self].count = 0; }
+        return self;
+    }
+    void build() {
+        auto t0 = std::chrono::steady_clock::now();
+        const size_t n = tris.size();
+        order.resize(n);
+        std::iota(order.begin(), order.end(), 0);
+        std::vector<float> cen(3 * n);
+        float slo[3] = {INFINITY, INFINITY, INFINITY}, shi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (size_t k = 0; k < n; ++k) {
+            float lo[3], hi[3];
+            tri_box(tris[k], lo, hi);
+            for (int a = 0; a < 3; ++a) {
+                cen[3 * k + a] = 0.5f * lo[a] + 0.5f * hi[a];
+                slo[a] = fminf(slo[a], lo[a]); shi[a] = fmaxf(shi[a], hi[a]);
+            }
+        }
+        // conservative padding: a few hundred ulps of the scene scale
+        float scale = 0.f;
+        for (int a = 0; a < 3; ++a)
+            scale = fmaxf(scale, fmaxf(fmaxf(fabsf(slo[a]), fabsf(shi[a])), shi[a] - slo[a]));
+        pad = scale * 4.0e-6f;
+        nodes.clear();
+        nodes.reserve(n / 2 + 16);
+        if (n > 0) {
+#pragma omp parallel
+#pragma omp single
+            build_rec(0, (int)n, cen);
+        }
+        build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+
+    static inline bool slab(const BNode& nd, V3 O, const float* inv, float tfar, float* tnear) {
+        float t0 = 0.f, t1 = tfar;
+        const float o[3] = {O.x, O.y, O.z};
+        for (int a = 0; a < 3; ++a) {
+            float ta = (nd.lo[a] - o[a]) * inv[a], tb = (nd.hi[a] - o[a]) * inv[a];
+            if (ta > tb) std::swap(ta, tb);
+            t0 = fmaxf(t0, ta); t1 = fminf(t1, tb);
+        }
+        *tnear = t0;
+        return t0 <= t1 * 1.000001f + 0.0f;
+    }
+    static inline void safe_inv(V3 D, float* inv) {
+        const float d[3] = {D.x, D.y, D.z};
+        for (int a = 0; a < 3; ++a) {
+            float v = d[a];
+            if (fabsf(v) < 1e-30f) v = copysignf(1e-30f, v);
+            inv[a] = 1.0f / v;
+        }
+    }
+    // any-hit (rtcOccluded1 stand-in; horizon_comp.cpp:241-262)
+    bool occluded(V3 O, V3 D, float tfar, bool brute) const {
+        float t;
+        if (brute) {
+            for (const Tri& T : tris) if (tri_hit(T, O, D, tfar, &t)) return true;
+            return false;
+        }
+        if (nodes.empty()) return false;
+        float inv[3]; safe_inv(D, inv);
+        int stack[128], sp = 0; stack[sp++] = 0;
+        while (sp) {
+            const BNode& nd = nodes[stack[--sp]];
+            float tn;
+            if (!slab(nd, O, inv, tfar, &tn)) continue;
+            if (nd.left < 0) {
+                for (int k = 0; k < nd.count; ++k)
+                    if (tri_hit(tris[order[nd.first + k]], O, D, tfar, &t)) return true;
+            } else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+        }
+        return false;
+    }
+    // closest-hit (rtcIntersect1 stand-in; horizon_comp.cpp:268-292): *dist gets
+    // the smallest t over all hit triangles, or stays tfar when nothing is hit.
+    bool closest(V3 O, V3 D, float tfar, bool brute, float* dist) const {
+        float best = tfar; bool any = false; float t;
+        if (brute) {
+            for (const Tri& T : tris)
+                if (tri_hit(T, O, D, best, &t)) { best = t; any = true; }
+            *dist = best; return any;
+        }
+        if (!nodes.empty()) {
+            float inv[3]; safe_inv(D, inv);
+            int stack[128], sp = 0; stack[sp++] = 0;
+            while (sp) {
+                const BNode& nd = nodes[stack[--sp]];
+                float tn;
+                if (!slab(nd, O, inv, best, &tn)) continue;
+                if (nd.left < 0) {
+                    for (int k = 0; k < nd.count; ++k)
+                        if (tri_hit(tris[order[nd.first + k]], O, D, best, &t)) { best = t; any = true; }
+                } else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+            }
+        }
+        *dist = best; return any;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// unit conversion and tables (horizon_comp.cpp:36-44, 667-670, 711-731)
+// ---------------------------------------------------------------------------
+static inline float deg2rad_f(float a) { return (float)(((double)a / 180.0) * M_PI); }
+static inline float rad2deg_f(float a) { return (float)(((double)a / M_PI) * 180.0); }
+
+struct Tables {
+    int azim_num = 0, elev_num = 0;
+    float acc = 0.f, low = 0.f, up = 0.f, dist = 0.f;  // radians / metres
+    std::vector<float> as, ac, ea, es, ec;
+    void make(int azim_n, float dist_km, float acc_deg, float low_deg) {
+        azim_num = azim_n;
+        acc = deg2rad_f(acc_deg);
+        low = deg2rad_f(low_deg);
+        up = deg2rad_f(89.98f);                      // :648
+        dist = (float)((double)dist_km * 1000.0);    // :670
+        as.resize(azim_n); ac.resize(azim_n);
+        for (int i = 0; i < azim_n; ++i) {           // :714-718 (float angle, float sin/cos)
+            const float ang = (float)((2 * M_PI) / azim_n * i);
+            as[i] = sinf(ang); ac[i] = cosf(ang);
+        }
+        const double step = (double)acc / 5.0;
+        elev_num = (int)ceil((double)(up - low) / step) + 1;  // :721-722
+        ea.resize(elev_num); es.resize(elev_num); ec.resize(elev_num);
+        for (int i = 0; i < elev_num; ++i) {         // :726-731, anchored at the upper limit
+            const float ang = (float)((double)up - step * i);
+            ea[elev_num - i - 1] = ang;
+            es[elev_num - i - 1] = sinf(ang);
+            ec[elev_num - i - 1] = cosf(ang);
+        }
+    }
+    inline int index_of(float elev) const {          // :351-352 etc.
+        return (int)roundf((float)((double)(elev - low) / ((double)acc / 5.0)));
+    }
+};
+
+struct Frame { V3 org; float m[3][3]; };  // m = [east north norm] as columns (:773-779)
+
+static inline Frame make_frame(V3 vert, V3 norm, V3 north, float elev) {
+    Frame f;
+    f.org = {vert.x + norm.x * elev, vert.y + norm.y * elev, vert.z + norm.z * elev};
+    const V3 east = {north.y * norm.z - north.z * norm.y, north.z * norm.x - north.x * norm.z,
+                     north.x * norm.y - north.y * norm.x};
+    f.m[0][0] = east.x; f.m[0][1] = north.x; f.m[0][2] = norm.x;
+    f.m[1][0] = east.y; f.m[1][1] = north.y; f.m[1][2] = norm.y;
+    f.m[2][0] = east.z; f.m[2][1] = north.z; f.m[2][2] = norm.z;
+    return f;
+}
+static inline V3 ray_dir(const Frame& f, const Tables& T, int ie, int k) {
+    const float r0 = T.ec[ie] * T.as[k], r1 = T.ec[ie] * T.ac[k], r2 = T.es[ie];
+    return {f.m[0][0] * r0 + f.m[0][1] * r1 + f.m[0][2] * r2,
+            f.m[1][0] * r0 + f.m[1][1] * r1 + f.m[1][2] * r2,
+            f.m[2][0] * r0 + f.m[2][1] * r1 + f.m[2][2] * r2};
+}
+
+// One cast = (table index, azimuth) -> hit?, with the termination rule applied.
+template <bool WANT_DIST>
+struct Caster {
+    const Scene& sc; const Tables& T; const Frame& fr; bool brute;
+    uint64_t rays = 0; float last_dist = 0.f;
+    inline bool operator()(int ie, int k) {
+        ++rays;
+        const V3 d = ray_dir(fr, T, ie, k);
+        if (WANT_DIST) return sc.closest(fr.org, d, T.dist, brute, &last_dist);
+        return sc.occluded(fr.org, d, T.dist, brute);
+    }
+};
+
+// discrete sampling (:302-333 / :519-557)
+template <bool WD>
+static void algo_discrete(Caster<WD>& cast, const Tables& T, float* hori, float* distb) {
+    float dist_hit = 0.f;
+    for (int k = 0; k < T.azim_num; ++k) {
+        int cur = 0, prev = 0; bool hit = true;
+        while (hit) {
+            prev = cur; cur = std::min(cur + 10, T.elev_num - 1);
+            hit = cast(cur, k);
+            if (WD && hit) dist_hit = cast.last_dist;
+            if (cur == T.elev_num - 1) hit = false;     // termination rule
+        }
+        hori[k] = (float)((double)(T.ea[prev] + T.ea[cur]) / 2.0);
+        if (WD) distb[k] = dist_hit;
+    }
+}
+// bisection on table indices for one azimuth; returns final index (:348-376)
+template <bool WD>
+static int bisect(Caster<WD>& cast, const Tables& T, int k, float* mid_out, float* dist_hit) {
+    float lim_up = T.up, lim_low = T.low;
+    float samp = (float)((double)(lim_up + lim_low) / 2.0);
+    int ie = T.index_of(samp);
+    while (fmaxf(lim_up - T.ea[ie], T.ea[ie] - lim_low) > T.acc) {
+        const bool hit = cast(ie, k);
+        if (WD && hit) *dist_hit = cast.last_dist;
+        if (hit) lim_low = T.ea[ie]; else lim_up = T.ea[ie];
+        samp = (float)((double)(lim_up + lim_low) / 2.0);
+        ie = T.index_of(samp);
+    }
+    *mid_out = samp;
+    return ie;
+}
+template <bool WD>
+static void algo_binary(Caster<WD>& cast, const Tables& T, float* hori, float* distb) {
+    float dist_hit = 0.f;
+    for (int k = 0; k < T.azim_num; ++k) {
+        float mid; bisect(cast, T, k, &mid, &dist_hit);
+        hori[k] = mid;                                // un-quantised midpoint (:377)
+        if (WD) distb[k] = dist_hit;
+    }
+}
+// guess from the previous azimuth (:387-498)
+static void algo_guess(Caster<false>& cast, const Tables& T, float* hori) {
+    float mid, dummy = 0.f;
+    int prev_az = bisect(cast, T, 0, &mid, &dummy);
+    hori[0] = mid;                                    // :428
+    const int top = T.elev_num - 1;
+    for (int k = 1; k < T.azim_num; ++k) {
+        int cur = std::max(prev_az - 5, 0), prev = 0, count = 0; bool hit = true;
+        while (hit) {                                 // upwards, +10 per cast
+            prev = cur; cur = std::min(cur + 10, top);
+            hit = cast(cur, k); ++count;
+            if (cur == top) hit = false;              // termination rule
+        }
+        if (count <= 1) {                             // first upward cast missed: go down
+            cur = std::min(prev_az + 5, top); hit = false;
+            while (!hit) {
+                prev = cur; cur = std::max(cur - 10, 0);
+                hit = cast(cur, k);
+                if (cur == 0) hit = true;             // termination rule
+            }
+        }
+        const float samp = (float)((double)(T.ea[prev] + T.ea[cur]) / 2.0);
+        const int ie = T.index_of(samp);
+        hori[k] = T.ea[ie];
+        prev_az = ie;
+    }
+}
+
+static int algo_id(const char* s) {
+    if (!strcmp(s, "discrete_sampling")) return 0;
+    if (!strcmp(s, "binary_search")) return 1;
+    if (!strcmp(s, "guess_constant")) return 2;
+    return -1;
+}
+
+thread_local std::string g_err;
+double g_build_s = 0.0, g_trace_s = 0.0;
+
+}  // namespace
+
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+void orc_last_timing(double* build_s, double* trace_s) { *build_s = g_build_s; *trace_s = g_trace_s; }
+int orc_num_threads(void) { return omp_get_max_threads(); }
+
+// Number of entries and contents of the elevation/azimuth tables (for tests).
+int orc_tables(int azim_num, float dist_km, float acc_deg, float low_deg, int cap,
+               float* elev_ang, float* elev_sin, float* elev_cos, float* azim_sin, float* azim_cos) {
+    Tables T; T.make(azim_num, dist_km, acc_deg, low_deg);
+    if (elev_ang && cap >= T.elev_num) {
+        memcpy(elev_ang, T.ea.data(), 4 * T.elev_num);
+        memcpy(elev_sin, T.es.data(), 4 * T.elev_num);
+        memcpy(elev_cos, T.ec.data(), 4 * T.elev_num);
+    }
+    if (azim_sin) { memcpy(azim_sin, T.as.data(), 4 * azim_num); memcpy(azim_cos, T.ac.data(), 4 * azim_num); }
+    return T.elev_num;
+}
+
+// horizon_gridded_comp (horizon_comp.cpp:629-822); argument order as horizon_comp.h:8-20
+int orc_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                        const float* vec_norm, const float* vec_north, int offset_0, int offset_1,
+                        float* hori_buffer, int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+                        float hori_acc, const char* ray_algorithm, const char* geom_type,
+                        const float* vert_simp, int num_vert_simp, const int32_t* tri_ind_simp,
+                        int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+                        float ray_org_elev, int brute_force, unsigned long long* num_rays_out) {
+    (void)geom_type;  // all three types describe the same surface
+    const int alg = algo_id(ray_algorithm);
+    if (alg < 0) { g_err = "unknown ray_algorithm"; return 1; }
+    Scene sc;
+    sc.add_grid(vert_grid, dem_dim_0, dem_dim_1);
+    sc.add_tin(vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp);
+    if (!brute_force) sc.build();
+    g_build_s = sc.build_s;
+    Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    uint64_t rays = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rays)
+    for (int i = 0; i < dim_in_0; ++i) {
+        for (int j = 0; j < dim_in_1; ++j) {
+            const size_t c = (size_t)i * dim_in_1 + j;
+            float* out = hori_buffer + c * azim_num;
+            if (mask[c] != 1) { for (int k = 0; k < azim_num; ++k) out[k] = hori_fill; continue; }
+            const V3 nrm = {vec_norm[3 * c], vec_norm[3 * c + 1], vec_norm[3 * c + 2]};
+            const V3 nth = {vec_north[3 * c], vec_north[3 * c + 1], vec_north[3 * c + 2]};
+            const float* vp = vert_grid + 3 * ((size_t)(i + offset_0) * dem_dim_1 + (j + offset_1));
+            const Frame fr = make_frame({vp[0], vp[1], vp[2]}, nrm, nth, ray_org_elev);
+            Caster<false> cast{sc, T, fr, brute_force != 0};
+            if (alg == 0) algo_discrete(cast, T, out, nullptr);
+            else if (alg == 1) algo_binary(cast, T, out, nullptr);
+            else algo_guess(cast, T, out);
+            rays += cast.rays;
+        }
+    }
+    g_trace_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (num_rays_out) *num_rays_out = rays;
+    return 0;
+}
+
+// horizon_locations_comp (horizon_comp.cpp:828-1094); argument order as horizon_comp.h:23-34
+int orc_horizon_locations(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* coords,
+                          const float* vec_norm, const float* vec_north, float* hori_buffer,
+                          float* hori_dist_buffer, int num_loc, int azim_num, float dist_search,
+                          float hori_acc, const char* ray_algorithm, const char* geom_type,
+                          float elev_ang_low_lim, const float* ray_org_elev, int hori_dist_out,
+                          int brute_force, unsigned long long* num_rays_out) {
+    (void)geom_type;
+    const int alg = algo_id(ray_algorithm);
+    if (alg < 0 || (hori_dist_out && alg == 2)) { g_err = "invalid ray_algorithm"; return 1; }
+    Scene sc;
+    sc.add_grid(vert_grid, dem_dim_0, dem_dim_1);   // no TIN here (:848-852)
+    if (!brute_force) sc.build();
+    g_build_s = sc.build_s;
+    Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    uint64_t rays = 0;
+    const bool brute = brute_force != 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rays)
+    for (int i = 0; i < num_loc; ++i) {
+        const V3 nrm = {vec_norm[3 * i], vec_norm[3 * i + 1], vec_norm[3 * i + 2]};
+        const V3 nth = {vec_north[3 * i], vec_north[3 * i + 1], vec_north[3 * i + 2]};
+        const V3 ini = {coords[3 * i], coords[3 * i + 1], coords[3 * i + 2]};
+        // snap to the surface along +normal, then -normal, 100 km (:946-957)
+        float dist = 0.f;
+        bool hit = sc.closest(ini, nrm, 100000.0f, brute, &dist);
+        if (!hit) {
+            hit = sc.closest(ini, {-nrm.x, -nrm.y, -nrm.z}, 100000.0f, brute, &dist);
+            dist = (float)((double)dist * -1.0);
+        }
+        if (!hit) continue;  // output keeps the wrapper's NaN
+        const float lift = dist + ray_org_elev[i];
+        Frame fr = make_frame({0, 0, 0}, nrm, nth, 0.f);
+        fr.org = {ini.x + nrm.x * lift, ini.y + nrm.y * lift, ini.z + nrm.z * lift};  // :961-963
+        float* out = hori_buffer + (size_t)i * azim_num;
+        if (!hori_dist_out) {
+            Caster<false> cast{sc, T, fr, brute};
+            if (alg == 0) algo_discrete(cast, T, out, nullptr);
+            else if (alg == 1) algo_binary(cast, T, out, nullptr);
+            else algo_guess(cast, T, out);
+            rays += cast.rays;
+        } else {
+            Caster<true> cast{sc, T, fr, brute};
+            float* dout = hori_dist_buffer + (size_t)i * azim_num;
+            if (alg == 0) algo_discrete(cast, T, out, dout);
+            else algo_binary(cast, T, out, dout);
+            rays += cast.rays;
+        }
+    }
+    g_trace_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (num_rays_out) *num_rays_out = rays;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// shapes::CppTerrain (shadow_comp.h:3-40, shadow_comp.cpp:304-605).  Unlike the
+// reference the handle COPIES its inputs (removes the dangling-pointer hazard).
+// ---------------------------------------------------------------------------
+struct OrcTerrain {
+    Scene sc; bool ready = false; int brute = 0;
+    int H = 0, W = 0, off0 = 0, off1 = 0, ny = 0, nx = 0, refrac = 0;
+    std::vector<float> vert, tilt, norm, enl, elev; std::vector<uint8_t> mask;
+    float fill = 0.f, ang_max = 0.f;
+    float t_ref = 283.15f, p_ref = 101.0f, lapse = 0.0065f, expo = 0.f;  // :349-354
+};
+
+extern "C" {
+void* orc_terrain_create(void) { return new OrcTerrain(); }
+void orc_terrain_destroy(void* h) { delete (OrcTerrain*)h; }
+
+int orc_terrain_initialise(void* h, const float* vert_grid, int dem_dim_0, int dem_dim_1, int offset_0,
+                           int offset_1, const float* vec_tilt, const float* vec_norm, int dim_in_0,
+                           int dim_in_1, const float* surf_enl_fac, const float* elevation,
+                           const uint8_t* mask, const char* geom_type, float sw_dir_cor_fill,
+                           float ang_max, int refrac_cor, int brute_force) {
+    (void)geom_type;
+    OrcTerrain& t = *(OrcTerrain*)h;
+    t.H = dem_dim_0; t.W = dem_dim_1; t.off0 = offset_0; t.off1 = offset_1;
+    t.ny = dim_in_0; t.nx = dim_in_1; t.refrac = refrac_cor; t.brute = brute_force;
+    const size_t nc = (size_t)dim_in_0 * dim_in_1;
+    t.vert.assign(vert_grid, vert_grid + (size_t)3 * dem_dim_0 * dem_dim_1);
+    t.tilt.assign(vec_tilt, vec_tilt + 3 * nc); t.norm.assign(vec_norm, vec_norm + 3 * nc);
+    t.enl.assign(surf_enl_fac, surf_enl_fac + nc); t.elev.assign(elevation, elevation + nc);
+    t.mask.assign(mask, mask + nc);
+    t.fill = sw_dir_cor_fill; t.ang_max = ang_max;
+    const float g = 9.81f, R_d = 287.0f;
+    t.expo = g / (R_d * t.lapse);
+    t.sc = Scene();
+    t.sc.add_grid(t.vert.data(), dem_dim_0, dem_dim_1);
+    if (!brute_force) t.sc.build();
+    g_build_s = t.sc.build_s;
+    t.ready = true;
+    return 0;
+}
+}  // extern "C"
+
+namespace {
+static inline void unit3(V3& v) {  // shadow_comp.cpp:96-106 (float sqrt)
+    const float mag = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+    v = {v.x / mag, v.y / mag, v.z / mag};
+}
+// Saemundsson refraction, degrees in / degrees out (shadow_comp.cpp:135-159)
+static inline float refraction_deg(float elev_true, float temp_c, float pressure) {
+    elev_true = std::max(-1.0f, std::min(elev_true, 90.0f));
+    const float arg = deg2rad_f((float)((double)elev_true + 10.3 / ((double)elev_true + 5.11)));
+    float r = (float)(1.02 / (double)tanf(arg));
+    r = (float)((double)r + 0.0019279);
+    r = (float)((double)r * (((double)pressure / 101.0) * (283.0 / (273.0 + (double)temp_c))));
+    return (float)((double)r * (1.0 / 60.0));
+}
+// Sun unit vector for one cell, incl. optional refraction (shadow_comp.cpp:421-446)
+static inline void sun_vector(const OrcTerrain& t, size_t c, V3 org, V3 nrm, const float* sunpos,
+                              V3* sun, float* dot_ns) {
+    V3 s = {sunpos[0] - org.x, sunpos[1] - org.y, sunpos[2] - org.z};
+    unit3(s);
+    float dns = nrm.x * s.x + nrm.y * s.y + nrm.z * s.z;
+    if (t.refrac == 1) {
+        const float elev_true = (float)(90.0 - (double)rad2deg_f(acosf(dns)));
+        const float temperature = t.t_ref - (t.lapse * t.elev[c]);
+        const float pressure = t.p_ref * powf(temperature / t.t_ref, t.expo);
+        const float rc = refraction_deg(elev_true, (float)((double)temperature - 273.15), pressure);
+        V3 k = {s.y * nrm.z - s.z * nrm.y, s.z * nrm.x - s.x * nrm.z, s.x * nrm.y - s.y * nrm.x};
+        unit3(k);
+        const float th = deg2rad_f(rc);
+        const float ct = cosf(th), st = sinf(th);   // Rodrigues (:109-132)
+        const float part = (float)((double)(k.x * s.x + k.y * s.y + k.z * s.z) * (1.0 - (double)ct));
+        const V3 r = {s.x * ct + (k.y * s.z - k.z * s.y) * st + k.x * part,
+                      s.y * ct + (k.z * s.x - k.x * s.z) * st + k.y * part,
+                      s.z * ct + (k.x * s.y - k.y * s.x) * st + k.z * part};
+        s = r;
+        dns = nrm.x * s.x + nrm.y * s.y + nrm.z * s.z;
+    }
+    *sun = s; *dot_ns = dns;
+}
+template <bool SW>
+static void terrain_pass(const OrcTerrain& t, const float* sunpos, uint8_t* shadow, float* swc) {
+    const float lift = 0.05f;                                    // :388, :497
+    const float dot_min = SW ? cosf(deg2rad_f(t.ang_max)) : 0.0f;  // :498
+    const float inf = std::numeric_limits<float>::infinity();
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < t.ny; ++i)
+        for (int j = 0; j < t.nx; ++j) {
+            const size_t c = (size_t)i * t.nx + j;
+            if (t.mask[c] != 1) { if (SW) swc[c] = t.fill; else shadow[c] = 3; continue; }
+            const V3 tl = {t.tilt[3 * c], t.tilt[3 * c + 1], t.tilt[3 * c + 2]};
+            const V3 nm = {t.norm[3 * c], t.norm[3 * c + 1], t.norm[3 * c + 2]};
+            const float* vp = t.vert.data() + 3 * ((size_t)(i + t.off0) * t.W + (j + t.off1));
+            const V3 org = {vp[0] + nm.x * lift, vp[1] + nm.y * lift, vp[2] + nm.z * lift};
+            V3 sun; float dns;
+            sun_vector(t, c, org, nm, sunpos, &sun, &dns);
+            const float dts = tl.x * sun.x + tl.y * sun.y + tl.z * sun.z;
+            if (dts > dot_min) {
+                const bool occ = t.sc.occluded(org, sun, inf, t.brute != 0);
+                if (SW) {
+                    if (occ) swc[c] = 0.0f;
+                    else { if (dns < dot_min) dns = dot_min; swc[c] = (dts / dns) * t.enl[c]; }  // :581-585
+                } else shadow[c] = occ ? 2 : 0;
+            } else { if (SW) swc[c] = 0.0f; else shadow[c] = 1; }
+        }
+    g_trace_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+}  // namespace
+
+extern "C" {
+
+int orc_terrain_shadow(void* h, const float* sun_position, uint8_t* shadow_buffer) {
+    OrcTerrain& t = *(OrcTerrain*)h;
+    if (!t.ready) { g_err = "terrain not initialised"; return 1; }
+    terrain_pass<false>(t, sun_position, shadow_buffer, nullptr);
+    return 0;
+}
+int orc_terrain_sw_dir_cor(void* h, const float* sun_position, float* sw_dir_cor_buffer) {
+    OrcTerrain& t = *(OrcTerrain*)h;
+    if (!t.ready) { g_err = "terrain not initialised"; return 1; }
+    terrain_pass<true>(t, sun_position, nullptr, sw_dir_cor_buffer);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Azimuthal integrals (topo_param.pyx:412-460, 499-543, 577-603): per-term
+// arithmetic in double (libm), float accumulator rounded every iteration,
+// float trig tables, single thread like the reference.
+// ---------------------------------------------------------------------------
+int orc_sky_view_factor(const float* azim, const float* hori, const float* vec_tilt, int ny, int nx,
+                        int K, float* out) {
+    std::vector<float> as(K), ac(K);
+    for (int k = 0; k < K; ++k) { as[k] = (float)sin((double)azim[k]); ac[k] = (float)cos((double)azim[k]); }
+    const float spac = azim[1] - azim[0];
+    for (size_t c = 0; c < (size_t)ny * nx; ++c) {
+        const float tx = vec_tilt[3 * c], ty = vec_tilt[3 * c + 1], tz = vec_tilt[3 * c + 2];
+        const float* h = hori + c * K;
+        float agg = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float hp = (float)atan((double)(-as[k] * tx / tz - ac[k] * ty / tz));
+            const float he = (h[k] >= hp) ? h[k] : hp;
+            const double cs = cos((double)he);
+            agg = (float)((double)agg + ((double)(tx * as[k] + ty * ac[k]) *
+                                             ((M_PI / 2.0) - (double)he - (sin(2.0 * (double)he) / 2.0)) +
+                                         (double)tz * cs * cs));
+        }
+        out[c] = (float)(((double)spac / (2.0 * M_PI)) * (double)agg);
+    }
+    return 0;
+}
+int orc_visible_sky_fraction(const float* azim, const float* hori, const float* vec_tilt, int ny, int nx,
+                             int K, float* out) {
+    std::vector<float> as(K), ac(K);
+    for (int k = 0; k < K; ++k) { as[k] = (float)sin((double)azim[k]); ac[k] = (float)cos((double)azim[k]); }
+    const float spac = azim[1] - azim[0];
+    for (size_t c = 0; c < (size_t)ny * nx; ++c) {
+        const float tx = vec_tilt[3 * c], ty = vec_tilt[3 * c + 1], tz = vec_tilt[3 * c + 2];
+        const float* h = hori + c * K;
+        float agg = 0.f;
+        for (int k = 0; k < K; ++k) {
+            const float hp = (float)atan((double)(-as[k] * tx / tz - ac[k] * ty / tz));
+            const float he = (h[k] >= hp) ? h[k] : hp;
+            agg = (float)((double)agg + (1.0 - cos((M_PI / 2.0) - (double)he)));
+        }
+        out[c] = (float)(((double)spac / (2.0 * M_PI)) * (double)agg);
+    }
+    return 0;
+}
+int orc_topographic_openness(const float* azim, const float* hori, int ny, int nx, int K, float* out) {
+    (void)azim;
+    for (size_t c = 0; c < (size_t)ny * nx; ++c) {
+        const float* h = hori + c * K;
+        float agg = 0.f;
+        for (int k = 0; k < K; ++k) agg = (float)(((double)agg + (M_PI / 2.0)) - (double)h[k]);
+        out[c] = agg / (float)K;
+    }
+    return 0;
+}
+
+}  // extern "C"
