@@ -1,0 +1,68 @@
+"""Generate the committed golden fixtures.  Run in the BUILD container only:
+
+    python oracle/build_ref.py && python tests/golden/make_golden.py
+
+* ``integrals_ref.npz`` -- inputs and outputs of the UNMODIFIED reference
+  ``topo_param.sky_view_factor / visible_sky_fraction / topographic_openness``
+  (compiled from /root/reference by oracle/build_ref.py).  These pin the oracle's
+  restatement of topo_param.pyx:412-603.
+* ``horizon_oracle_regression.npz`` -- outputs of the CPU ORACLE (not of the
+  reference: Embree is unavailable, the ray path is "parity unpinned") for a
+  small seeded DEM and all three search algorithms.  A regression anchor only.
+"""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def integral_inputs(seed, ny, nx, K):
+    rng = np.random.default_rng(seed)
+    azim = np.array([2 * np.pi / K * i for i in range(K)], np.float32)
+    hori = rng.uniform(-0.1, 0.7, (ny, nx, K)).astype(np.float32)
+    sl = np.deg2rad(rng.uniform(0, 55, (ny, nx)))
+    asp = rng.uniform(0, 2 * np.pi, (ny, nx))
+    tilt = np.stack([np.sin(sl) * np.sin(asp), np.sin(sl) * np.cos(asp), np.cos(sl)], axis=2).astype(np.float32)
+    return azim, hori, tilt
+
+
+def main():
+    br = _load(os.path.join(ROOT, "oracle", "build_ref.py"), "build_ref")
+    br.build()
+    tp, _, _ = br.load()
+    out = {}
+    for tag, (seed, ny, nx, K) in {"a": (0, 12, 16, 72), "b": (1, 6, 8, 360)}.items():
+        azim, hori, tilt = integral_inputs(seed, ny, nx, K)
+        out[tag + "_shape"] = np.array([seed, ny, nx, K])
+        out[tag + "_svf"] = np.asarray(tp.sky_view_factor(azim, hori, tilt))
+        out[tag + "_vsf"] = np.asarray(tp.visible_sky_fraction(azim, hori, tilt))
+        out[tag + "_top"] = np.asarray(tp.topographic_openness(azim, hori))
+    np.savez_compressed(os.path.join(HERE, "integrals_ref.npz"), **out)
+
+    import oracle
+    syn = _load(os.path.join(ROOT, "horayzon_b200", "synthetic.py"), "synthetic")
+    c = syn.make_config("cfg1", n=64)
+    args = (c["vert_grid"], 64, 64, c["vec_norm"], c["vec_north"], 16, 16, 5.0)
+    reg = {}
+    for alg in ("guess_constant", "binary_search", "discrete_sampling"):
+        h, _, rays = oracle.horizon_gridded(*args, azim_num=24, ray_algorithm=alg, return_rays=True)
+        reg[alg] = h
+        reg[alg + "_rays"] = np.array([rays])
+    np.savez_compressed(os.path.join(HERE, "horizon_oracle_regression.npz"), **reg)
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()

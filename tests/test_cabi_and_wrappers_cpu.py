@@ -1,0 +1,183 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol
+include/horayzon_b200.h declares, the wrappers keep the reference's signatures
+and validation messages, and compute calls fail loudly without a GPU."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+import horayzon_b200 as hb
+from horayzon_b200 import resident, synthetic as syn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "horayzon_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hzb_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    names = _declared_functions()
+    assert len(names) >= 25
+    L = ctypes.CDLL(os.path.join(ROOT, "horayzon_b200", "libhorayzon_b200.so"))
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    L.hzb_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.hzb_version()
+
+
+def test_library_is_built_for_sm_100a_only(built):
+    out = os.popen("cuobjdump --list-elf %s 2>/dev/null" % os.path.join(ROOT, "horayzon_b200", "libhorayzon_b200.so")).read()
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_signatures_mirror_the_reference():
+    """Parameter names/defaults of horizon.pyx:29-49, :218-232 and shadow.pyx:27-38."""
+    doc = hb.horizon.horizon_gridded.__doc__
+    assert "horizon_gridded" in doc or "Horizon" in doc
+    c = syn.make_config("cfg1", n=48)
+    # keyword names must be accepted exactly as the reference spells them
+    with pytest.raises(ValueError, match="invalid input argument for ray_algorithm"):
+        hb.horizon.horizon_gridded(vert_grid=c["vert_grid"], dem_dim_0=48, dem_dim_1=48, vec_norm=c["vec_norm"],
+                                   vec_north=c["vec_north"], offset_0=16, offset_1=16, dist_search=5.0, azim_num=8,
+                                   hori_acc=0.25, ray_algorithm="nope", geom_type="grid",
+                                   vert_simp=np.zeros(4, np.float32), num_vert_simp=1,
+                                   tri_ind_simp=np.zeros(4, np.int32), num_tri_simp=1, elev_ang_low_lim=-15.0,
+                                   mask=None, hori_fill=0.0, ray_org_elev=0.01)
+    t = hb.shadow.Terrain()
+    assert all(hasattr(t, m) for m in ("initialise", "shadow", "sw_dir_cor"))
+
+
+def _hg_args(c):
+    return [c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["vec_norm"], c["vec_north"],
+            c["offset_0"], c["offset_1"], c["dist_search"]]
+
+
+def test_horizon_gridded_validation_messages():
+    """Same exceptions and wording as horizon.pyx:109-156."""
+    c = syn.make_config("cfg1", n=48)
+    a = _hg_args(c)
+    with pytest.raises(ValueError, match="inconsistency between input arguments vert_grid"):
+        hb.horizon.horizon_gridded(a[0][:100], *a[1:])
+    with pytest.raises(ValueError, match="dem_dim_1, offset_0, offset_1 and vec_norm"):
+        hb.horizon.horizon_gridded(a[0], a[1], a[2], a[3], a[4], 40, 16, 5.0)
+    with pytest.raises(ValueError, match="vec_norm and/or vec_north"):
+        hb.horizon.horizon_gridded(a[0], a[1], a[2], a[3], a[4][:, :-1], 16, 16, 5.0)
+    with pytest.raises(ValueError, match="invalid input argument for geom_type"):
+        hb.horizon.horizon_gridded(*a, geom_type="mesh")
+    with pytest.raises(ValueError, match="limit of hori_acc"):
+        hb.horizon.horizon_gridded(*a, hori_acc=10.5)
+    with pytest.raises(ValueError, match="shape of mask is inconsistent"):
+        hb.horizon.horizon_gridded(*a, mask=np.ones((3, 3), np.uint8))
+    with pytest.raises(TypeError, match="minimal allowed value for 'ray_org_elev'"):
+        hb.horizon.horizon_gridded(*a, ray_org_elev=0.001)
+    with pytest.raises(ValueError, match="triangle indices of simplified outer domain"):
+        hb.horizon.horizon_gridded(*a, vert_simp=np.zeros(9, np.float32), num_vert_simp=3,
+                                   tri_ind_simp=np.array([0, 1, 3], np.int32), num_tri_simp=1)
+    with pytest.raises(ValueError, match="32'767"):
+        hb.horizon.horizon_gridded(np.zeros(40000 * 3, np.float32), 40000, 1, a[3][:1, :1], a[4][:1, :1], 0, 0, 5.0)
+    with pytest.raises((ValueError, TypeError)):  # float64 buffer rejected like the typed Cython signature
+        hb.horizon.horizon_gridded(a[0].astype(np.float64), *a[1:])
+
+
+def test_horizon_locations_validation_messages():
+    """Same exceptions and wording as horizon.pyx:282-313."""
+    c = syn.make_config("cfg1", n=48)
+    co = np.zeros((3, 3), np.float32); v = np.zeros((3, 3), np.float32); v[:, 2] = 1
+    with pytest.raises(ValueError, match="length\\(s\\) of 'coords' incorrect"):
+        hb.horizon.horizon_locations(c["vert_grid"], 48, 48, co[:2], v, v, 5.0)
+    with pytest.raises(ValueError, match="length of array 'ray_org_elev'"):
+        hb.horizon.horizon_locations(c["vert_grid"], 48, 48, co, v, v, 5.0, ray_org_elev=np.ones(2, np.float32))
+    with pytest.raises(TypeError, match="not implemented for horizon distance"):
+        hb.horizon.horizon_locations(c["vert_grid"], 48, 48, co, v, v, 5.0, ray_algorithm="guess_constant", hori_dist_out=True)
+    with pytest.raises(TypeError, match="minimal allowed value"):
+        hb.horizon.horizon_locations(c["vert_grid"], 48, 48, co, v, v, 5.0, ray_org_elev=np.array([0.001], np.float32))
+
+
+def test_terrain_validation_messages():
+    """Same exceptions and wording as shadow.pyx:87-133, 165-168, 195-198."""
+    n, rim = 40, 8
+    x, y, z = syn.sinusoid_dem(n, n, 50.0, 100.0, 1000.0, 0, 2)
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    tilt = syn.tilt_vectors(x, y, z, rim)
+    ny = nx = n - 2 * rim
+    norm, _ = syn.planar_frames(ny, nx)
+    one = np.ones((ny, nx), np.float32); mask = np.ones((ny, nx), np.uint8)
+    t = hb.shadow.Terrain()
+    with pytest.raises(ValueError, match="'vert_grid', 'dem_dim_0' and 'dem_dim_1'"):
+        t.initialise(vg[:10], n, n, rim, rim, tilt, norm, one, one, mask)
+    with pytest.raises(ValueError, match="not normalised"):
+        t.initialise(vg, n, n, rim, rim, tilt * 1.1, norm, one, one, mask)
+    with pytest.raises(ValueError, match="not all input arrays are C-contiguous"):
+        t.initialise(vg, n, n, rim, rim, tilt, norm, np.asfortranarray(one), one, mask)
+    with pytest.raises(TypeError, match="'ang_max' must be in the range"):
+        t.initialise(vg, n, n, rim, rim, tilt, norm, one, one, mask, ang_max=80.0)
+    with pytest.raises(ValueError, match="'surf_enl_fac',  'elevation' and/or 'mask'"):
+        t.initialise(vg, n, n, rim, rim, tilt, norm, one[:-1], one, mask)
+    with pytest.raises(ValueError, match="'sun_position' has incorrect shape"):
+        t.shadow(np.zeros(2, np.float32), np.zeros((ny, nx), np.uint8))
+    with pytest.raises(RuntimeError, match="initialise"):
+        t.shadow(np.zeros(3, np.float32), np.zeros((ny, nx), np.uint8))
+
+
+def test_integral_validation_messages():
+    """topo_param.pyx:400-405."""
+    az = np.zeros(4, np.float32); h = np.zeros((2, 2, 4), np.float32); t = np.zeros((2, 2, 3), np.float32)
+    with pytest.raises(ValueError, match="Inconsistent/incorrect shapes"):
+        hb.topo_param.sky_view_factor(az[:3], h, t)
+    with pytest.raises(ValueError, match="incorrect data type"):
+        hb.topo_param.visible_sky_fraction(az, h.astype(np.float64), t)
+    with pytest.raises(ValueError, match="Inconsistent/incorrect shapes"):
+        hb.topo_param.topographic_openness(az[:2], h)
+
+
+def test_compute_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without a CUDA device every compute entry point raises."""
+    if resident.lib().hzb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    c = syn.make_config("cfg1", n=48)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.horizon.horizon_gridded(*_hg_args(c))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.topo_param.sky_view_factor(np.zeros(4, np.float32), np.zeros((2, 2, 4), np.float32), np.ones((2, 2, 3), np.float32))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        resident.Scene(c["vert_grid"], 48, 48)
+
+
+def test_product_never_touches_the_oracle():
+    """The product tree must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "horayzon_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".pyx", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "hzb_oracle" not in text and "orc_" not in text, f
+    deps = os.popen("ldd %s" % os.path.join(pkg, "libhorayzon_b200.so")).read()
+    assert "oracle" not in deps
+
+
+def test_vertex_buffer_wire_format():
+    """auxiliary.py:49-133: [y][x][xyz] float32 + >= 16 zeros, 16-byte multiple."""
+    x = np.arange(6, dtype=np.float32).reshape(2, 3); y = x + 10; z = x + 20
+    b = syn.rearrange_pad_buffer(x, y, z)
+    assert b.dtype == np.float32 and b.nbytes % 16 == 0 and len(b) >= 18 + 16
+    assert np.array_equal(b[:18].reshape(2, 3, 3)[..., 0], x) and np.array_equal(b[:18].reshape(2, 3, 3)[..., 2], z)
+    assert np.all(b[18:] == 0)
+    with pytest.raises(TypeError):
+        syn.rearrange_pad_buffer(x.astype(np.float64), y, z)
+
+
+def test_signature_parameter_order():
+    # Cython functions expose no inspect.signature by default; the docstring's first line does (embedsignature off)
+    # -> check through a positional call instead: all 8 leading positionals as in the reference
+    c = syn.make_config("cfg1", n=48)
+    with pytest.raises(ValueError, match="limit of hori_acc"):
+        hb.horizon.horizon_gridded(c["vert_grid"], 48, 48, c["vec_norm"], c["vec_north"], 16, 16, 5.0, 8, 11.0)

@@ -1,0 +1,196 @@
+"""CPU tests of the oracle: golden vectors from the compiled reference, analytic
+known-answer cases, cross-algorithm consistency.  No GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from horayzon_b200 import synthetic as syn
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _integral_inputs(seed, ny, nx, K):  # must match tests/golden/make_golden.py
+    rng = np.random.default_rng(seed)
+    azim = np.array([2 * np.pi / K * i for i in range(K)], np.float32)
+    hori = rng.uniform(-0.1, 0.7, (ny, nx, K)).astype(np.float32)
+    sl = np.deg2rad(rng.uniform(0, 55, (ny, nx)))
+    asp = rng.uniform(0, 2 * np.pi, (ny, nx))
+    tilt = np.stack([np.sin(sl) * np.sin(asp), np.sin(sl) * np.cos(asp), np.cos(sl)], axis=2).astype(np.float32)
+    return azim, hori, tilt
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_integrals_match_reference_golden(tag):
+    """Oracle restatement vs outputs of the reference's own compiled topo_param
+    (fixture written by tests/golden/make_golden.py).  The reference is built
+    with -ffast-math; its own fp32 self-noise is 1.2e-6."""
+    g = np.load(os.path.join(GOLD, "integrals_ref.npz"))
+    seed, ny, nx, K = (int(v) for v in g[tag + "_shape"])
+    azim, hori, tilt = _integral_inputs(seed, ny, nx, K)
+    assert np.abs(oracle.sky_view_factor(azim, hori, tilt) - g[tag + "_svf"]).max() <= 3e-6
+    assert np.abs(oracle.visible_sky_fraction(azim, hori, tilt) - g[tag + "_vsf"]).max() <= 3e-6
+    assert np.abs(oracle.topographic_openness(azim, hori) - g[tag + "_top"]).max() <= 3e-6
+
+
+def test_integrals_known_answers():
+    """Analytic cases verified against the compiled reference in SURVEY.md 8c."""
+    K = 360
+    azim = np.array([2 * np.pi / K * i for i in range(K)], np.float32)
+    flat = np.zeros((1, 1, 3), np.float32); flat[..., 2] = 1.0
+    h0 = np.zeros((1, 1, K), np.float32)
+    assert abs(oracle.sky_view_factor(azim, h0, flat)[0, 0] - 1.0) < 2e-6
+    assert abs(oracle.visible_sky_fraction(azim, h0, flat)[0, 0] - 1.0) < 2e-6
+    assert oracle.topographic_openness(azim, h0)[0, 0] == np.float32(1.5707995)  # the compiled reference's value (float accumulator)
+    h30 = np.full((1, 1, K), np.deg2rad(30.0), np.float32)
+    assert abs(oracle.sky_view_factor(azim, h30, flat)[0, 0] - 0.75) < 3e-6       # cos^2 h
+    assert abs(oracle.visible_sky_fraction(azim, h30, flat)[0, 0] - 0.5) < 3e-6   # 1 - sin h
+    a = np.deg2rad(40.0)
+    tilt = np.array([[[np.sin(a), 0.0, np.cos(a)]]], np.float32)
+    assert abs(oracle.sky_view_factor(azim, h0, tilt)[0, 0] - (1 + np.cos(a)) / 2) < 5e-6
+
+
+def test_live_reference_if_built():
+    """When oracle/_ref holds the compiled reference (build container), compare live."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("build_ref", os.path.join(os.path.dirname(GOLD), "..", "oracle", "build_ref.py"))
+    br = importlib.util.module_from_spec(spec); spec.loader.exec_module(br)
+    try:
+        tp, _, _ = br.load()
+    except ImportError:
+        pytest.skip("oracle/_ref not built")
+    azim, hori, tilt = _integral_inputs(42, 9, 11, 120)
+    assert np.abs(oracle.sky_view_factor(azim, hori, tilt) - np.asarray(tp.sky_view_factor(azim, hori, tilt))).max() <= 3e-6
+    assert np.abs(oracle.visible_sky_fraction(azim, hori, tilt) - np.asarray(tp.visible_sky_fraction(azim, hori, tilt))).max() <= 3e-6
+    assert np.abs(oracle.topographic_openness(azim, hori) - np.asarray(tp.topographic_openness(azim, hori))).max() <= 3e-6
+
+
+def test_tables_match_specification():
+    """Defaults: 2101 entries, step 0.05 deg, anchored at 89.98 deg, first entry
+    -15.02 deg."""
+    t = oracle.tables(360, 50.0, 0.25, -15.0)
+    ea = t["elev_ang"]
+    assert len(ea) == 2101
+    assert abs(np.rad2deg(ea[-1]) - 89.98) < 1e-4 and abs(np.rad2deg(ea[0]) + 15.02) < 1e-3
+    assert np.allclose(np.diff(ea.astype(np.float64)), np.deg2rad(0.05), atol=2e-7)
+    assert np.allclose(t["elev_sin"], np.sin(ea.astype(np.float64)), atol=1e-7)
+    assert t["azim_sin"][0] == 0.0 and t["azim_cos"][0] == 1.0
+
+
+def _flat(n=48, spacing=50.0, z=0.0):
+    xs = (np.arange(n) * spacing).astype(np.float32)
+    x, y = np.meshgrid(xs, xs)
+    return x, y, np.full((n, n), z, np.float32)
+
+
+@pytest.mark.parametrize("alg", ["guess_constant", "binary_search", "discrete_sampling"])
+def test_kat_flat_plane(alg):
+    """Horizontal plane: a ray at e >= 0 from 1 cm up never hits, a ray 0.05 deg
+    below horizontal lands 11 m away => horizon = 0 within +-hori_acc."""
+    x, y, z = _flat()
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    nrm, nth = syn.planar_frames(8, 8)
+    h, az = oracle.horizon_gridded(vg, 48, 48, nrm, nth, 20, 20, 2.0, azim_num=24, ray_algorithm=alg)
+    assert h.shape == (8, 8, 24) and az.shape == (24,)
+    assert np.abs(h).max() <= np.deg2rad(0.25) + 1e-6
+
+
+@pytest.mark.parametrize("alg", ["guess_constant", "binary_search"])
+def test_kat_plateau_edge(alg):
+    """Plateau of height h north of row y0: seen from a low cell at distance d
+    the edge has elevation atan(h cos(a) / d) for azimuth a (clockwise from
+    north, y = north: horizon_comp.cpp:447-449) within +-hori_acc."""
+    n, sp, hgt, row0 = 96, 25.0, 120.0, 70
+    x, y, z = _flat(n, sp)
+    z[row0:, :] = hgt
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    nrm, nth = syn.planar_frames(1, 1)
+    i0, j0 = 40, 48
+    K = 72
+    h, az = oracle.horizon_gridded(vg, n, n, nrm, nth, i0, j0, 5.0, azim_num=K, ray_algorithm=alg)
+    d = (row0 - i0) * sp
+    for k in range(K):
+        a = az[k]
+        if np.cos(a) > 0.5:  # looking towards the plateau, edge inside the DEM
+            want = np.arctan(hgt * np.cos(a) / d)
+            assert abs(h[0, 0, k] - want) <= np.deg2rad(0.25) + 2e-4, (k, h[0, 0, k], want)
+        if np.cos(a) < -0.2:  # looking away: flat
+            assert abs(h[0, 0, k]) <= np.deg2rad(0.25) + 1e-6
+
+
+def test_algorithms_agree_and_bvh_equals_brute_force():
+    c = syn.make_config("cfg1", n=48)
+    c_args = (c["vert_grid"], 48, 48, c["vec_norm"], c["vec_north"], 16, 16, 5.0)
+    res = {}
+    for alg in ("guess_constant", "binary_search", "discrete_sampling"):
+        h, _, rays = oracle.horizon_gridded(*c_args, azim_num=16, ray_algorithm=alg, return_rays=True)
+        hb, _, raysb = oracle.horizon_gridded(*c_args, azim_num=16, ray_algorithm=alg, brute_force=True, return_rays=True)
+        assert np.array_equal(h, hb) and rays == raysb, "BVH culling changed a decision"
+        res[alg] = h
+    acc = np.deg2rad(0.25)
+    assert np.abs(res["guess_constant"] - res["binary_search"]).max() <= 2 * acc + 1e-6
+    assert np.abs(res["guess_constant"] - res["discrete_sampling"]).max() <= 2 * acc + 1e-6
+
+
+def test_oracle_regression_fixture():
+    """Oracle self-regression (NOT a reference vector: ray path is parity-unpinned)."""
+    g = np.load(os.path.join(GOLD, "horizon_oracle_regression.npz"))
+    c = syn.make_config("cfg1", n=64)
+    args = (c["vert_grid"], 64, 64, c["vec_norm"], c["vec_north"], 16, 16, 5.0)
+    for alg in ("guess_constant", "binary_search", "discrete_sampling"):
+        h, _, rays = oracle.horizon_gridded(*args, azim_num=24, ray_algorithm=alg, return_rays=True)
+        assert np.array_equal(h, g[alg]) and rays == int(g[alg + "_rays"][0])
+
+
+def test_masked_cells_and_termination_rule():
+    """Masked cells get hori_fill; a cell on a pedestal looking over empty space
+    terminates (the reference would loop forever) at table index 0.
+    Cell (0, 0) of the inner domain sits on the apex."""
+    x, y, z = _flat(24, 100.0)
+    z[11, 11] = 5000.0  # 5 km spike: from its apex nothing is visible down to -15 deg within 1 km
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    nrm, nth = syn.planar_frames(2, 2)
+    mask = np.array([[1, 0], [0, 1]], np.uint8)
+    h, _ = oracle.horizon_gridded(vg, 24, 24, nrm, nth, 11, 11, 1.0, azim_num=8, mask=mask, hori_fill=7.0)
+    assert np.all(h[0, 1] == 7.0) and np.all(h[1, 0] == 7.0)
+    assert np.all(np.isfinite(h)) and h[0, 0].min() < np.deg2rad(-14.0)
+
+
+def _hemisphere(n=200, spacing=125.0, radius=4500.0):
+    xs = ((np.arange(n) - (n - 1) / 2.0) * spacing).astype(np.float32)
+    x, y = np.meshgrid(xs, xs)
+    r2 = radius ** 2 - x.astype(np.float64) ** 2 - y.astype(np.float64) ** 2
+    z = np.sqrt(np.clip(r2, 0.0, None)).astype(np.float32)
+    return x, y, z
+
+
+def test_hemisphere_shadow_partition_and_energy_conservation():
+    """Synthetic hemispherical mountain of examples/shadow/gridded_planar_DEM_
+    artificial.py:45-63: codes partition the domain, the lit side faces the sun,
+    and the domain-mean sw_dir_cor stays close to 1 (:190-204 plots 0.85-1.05)."""
+    n, rim = 200, 20  # inner domain +-10 km holds the whole shadow (tip at R / sin(30 deg) = 9 km)
+    x, y, z = _hemisphere(n)
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    tilt = syn.tilt_vectors(x, y, z, rim)
+    ny = nx = n - 2 * rim
+    norm, _ = syn.planar_frames(ny, nx)
+    enl = (1.0 / (norm * tilt).sum(axis=2)).astype(np.float32)
+    elev = np.ascontiguousarray(z[rim:-rim, rim:-rim])
+    mask = np.ones((ny, nx), np.uint8)
+    t = oracle.Terrain()
+    t.initialise(vg, n, n, rim, rim, tilt, norm, enl, elev, mask, ang_max=89.99)
+    el = np.deg2rad(30.0)
+    for azd in (0.0, 90.0, 200.0):
+        a = np.deg2rad(azd)
+        sun = np.array([1e7 * np.cos(el) * np.sin(a), 1e7 * np.cos(el) * np.cos(a), 1e7 * np.sin(el)], np.float32)
+        code = np.empty((ny, nx), np.uint8); sw = np.empty((ny, nx), np.float32)
+        t.shadow(sun, code); t.sw_dir_cor(sun, sw)
+        assert set(np.unique(code)) <= {0, 1, 2}
+        assert (code == 1).sum() > 0 and (code == 2).sum() > 0 and (code == 0).sum() > 0
+        assert np.all(sw[code != 0] == 0.0) and np.all(sw[code == 0] > 0.0)
+        assert abs(float(sw.mean()) - 1.0) < 0.05
+        # terrain shadow lies on the far side of the mountain from the sun
+        yy, xx = np.nonzero(code == 2)
+        cx = x[rim:-rim, rim:-rim][yy, xx].mean(); cy = y[rim:-rim, rim:-rim][yy, xx].mean()
+        assert cx * np.sin(a) + cy * np.cos(a) < 0.0
