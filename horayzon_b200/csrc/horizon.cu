@@ -10,6 +10,7 @@
 #include "hzb_geom.cuh"
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace hzb {
 
@@ -262,6 +263,211 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
     }
 }
 
+
+// ===========================================================================
+// Persistent state-machine kernel (the production path for gridded domains).
+//
+// The simple kernel above inlines the traversal at three call sites and tests
+// leaves inside the node loop, so lanes of a warp sit in different copies of
+// the code (ncu r01: 4.9 of 32 lanes active per instruction).  Here every lane
+// owns one cell and runs the search as an explicit state machine; there is ONE
+// traversal loop per warp in which all lanes step through BVH nodes together,
+// each on its own ray:
+//   * refill: the loop is left only when fewer than `thr` lanes still have a
+//     ray in flight (warp ballot); lanes whose ray finished then advance their
+//     state machine (next table index / next azimuth / cell done) and re-enter
+//     with a fresh ray while the others resume where they stopped;
+//   * postponed leaves: primitives found during node steps are queued per lane
+//     (4 registers) and tested in a separate leaf step that runs only when
+//     enough lanes have queued work or a lane cannot continue otherwise.
+// The hit/miss DECISIONS are those of cell_search<ALG> above, bit for bit.
+// ===========================================================================
+constexpr int NODE_NONE = 0x7fffffff;
+constexpr int PEND_MAX = 4;
+
+struct LaneSM {
+    // search state (horizon_comp.cpp:387-498 unrolled into states)
+    int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
+    int k, cur, prev, count, prev_az;
+    float lim_up, lim_low, samp;
+};
+
+template <int ALG>
+__device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int& cast_ie) {
+    // returns true if a cast is required (cast_ie set), false if the azimuth needs none
+    const int top = s.elev_num - 1;
+    if (ALG == 0) {
+        m.phase = 4; m.prev = 0; m.cur = min(10, top); cast_ie = m.cur; return true;
+    } else if (ALG == 1 || m.k == 0) {
+        m.phase = 1; m.lim_up = s.up; m.lim_low = s.low;
+        m.samp = midpoint(m.lim_up, m.lim_low);
+        m.cur = index_of(s, m.samp);
+        const float ea = __ldg(s.elev_ang + m.cur);
+        if (fmaxf(__fsub_rn(m.lim_up, ea), __fsub_rn(ea, m.lim_low)) > s.acc) { cast_ie = m.cur; return true; }
+        return false;
+    } else {
+        m.phase = 2; m.count = 0;
+        m.prev = max(m.prev_az - 5, 0); m.cur = min(m.prev + 10, top); cast_ie = m.cur; return true;
+    }
+}
+
+// Consume the result of the last cast (if any) and move on until the next cast
+// is known or the cell is finished.  Returns true with cast_ie set when a ray
+// must be traced; false when the cell is complete.
+template <int ALG>
+__device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have_result, bool hit, OutBuf& ob, int& cast_ie) {
+    const int top = s.elev_num - 1;
+    while (true) {
+        if (!have_result) {  // start of an azimuth
+            if (sm_begin_azimuth<ALG>(s, m, cast_ie)) return true;
+            // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
+            hit = false; have_result = true;
+            // (emulate loop exit below)
+            goto bisect_done;
+        }
+        if (m.phase == 1) {
+            {
+                const float ea = __ldg(s.elev_ang + m.cur);
+                if (hit) m.lim_low = ea; else m.lim_up = ea;
+                m.samp = midpoint(m.lim_up, m.lim_low);
+                m.cur = index_of(s, m.samp);
+                const float ea2 = __ldg(s.elev_ang + m.cur);
+                if (fmaxf(__fsub_rn(m.lim_up, ea2), __fsub_rn(ea2, m.lim_low)) > s.acc) { cast_ie = m.cur; return true; }
+            }
+        bisect_done:
+            ob.put(m.k, m.samp);          // un-quantised midpoint (:377, :428)
+            m.prev_az = m.cur;            // seeds the chain (:429)
+        } else if (m.phase == 2) {
+            m.count++;
+            if (m.cur == top) hit = false;            // termination rule
+            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); cast_ie = m.cur; return true; }
+            if (m.count <= 1) {                       // first upward cast missed: search downwards (:471-488)
+                m.phase = 3;
+                m.prev = min(m.prev_az + 5, top); m.cur = max(m.prev - 10, 0); cast_ie = m.cur; return true;
+            }
+            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
+            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
+        } else if (m.phase == 3) {
+            if (m.cur == 0) hit = true;               // termination rule
+            if (!hit) { m.prev = m.cur; m.cur = max(m.cur - 10, 0); cast_ie = m.cur; return true; }
+            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
+            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
+        } else {  // phase 4: discrete sampling (:309-331)
+            if (m.cur == top) hit = false;
+            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); cast_ie = m.cur; return true; }
+            ob.put(m.k, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
+        }
+        // azimuth finished
+        m.k++;
+        if (m.k >= s.azim_num) { m.phase = 0; return false; }
+        have_result = false;
+    }
+}
+
+constexpr int SM_THREADS = 128;
+
+template <int ALG>
+__global__ void __launch_bounds__(SM_THREADS, 4) k_horizon_sm(SceneView sv, HorizonParams p, Counters* counters,
+                                                              unsigned int* tile_counter, int refill_thr, int leaf_thr) {
+    const Search s = make_search(sv, p, counters);
+    const int lane = threadIdx.x & 31;
+    const int rows = p.row_end - p.row_begin;
+    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    int stack[HZB_STACK2];
+
+    while (true) {
+        unsigned int tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= num_tiles) break;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int ci = p.row_begin + ty * 4 + (lane >> 3), cj = tx * 8 + (lane & 7);
+
+        // ---- per-lane cell set-up
+        LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
+        Frame f; OutBuf ob; ob.init(nullptr, false);
+        bool has_cell = false;
+        unsigned int units = 0;
+        if (ci < p.row_end && cj < p.dim_in_1) {
+            const size_t c = (size_t)ci * p.dim_in_1 + cj;
+            float* out = p.hori + c * p.azim_num;
+            if (p.mask[c] == 1) {
+                const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
+                const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
+                const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
+                f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+                ob.init(out, vec);
+                has_cell = true; units = p.azim_num;
+            } else {
+                for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+            }
+        }
+
+        // ---- ray state
+        bool ray_active = false, ray_hit = false, have_result = false;
+        F3 D = f3(0.f, 0.f, 1.f); RayInv inv = make_inv(D);
+        int node = NODE_NONE, sp = 0, npend = 0;
+        unsigned int pq0 = 0, pq1 = 0, pq2 = 0, pq3 = 0;
+
+        while (true) {
+            // (1) refill: lanes with a cell but no ray in flight advance their state machine
+            if (has_cell && !ray_active) {
+                int ie;
+                if (sm_advance<ALG>(s, m, have_result, ray_hit, ob, ie)) {
+                    D = ray_dir(s, f, ie, m.k); inv = make_inv(D);
+                    node = 0; sp = 0; npend = 0; ray_active = true; cnt.rays++;
+                } else has_cell = false;
+            }
+            const unsigned int cell_mask = __ballot_sync(0xffffffffu, has_cell);
+            if (cell_mask == 0u) break;
+            const int thr = min(refill_thr, __popc(cell_mask));
+
+            // (2) shared traversal loop: every lane steps its own ray
+            while (true) {
+                if (ray_active && node != NODE_NONE && npend <= PEND_MAX - 2) {
+                    const float4* np = reinterpret_cast<const float4*>(sv.nodes2 + node);
+                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+                    cnt.nodes++;
+                    const float lo0[3] = {n0.x, n0.y, n0.z}, hi0[3] = {n0.w, n1.x, n1.y};
+                    const float lo1[3] = {n1.z, n1.w, n2.x}, hi1[3] = {n2.y, n2.z, n2.w};
+                    const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
+                    float tn0, tn1;
+                    bool h0 = slab(lo0, hi0, f.org, inv, s.dist, tn0);
+                    bool h1 = slab(lo1, hi1, f.org, inv, s.dist, tn1);
+                    if (h0 && c0 < 0) { pq3 = pq2; pq2 = pq1; pq1 = pq0; pq0 = (unsigned int)(~c0); npend++; h0 = false; }
+                    if (h1 && c1 < 0) { pq3 = pq2; pq2 = pq1; pq1 = pq0; pq0 = (unsigned int)(~c1); npend++; h1 = false; }
+                    if (h0 && h1) {
+                        int nearc = c0, farc = c1;
+                        if (tn1 < tn0) { nearc = c1; farc = c0; }
+                        if (sp < HZB_STACK2) stack[sp++] = farc; else atomicAdd(s.overflow, 1u);
+                        node = nearc;
+                    } else if (h0) node = c0;
+                    else if (h1) node = c1;
+                    else node = (sp > 0) ? stack[--sp] : NODE_NONE;
+                }
+                // leaf step: only when worthwhile or unavoidable
+                const bool pending = ray_active && npend > 0;
+                const bool must = pending && (npend > PEND_MAX - 2 || node == NODE_NONE);
+                const unsigned int pend_mask = __ballot_sync(0xffffffffu, pending);
+                if (__any_sync(0xffffffffu, must) || __popc(pend_mask) >= leaf_thr) {
+                    if (pending) {
+                        const unsigned int prim = pq0; pq0 = pq1; pq1 = pq2; pq2 = pq3; npend--;
+                        cnt.prims++;
+                        float tfar = s.dist;
+                        if (prim_hit<false>(sv, prim, f.org, D, tfar)) { ray_active = false; ray_hit = true; have_result = true; }
+                    }
+                }
+                if (ray_active && node == NODE_NONE && npend == 0) { ray_active = false; ray_hit = false; have_result = true; }
+                if (__popc(__ballot_sync(0xffffffffu, ray_active)) < thr) break;
+            }
+        }
+        flush_counters(cnt, units, counters);
+    }
+}
+
 // ---- arbitrary locations (horizon_comp.cpp:828-1094)
 __global__ void k_loc_snap(SceneView sv, LocationParams lp, float4* org_valid, Counters* counters) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,12 +563,24 @@ __global__ void k_loc_dist_fix(LocationParams lp, int azim_num, const float4* or
 int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
     if (p.row_end <= p.row_begin || p.dim_in_1 <= 0) return 0;
     HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-    const int grid = sm_count() * 8;
     const SceneView sv = s.view();
-    switch (p.algorithm) {
-        case 0: k_horizon_gridded<0><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
-        case 1: k_horizon_gridded<1><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
-        default: k_horizon_gridded<2><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+    static const char* kern_env = getenv("HZB_KERNEL");      // "simple" selects the reference-shaped kernel
+    static const int refill_thr = getenv("HZB_REFILL") ? atoi(getenv("HZB_REFILL")) : 24;
+    static const int leaf_thr = getenv("HZB_LEAF") ? atoi(getenv("HZB_LEAF")) : 12;
+    if (kern_env && !strcmp(kern_env, "simple")) {
+        const int grid = sm_count() * 8;
+        switch (p.algorithm) {
+            case 0: k_horizon_gridded<0><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+            case 1: k_horizon_gridded<1><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+            default: k_horizon_gridded<2><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+        }
+    } else {
+        const int grid = sm_count() * 4;
+        switch (p.algorithm) {
+            case 0: k_horizon_sm<0><<<grid, SM_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, refill_thr, leaf_thr); break;
+            case 1: k_horizon_sm<1><<<grid, SM_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, refill_thr, leaf_thr); break;
+            default: k_horizon_sm<2><<<grid, SM_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, refill_thr, leaf_thr); break;
+        }
     }
     HZB_CUDA(cudaGetLastError());
     return 0;

@@ -114,7 +114,11 @@ class Scene:
             lib().hzb_scene_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals may be gone
+            pass
 
     def stats(self):
         st = Stats()
