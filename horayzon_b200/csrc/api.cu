@@ -62,7 +62,7 @@ static int read_counters(const Scene& s, hzb_stats& st) {
     HZB_CUDA(cudaMemcpy(&c, s.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     st.rays = c.rays; st.node_visits = c.node_visits; st.prim_tests = c.prim_tests; st.units = c.units;
     st.warp_node_visits = c.warp_node_visits;
-    st.num_prims = s.num_prims; st.num_nodes = s.num_nodes8; st.bvh_bytes = s.bvh_bytes;
+    st.num_prims = s.num_prims; st.num_nodes = s.num_nodes4; st.bvh_bytes = s.bvh_bytes;
     st.t_h2d = s.t_h2d; st.t_build = s.t_build;
     if (c.stack_overflow) { set_error("BVH traversal stack overflow (results invalid)"); return 1; }
     return 0;

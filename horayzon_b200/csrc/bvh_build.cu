@@ -332,9 +332,9 @@ int exclusive_scan_u32(uint32_t* d_in, uint32_t* d_out, size_t m, uint32_t* d_su
 
 
 void scene_free(Scene& s) {
-    cudaFree(s.d_vert4); cudaFree(s.d_tin4); cudaFree(s.d_nodes2); cudaFree(s.d_nodes8);
+    cudaFree(s.d_vert4); cudaFree(s.d_tin4); cudaFree(s.d_nodes2); cudaFree(s.d_nodes4);
     cudaFree(s.d_prim_ids); cudaFree(s.d_counters); cudaFree(s.d_tile_counter); cudaFree(s.d_tables);
-    s.d_vert4 = nullptr; s.d_tin4 = nullptr; s.d_nodes2 = nullptr; s.d_nodes8 = nullptr; s.d_prim_ids = nullptr;
+    s.d_vert4 = nullptr; s.d_tin4 = nullptr; s.d_nodes2 = nullptr; s.d_nodes4 = nullptr; s.d_prim_ids = nullptr;
     s.d_counters = nullptr; s.d_tile_counter = nullptr; s.d_tables = nullptr; s.tables_cap = 0;
 }
 
@@ -419,7 +419,8 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
     k_refit<<<(n + 255) / 256, 256, 0, st>>>(g, s.d_prim_ids, n, s.pad, s.d_nodes2, d_np, d_lp, d_visit, d_root);
     HZB_CUDA(cudaGetLastError());
     HZB_CUDA(cudaStreamSynchronize(st));
-    s.bvh_bytes = (size_t)n_int * sizeof(Bvh2Node);
+    HZB_TRY(build_wide_bvh(s, st));
+    s.bvh_bytes = (size_t)s.num_nodes4 * sizeof(Bvh4Node);
 
     cudaFree(d_v3); cudaFree(d_vs); cudaFree(d_ti); cudaFree(d_bounds);
     cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_v0); cudaFree(d_v1);

@@ -37,19 +37,17 @@ struct __align__(16) Bvh2Node {
 };
 static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be 64 bytes");
 
-// 8-wide BVH node with child boxes quantised to 8 bits relative to the node
-// origin (power-of-two scale per axis).  96 B = three 32-byte sectors.
-//   ref[k]: child k: 0xFFFFFFFF empty; bit31 set -> leaf range of sorted
-//           primitives: bits 0..27 first slot, bits 28..30 count-1; else
-//           internal node index.
-struct __align__(32) Bvh8Node {
-    float ox, oy, oz;          // node origin (box minimum)
-    uint8_t ex, ey, ez, nchild;  // biased exponents: scale = 2^(e-127) per axis
-    uint8_t qlo[3][8];         // [axis][child]
-    uint8_t qhi[3][8];
-    uint32_t ref[8];
-};
-static_assert(sizeof(Bvh8Node) == 96, "Bvh8Node must be 96 bytes");
+// 4-wide BVH node with child boxes quantised to 16 bits on a scene-global grid
+// (plane = qorg[a] + q * qstep[a]): no per-node header, so the lane that owns
+// child k needs exactly one 16-byte load per node.  64 B = two 32-byte sectors.
+//   qx/qy/qz : lo | hi << 16 (conservative: lo rounded down, hi rounded up)
+//   ref      : 0xFFFFFFFF empty (box inverted); bit 31 set -> leaf holding
+//              primitive (ref & 0x7FFFFFFF); else index of the child node.
+struct __align__(16) WideChild { uint32_t qx, qy, qz, ref; };
+struct __align__(64) Bvh4Node { WideChild c[4]; };
+static_assert(sizeof(Bvh4Node) == 64, "Bvh4Node must be 64 bytes");
+constexpr uint32_t WIDE_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t WIDE_LEAF = 0x80000000u;
 
 // Device view of a scene: DEM vertices, optional TIN, BVH.
 // Primitive p < num_quads is grid quad (i = p / (W-1), j = p % (W-1)), split
@@ -60,11 +58,12 @@ struct SceneView {
     const float4* vert4;   // [H*W] (x, y, z, 0)
     const float4* tin4;    // [3*num_tin] (x, y, z, 0)
     const Bvh2Node* nodes2;
-    const Bvh8Node* nodes8;
+    const Bvh4Node* nodes4;
+    float qorg[3], qstep[3];  // quantisation grid of nodes4
     const uint32_t* prim_ids;  // sorted (Morton) order -> primitive id
     int H, W;
     uint32_t num_quads, num_tin, num_prims;
-    uint32_t num_nodes8;
+    uint32_t num_nodes4;
 };
 
 struct Counters {  // device-side accumulators (one struct per scene / terrain)
@@ -75,11 +74,12 @@ struct Counters {  // device-side accumulators (one struct per scene / terrain)
 struct Scene {
     int device = 0;
     int H = 0, W = 0;
-    uint32_t num_quads = 0, num_tin = 0, num_prims = 0, num_nodes8 = 0;
+    uint32_t num_quads = 0, num_tin = 0, num_prims = 0, num_nodes4 = 0;
     float4* d_vert4 = nullptr;
     float4* d_tin4 = nullptr;
     Bvh2Node* d_nodes2 = nullptr;
-    Bvh8Node* d_nodes8 = nullptr;
+    Bvh4Node* d_nodes4 = nullptr;
+    float qorg[3] = {0, 0, 0}, qstep[3] = {1, 1, 1};
     uint32_t* d_prim_ids = nullptr;
     Counters* d_counters = nullptr;
     unsigned int* d_tile_counter = nullptr;
@@ -91,14 +91,16 @@ struct Scene {
     size_t tables_cap = 0;
     SceneView view() const {
         SceneView v;
-        v.vert4 = d_vert4; v.tin4 = d_tin4; v.nodes2 = d_nodes2; v.nodes8 = d_nodes8;
+        v.vert4 = d_vert4; v.tin4 = d_tin4; v.nodes2 = d_nodes2; v.nodes4 = d_nodes4;
+        for (int a = 0; a < 3; ++a) { v.qorg[a] = qorg[a]; v.qstep[a] = qstep[a]; }
         v.prim_ids = d_prim_ids; v.H = H; v.W = W; v.num_quads = num_quads; v.num_tin = num_tin;
-        v.num_prims = num_prims; v.num_nodes8 = num_nodes8;
+        v.num_prims = num_prims; v.num_nodes4 = num_nodes4;
         return v;
     }
 };
 
-// bvh_build.cu
+// bvh_build.cu / bvh_wide.cu
+int build_wide_bvh(Scene& s, cudaStream_t st);
 int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const float* vert_simp,
                            int num_vert_simp, const int32_t* tri_ind_simp, int num_tri_simp);
 void scene_free(Scene& s);

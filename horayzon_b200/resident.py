@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libhorayzon_b200.so")
+_LIB_PATH = os.environ.get("HZB_LIB", os.path.join(_HERE, "libhorayzon_b200.so"))  # HZB_LIB: A/B experiments only
 
 
 class Stats(ctypes.Structure):
