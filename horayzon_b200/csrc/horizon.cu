@@ -1155,7 +1155,7 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
             case 1: k_horizon_sm<1><<<grid, SM_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, refill_thr, leaf_thr); break;
             default: k_horizon_sm<2><<<grid, SM_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, refill_thr, leaf_thr); break;
         }
-    } else if (kern_env && !strcmp(kern_env, "wq4")) {
+    } else if (!kern_env || !strcmp(kern_env, "wq4")) {
         static const int w_refill = getenv("HZB_WREFILL") ? atoi(getenv("HZB_WREFILL")) : 24;
         static const int w_wait = getenv("HZB_WWAIT") ? atoi(getenv("HZB_WWAIT")) : 6;
         const int grid = sm_count() * 6;
@@ -1164,7 +1164,7 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
             case 1: k_horizon_wq4<1><<<grid, WQ_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
             default: k_horizon_wq4<2><<<grid, WQ_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
         }
-    } else if (!kern_env || !strcmp(kern_env, "wq")) {
+    } else if (!strcmp(kern_env, "wq")) {
         static const int w_refill = getenv("HZB_WREFILL") ? atoi(getenv("HZB_WREFILL")) : 24;
         static const int w_wait = getenv("HZB_WWAIT") ? atoi(getenv("HZB_WWAIT")) : 6;
         const int grid = sm_count() * 6;
