@@ -9,6 +9,9 @@
 #include <string.h>
 #include <chrono>
 #include <limits>
+#include <algorithm>
+#include <time.h>
+#include <stdlib.h>
 
 namespace hzb {
 
@@ -126,30 +129,39 @@ int hzb_scene_stats(const hzb_scene* h, hzb_stats* out) {
     return read_counters(h->s, *out);
 }
 
+static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                  int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
+                                  int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                                  float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
+                                  unsigned int* d_row_done, cudaStream_t st) {
+    const int alg = parse_algorithm(ray_algorithm);
+    if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
+    if (azim_num < 1 || dim_in_0 < 0 || dim_in_1 < 0 || row_begin < 0 || row_end > dim_in_0) { set_error("invalid dimensions"); return 1; }
+    if (offset_0 < 0 || offset_1 < 0 || offset_0 + dim_in_0 > sc.H || offset_1 + dim_in_1 > sc.W) {
+        set_error("inner domain exceeds DEM dimensions"); return 1;
+    }
+    if (!(hori_acc > 0.f)) { set_error("hori_acc must be positive"); return 1; }
+    HZB_CUDA(cudaSetDevice(sc.device));
+    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    if (T.elev_num < 2) { set_error("elevation table too small"); return 1; }
+    HorizonParams p{};
+    HZB_TRY(upload_tables(sc, T, p, st));
+    p.algorithm = alg; p.vec_norm = d_vec_norm; p.vec_north = d_vec_north; p.mask = d_mask;
+    p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1;
+    p.row_begin = row_begin; p.row_end = row_end; p.hori_fill = hori_fill; p.ray_org_elev = ray_org_elev;
+    p.hori = d_hori_buffer; p.row_done = d_row_done;
+    return launch_horizon_gridded(sc, p, st);
+}
+
 int hzb_horizon_gridded_dev(hzb_scene* h, const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
                             int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
                             int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
                             float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
                             void* stream) {
     if (!h) { set_error("null scene"); return 1; }
-    const int alg = parse_algorithm(ray_algorithm);
-    if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
-    if (azim_num < 1 || dim_in_0 < 0 || dim_in_1 < 0 || row_begin < 0 || row_end > dim_in_0) { set_error("invalid dimensions"); return 1; }
-    if (offset_0 < 0 || offset_1 < 0 || offset_0 + dim_in_0 > h->s.H || offset_1 + dim_in_1 > h->s.W) {
-        set_error("inner domain exceeds DEM dimensions"); return 1;
-    }
-    if (!(hori_acc > 0.f)) { set_error("hori_acc must be positive"); return 1; }
-    HZB_CUDA(cudaSetDevice(h->s.device));
-    cudaStream_t st = (cudaStream_t)stream;
-    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
-    if (T.elev_num < 2) { set_error("elevation table too small"); return 1; }
-    HorizonParams p{};
-    HZB_TRY(upload_tables(h->s, T, p, st));
-    p.algorithm = alg; p.vec_norm = d_vec_norm; p.vec_north = d_vec_north; p.mask = d_mask;
-    p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1;
-    p.row_begin = row_begin; p.row_end = row_end; p.hori_fill = hori_fill; p.ray_org_elev = ray_org_elev;
-    p.hori = d_hori_buffer;
-    return launch_horizon_gridded(h->s, p, st);
+    return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, row_begin,
+                                  row_end, azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
+                                  ray_org_elev, d_hori_buffer, nullptr, (cudaStream_t)stream);
 }
 
 // -------------------------------------------------------------- host tier
@@ -174,15 +186,66 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
     HZB_TRY(d_norm.upload(vec_norm, nc * 3)); HZB_TRY(d_north.upload(vec_north, nc * 3)); HZB_TRY(d_mask.upload(mask, nc));
     HZB_TRY(d_hori.alloc(nc * (size_t)azim_num));
     const double t_h2d_extra = now_s() - t0;
+    // Kernel on one stream; finished row blocks (published by the kernel through
+    // row_done counters) are copied to the caller's array on a second stream while
+    // the kernel is still running, so D2H and the page faults of the fresh ndarray
+    // hide behind the traversal.
     t0 = now_s();
-    HZB_TRY(hzb_horizon_gridded_dev(h, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
-                                    azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
-                                    ray_org_elev, d_hori.p, nullptr));
-    HZB_CUDA(cudaDeviceSynchronize());
-    const double t_trace = now_s() - t0;
-    t0 = now_s();
-    HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
-    const double t_d2h = now_s() - t0;
+    const int tiles_x = (dim_in_1 + 7) / 8, tiles_y = (dim_in_0 + 3) / 4;
+    const bool overlap = getenv("HZB_NO_OVERLAP") == nullptr && !(getenv("HZB_KERNEL") && strcmp(getenv("HZB_KERNEL"), "wq4"));
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t a, b; ~StreamGuard() { cudaStreamDestroy(a); cudaStreamDestroy(b); } } sguard{s_comp, s_copy};
+    DevBuf<unsigned int> d_done;
+    HZB_TRY(d_done.alloc((size_t)tiles_y));
+    HZB_CUDA(cudaMemsetAsync(d_done.p, 0, (size_t)tiles_y * sizeof(unsigned int), s_comp));
+    HZB_TRY(horizon_gridded_launch(h->s, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
+                                   azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
+                                   ray_org_elev, d_hori.p, overlap ? d_done.p : nullptr, s_comp));
+    double t_d2h = 0.0, t_trace = 0.0;
+    const size_t row_elems = (size_t)dim_in_1 * (size_t)azim_num;
+    if (overlap) {
+        unsigned int* h_done = nullptr;
+        HZB_CUDA(cudaMallocHost((void**)&h_done, (size_t)tiles_y * sizeof(unsigned int)));
+        struct PinGuard { unsigned int* p; ~PinGuard() { cudaFreeHost(p); } } pguard{h_done};
+        const int min_blocks = std::max(1, (int)((64u << 20) / (row_elems * 4 * sizeof(float)) ));  // >= 64 MB per copy
+        int copied_blocks = 0;
+        while (copied_blocks < tiles_y) {
+            const bool finished = cudaStreamQuery(s_comp) == cudaSuccess;
+            if (finished && t_trace == 0.0) t_trace = now_s() - t0;
+            HZB_CUDA(cudaMemcpyAsync(h_done, d_done.p, (size_t)tiles_y * sizeof(unsigned int), cudaMemcpyDeviceToHost, s_copy));
+            HZB_CUDA(cudaStreamSynchronize(s_copy));
+            int ready = copied_blocks;
+            while (ready < tiles_y && h_done[ready] == (unsigned int)tiles_x) ++ready;
+            if (finished && ready < tiles_y) {
+                cudaError_t e = cudaGetLastError();
+                set_error(std::string("horizon kernel ended with unfinished rows") + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : ""));
+                return 1;
+            }
+            if (ready - copied_blocks >= min_blocks || (ready == tiles_y && ready > copied_blocks)) {
+                const size_t r0 = (size_t)copied_blocks * 4, r1 = std::min<size_t>((size_t)ready * 4, (size_t)dim_in_0);
+                const double tc = now_s();
+                HZB_CUDA(cudaMemcpyAsync(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float),
+                                         cudaMemcpyDeviceToHost, s_copy));
+                HZB_CUDA(cudaStreamSynchronize(s_copy));
+                t_d2h += now_s() - tc;
+                copied_blocks = ready;
+            } else {
+                struct timespec ts = {0, 2000000};  // 2 ms
+                nanosleep(&ts, nullptr);
+            }
+        }
+        HZB_CUDA(cudaStreamSynchronize(s_comp));
+        if (t_trace == 0.0) t_trace = now_s() - t0;
+    } else {
+        HZB_CUDA(cudaStreamSynchronize(s_comp));
+        t_trace = now_s() - t0;
+        const double tc = now_s();
+        HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
+        t_d2h = now_s() - tc;
+    }
+    HZB_CUDA(cudaGetLastError());
     HZB_TRY(read_counters(h->s, g_stats));
     g_stats.t_h2d += t_h2d_extra; g_stats.t_trace = t_trace; g_stats.t_d2h = t_d2h; g_stats.t_total = now_s() - t_start;
     return 0;

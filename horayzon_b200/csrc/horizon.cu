@@ -835,6 +835,11 @@ __global__ void __launch_bounds__(WQ_THREADS, 6) k_horizon_wq4(SceneView sv, Hor
             }
         }
         flush_counters(cnt, units, counters);
+        if (p.row_done) {  // publish: this tile's outputs are complete and visible
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) atomicAdd(p.row_done + ty, 1u);
+        }
     }
 }
 

@@ -143,7 +143,9 @@ def horizon_gridded(
 
     cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] hori_buffer = \
         np.empty((ny, nx, azim_num), dtype=np.float32)
-    hori_buffer.fill(np.nan)  # horizon.pyx:170-173
+    # The reference pre-fills NaN (horizon.pyx:170-173).  The native call writes every
+    # element (masked cells get hori_fill), so the 2 GB-scale fill pass is skipped and
+    # the pages are first touched by the overlapped device-to-host copy instead.
     cdef int rc = 0
     if ny > 0 and nx > 0:
         with nogil:
