@@ -662,21 +662,6 @@ struct Wq4Shared {
     unsigned int hitmask[WQ_WARPS];
 };
 
-__device__ __forceinline__ void wide_child_test(const uint4 r, unsigned int selnx, unsigned int selny, unsigned int selnz,
-                                                float Ax, float Ay, float Az, float Bx, float By, float Bz, float tfar,
-                                                float& tmin, bool& hit) {
-    const float M = 8388608.0f;
-    const float qnx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selnx)) - M;
-    const float qfx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selnx ^ 0x0022u)) - M;
-    const float qny = __uint_as_float(__byte_perm(r.y, 0x4B000000u, selny)) - M;
-    const float qfy = __uint_as_float(__byte_perm(r.y, 0x4B000000u, selny ^ 0x0022u)) - M;
-    const float qnz = __uint_as_float(__byte_perm(r.z, 0x4B000000u, selnz)) - M;
-    const float qfz = __uint_as_float(__byte_perm(r.z, 0x4B000000u, selnz ^ 0x0022u)) - M;
-    tmin = fmaxf(fmaxf(fmaf(qnx, Ax, Bx), fmaf(qny, Ay, By)), fmaxf(fmaf(qnz, Az, Bz), 0.0f));
-    const float tmax = fminf(fminf(fmaf(qfx, Ax, Bx), fmaf(qfy, Ay, By)), fminf(fmaf(qfz, Az, Bz), tfar));
-    hit = (tmin <= tmax * 1.000001f) && (r.w != WIDE_EMPTY);
-}
-
 template <int ALG>
 __global__ void __launch_bounds__(WQ_THREADS, 6) k_horizon_wq4(SceneView sv, HorizonParams p, Counters* counters,
                                                                unsigned int* tile_counter, int refill_thr, int wait_thr) {
