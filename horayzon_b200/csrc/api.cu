@@ -192,7 +192,7 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
     // hide behind the traversal.
     t0 = now_s();
     const int tiles_x = (dim_in_1 + 7) / 8, tiles_y = (dim_in_0 + 3) / 4;
-    const bool overlap = getenv("HZB_NO_OVERLAP") == nullptr && !(getenv("HZB_KERNEL") && strcmp(getenv("HZB_KERNEL"), "wq4"));
+    const bool overlap = getenv("HZB_NO_OVERLAP") == nullptr && !(getenv("HZB_KERNEL") && !strcmp(getenv("HZB_KERNEL"), "simple"));
     cudaStream_t s_comp = nullptr, s_copy = nullptr;
     HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));

@@ -7,6 +7,7 @@
 // refraction branch evaluates the libm calls in double and rounds once (the
 // closest available stand-in for glibc's float functions).
 #include "hzb_geom.cuh"
+#include "hzb_wq.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -107,24 +108,13 @@ __global__ void __launch_bounds__(128) k_terrain(SceneView sv, TerrainParams tp,
 
 
 // ---------------------------------------------------------------------------
-// Production kernel: persistent warps, one lane per cell, warp-queue traversal
-// of the compressed 4-wide BVH (same scheme as k_horizon_wq4 in horizon.cu):
-// lanes refill with the next cell of the warp's block as soon as their ray
-// retires; leaf candidates of all lanes are tested 32 at a time.
+// Production kernel: persistent warps, one lane per cell, the shared warp-queue
+// traversal of the compressed 4-wide BVH (hzb_wq.cuh): lanes refill with the
+// next cell of the warp's block as soon as their ray retires; leaf candidates
+// of all lanes are tested 32 at a time.  (k_terrain above is the reference-
+// shaped per-lane kernel on the binary BVH, HZB_SHADOW_KERNEL=simple.)
 // ---------------------------------------------------------------------------
-constexpr int TW_THREADS = 128;
-constexpr int TW_WARPS = TW_THREADS / 32;
-constexpr int TW_STACK = 40;
-constexpr int TW_RING = 256;
 constexpr int TW_BLOCK = 512;   // cells per warp work block
-constexpr uint32_t TW_NONE = 0xFFFFFFFFu;
-
-struct TwShared {
-    uint32_t stack[TW_STACK][TW_THREADS];
-    uint2 ring[TW_WARPS][TW_RING];
-    float ray[TW_WARPS][6][32];
-    unsigned int hitmask[TW_WARPS];
-};
 
 // Sun vector, self-shading test and ray set-up for one cell (shadow_comp.cpp:397-451 / 507-561).
 // Returns true if an occlusion ray must be cast.
@@ -164,44 +154,41 @@ __device__ __forceinline__ bool terrain_cell_setup(const SceneView& sv, const Te
 }
 
 template <bool SW>
-__global__ void __launch_bounds__(TW_THREADS, 6) k_terrain_wq4(SceneView sv, TerrainParams tp, float sunx, float suny, float sunz,
-                                                               uint8_t* __restrict__ shadow, float* __restrict__ swc,
-                                                               Counters* counters, unsigned int* block_counter, int refill_thr,
-                                                               int wait_thr) {
-    __shared__ TwShared sh;
+__global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq(SceneView sv, TerrainParams tp, float sunx, float suny, float sunz,
+                                                            uint8_t* __restrict__ shadow, float* __restrict__ swc,
+                                                            Counters* counters, unsigned int* block_counter, int refill_thr,
+                                                            int wait_thr) {
+    __shared__ WqShared sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
     const unsigned int num_blocks = (unsigned int)((ncell + TW_BLOCK - 1) / TW_BLOCK);
     const float dot_min = SW ? tp.dot_prod_min : 0.0f;
-    const float tfar = INFINITY;
+    const float tfar = INFINITY;   // shadow_comp.cpp:462, 572
     unsigned int* overflow = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
     unsigned int units = 0;
-    uint2* ring = sh.ring[warp];
     if (lane == 0) sh.hitmask[warp] = 0u;
-    unsigned int pushed = 0, tested = 0;
+    WqWarp W; W.pushed = 0; W.tested = 0;
     __syncwarp();
 
     long long next = 0, end = 0;          // warp-uniform: unassigned cells of the current block
     bool more_blocks = true;
-    bool ray_active = false, ray_hit = false, have_queued = false;
     long long cell = -1; float dts = 0.f, dns = 0.f;
-    float Ax = 0.f, Ay = 0.f, Az = 0.f, Bx = 0.f, By = 0.f, Bz = 0.f;
-    unsigned int selnx = 0x7410u, selny = 0x7410u, selnz = 0x7410u;
-    uint32_t node = TW_NONE; int sp = 0; unsigned int my_last = 0;
+    WqLane L; L.state = 0; L.hit = false; L.queued = false; L.node = WQ_NONE; L.sp = 0; L.my_last = 0;
+    L.Ax = L.Ay = L.Az = L.Bx = L.By = L.Bz = 0.f; L.selnx = L.selny = L.selnz = 0x7410u;
 
     while (true) {
-        // (1) retire finished rays and hand out new cells
-        if (cell >= 0 && !ray_active) {   // ray finished: write the result (shadow_comp.cpp:468-472 / 578-586)
+        // (1) retire finished rays (shadow_comp.cpp:468-472 / 578-586) and hand out new cells
+        if (cell >= 0 && L.state == 0) {
             if (SW) {
-                if (ray_hit) swc[cell] = 0.0f;
+                if (L.hit) swc[cell] = 0.0f;
                 else { if (dns < dot_min) dns = dot_min; swc[cell] = __fmul_rn(__fdiv_rn(dts, dns), tp.surf_enl_fac[cell]); }
-            } else shadow[cell] = ray_hit ? 2 : 0;
+            } else shadow[cell] = L.hit ? 2 : 0;
             cell = -1;
         }
         while (true) {
-            const bool want = !ray_active;
+            const bool want = L.state == 0;
             const unsigned int wmask = __ballot_sync(FULL, want);
             if (wmask == 0u) break;
             if (next >= end) {
@@ -221,114 +208,19 @@ __global__ void __launch_bounds__(TW_THREADS, 6) k_terrain_wq4(SceneView sv, Ter
                     units++;
                     F3 org, sun;
                     if (terrain_cell_setup<SW>(sv, tp, mine, sunx, suny, sunz, org, sun, dts, dns)) {
-                        const RayInv inv = make_inv(sun);
-                        Ax = sv.qstep[0] * inv.ix; Ay = sv.qstep[1] * inv.iy; Az = sv.qstep[2] * inv.iz;
-                        Bx = (sv.qorg[0] - org.x) * inv.ix; By = (sv.qorg[1] - org.y) * inv.iy; Bz = (sv.qorg[2] - org.z) * inv.iz;
-                        selnx = inv.ix >= 0.f ? 0x7410u : 0x7432u;
-                        selny = inv.iy >= 0.f ? 0x7410u : 0x7432u;
-                        selnz = inv.iz >= 0.f ? 0x7410u : 0x7432u;
-                        sh.ray[warp][0][lane] = org.x; sh.ray[warp][1][lane] = org.y; sh.ray[warp][2][lane] = org.z;
-                        sh.ray[warp][3][lane] = sun.x; sh.ray[warp][4][lane] = sun.y; sh.ray[warp][5][lane] = sun.z;
-                        cell = mine; node = 0u; sp = 0; ray_active = true; ray_hit = false; have_queued = false; cnt.rays++;
+                        wq_start_ray(sv, sh, warp, lane, L, org, sun);
+                        cell = mine; cnt.rays++;
                     } else {
                         if (SW) swc[mine] = 0.0f; else shadow[mine] = 1;   // self-shaded (:474-478 / :588-592)
                     }
                 }
             }
         }
-        const unsigned int act_mask = __ballot_sync(FULL, ray_active);
-        if (act_mask == 0u) break;
+        if (__ballot_sync(FULL, L.state != 0) == 0u) break;
         const int thr = (more_blocks || next < end) ? refill_thr : 1;
         __syncwarp();
-
-        // (2) traversal (see k_horizon_wq4)
-        while (true) {
-            const bool do_node = ray_active && !ray_hit && node != TW_NONE;
-            bool lf0 = false, lf1 = false, lf2 = false, lf3 = false;
-            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-            if (do_node) {
-                const uint4* np = reinterpret_cast<const uint4*>(sv.nodes4 + node);
-                const uint4 r0 = __ldg(np), r1 = __ldg(np + 1), r2 = __ldg(np + 2), r3 = __ldg(np + 3);
-                cnt.nodes++;
-                float t0, t1, t2, t3; bool h0, h1, h2, h3;
-                wide_child_test(r0, selnx, selny, selnz, Ax, Ay, Az, Bx, By, Bz, tfar, t0, h0);
-                wide_child_test(r1, selnx, selny, selnz, Ax, Ay, Az, Bx, By, Bz, tfar, t1, h1);
-                wide_child_test(r2, selnx, selny, selnz, Ax, Ay, Az, Bx, By, Bz, tfar, t2, h2);
-                wide_child_test(r3, selnx, selny, selnz, Ax, Ay, Az, Bx, By, Bz, tfar, t3, h3);
-                w0 = r0.w; w1 = r1.w; w2 = r2.w; w3 = r3.w;
-                lf0 = h0 && (w0 & WIDE_LEAF); lf1 = h1 && (w1 & WIDE_LEAF); lf2 = h2 && (w2 & WIDE_LEAF); lf3 = h3 && (w3 & WIDE_LEAF);
-                const bool i0 = h0 && !(w0 & WIDE_LEAF), i1 = h1 && !(w1 & WIDE_LEAF), i2 = h2 && !(w2 & WIDE_LEAF), i3 = h3 && !(w3 & WIDE_LEAF);
-                const float k0 = i0 ? t0 : INFINITY, k1 = i1 ? t1 : INFINITY, k2 = i2 ? t2 : INFINITY, k3 = i3 ? t3 : INFINITY;
-                const float kmin = fminf(fminf(k0, k1), fminf(k2, k3));
-                const bool any_int = i0 || i1 || i2 || i3;
-                const int idx = (i0 && k0 == kmin) ? 0 : ((i1 && k1 == kmin) ? 1 : ((i2 && k2 == kmin) ? 2 : 3));
-                const uint32_t nearest = idx == 0 ? w0 : (idx == 1 ? w1 : (idx == 2 ? w2 : w3));
-                if (sp + 3 > TW_STACK) { if (any_int) atomicAdd(overflow, 1u); }
-                else {
-                    if (i0 && idx != 0) { sh.stack[sp][tid] = w0; ++sp; }
-                    if (i1 && idx != 1) { sh.stack[sp][tid] = w1; ++sp; }
-                    if (i2 && idx != 2) { sh.stack[sp][tid] = w2; ++sp; }
-                    if (i3 && idx != 3) { sh.stack[sp][tid] = w3; ++sp; }
-                }
-                if (any_int) node = nearest;
-                else if (sp > 0) { --sp; node = sh.stack[sp][tid]; }
-                else node = TW_NONE;
-            }
-            {
-                const unsigned int m0 = __ballot_sync(FULL, lf0), m1 = __ballot_sync(FULL, lf1);
-                const unsigned int m2 = __ballot_sync(FULL, lf2), m3 = __ballot_sync(FULL, lf3);
-                unsigned int base = pushed;
-                if (lf0) { const unsigned int q = base + __popc(m0 & lt_mask); ring[q & (TW_RING - 1)] = make_uint2(w0 & 0x7FFFFFFFu, lane); my_last = q; have_queued = true; }
-                base += __popc(m0);
-                if (lf1) { const unsigned int q = base + __popc(m1 & lt_mask); ring[q & (TW_RING - 1)] = make_uint2(w1 & 0x7FFFFFFFu, lane); my_last = q; have_queued = true; }
-                base += __popc(m1);
-                if (lf2) { const unsigned int q = base + __popc(m2 & lt_mask); ring[q & (TW_RING - 1)] = make_uint2(w2 & 0x7FFFFFFFu, lane); my_last = q; have_queued = true; }
-                base += __popc(m2);
-                if (lf3) { const unsigned int q = base + __popc(m3 & lt_mask); ring[q & (TW_RING - 1)] = make_uint2(w3 & 0x7FFFFFFFu, lane); my_last = q; have_queued = true; }
-                pushed = base + __popc(m3);
-            }
-            {
-                const bool drained = !have_queued || (int)(tested - my_last) > 0;
-                const bool waiting = ray_active && (ray_hit || node == TW_NONE) && !drained;
-                const unsigned int wmask = __ballot_sync(FULL, waiting);
-                const unsigned int trav = __ballot_sync(FULL, ray_active && !ray_hit && node != TW_NONE);
-                unsigned int avail = pushed - tested;
-                bool flush = avail > 0u && (__popc(wmask) >= wait_thr || trav == 0u);
-                __syncwarp();
-                while (avail >= 32u || flush) {
-                    const unsigned int nb = min(avail, 32u);
-                    bool hit = false; unsigned int owner = 0;
-                    if ((unsigned int)lane < nb) {
-                        const uint2 e = ring[(tested + lane) & (TW_RING - 1)];
-                        owner = e.y;
-                        const F3 O = f3(sh.ray[warp][0][owner], sh.ray[warp][1][owner], sh.ray[warp][2][owner]);
-                        const F3 D = f3(sh.ray[warp][3][owner], sh.ray[warp][4][owner], sh.ray[warp][5][owner]);
-                        float tf = tfar;
-                        hit = prim_hit<false>(sv, e.x, O, D, tf);
-                        cnt.prims++;
-                    }
-                    if (hit) atomicOr(&sh.hitmask[warp], 1u << owner);
-                    tested += nb; avail -= nb; flush = false;
-                    __syncwarp();
-                }
-                const unsigned int hm = sh.hitmask[warp];
-                if ((hm >> lane) & 1u) ray_hit = true;
-                __syncwarp();
-                if (hm != 0u && lane == 0) sh.hitmask[warp] = 0u;
-            }
-            {
-                const bool drained = !have_queued || (int)(tested - my_last) > 0;
-                if (ray_active && (ray_hit || node == TW_NONE) && drained) ray_active = false;
-            }
-            if (__popc(__ballot_sync(FULL, ray_active)) < thr) break;
-        }
-    }
-    // final results of lanes that retired in the last traversal round were written at loop top? No: write them here.
-    if (cell >= 0 && !ray_active) {
-        if (SW) {
-            if (ray_hit) swc[cell] = 0.0f;
-            else { if (dns < dot_min) dns = dot_min; swc[cell] = __fmul_rn(__fdiv_rn(dts, dns), tp.surf_enl_fac[cell]); }
-        } else shadow[cell] = ray_hit ? 2 : 0;
+        // (2) shared warp-queue traversal (hzb_wq.cuh)
+        while (__popc(wq_step<false>(sv, sh, nullptr, 0u, warp, lane, tid, L, W, tfar, wait_thr, cnt, overflow)) >= thr) {}
     }
     unsigned int r = cnt.rays, n = cnt.nodes, pp = cnt.prims, u = units;
     for (int o = 16; o > 0; o >>= 1) {
@@ -346,11 +238,11 @@ __global__ void __launch_bounds__(TW_THREADS, 6) k_terrain_wq4(SceneView sv, Ter
 int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* d_out, cudaStream_t st) {
     const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
     if (ncell <= 0) return 0;
-    static const bool simple = getenv("HZB_SHADOW_KERNEL") && !strcmp(getenv("HZB_SHADOW_KERNEL"), "simple");
+    const bool simple = getenv("HZB_SHADOW_KERNEL") && !strcmp(getenv("HZB_SHADOW_KERNEL"), "simple");
     if (simple) k_terrain<false><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters);
     else {
         HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-        k_terrain_wq4<false><<<sm_count() * 6, TW_THREADS, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 6);
+        k_terrain_wq<false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 6);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;
@@ -358,11 +250,11 @@ int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* 
 int launch_sw_dir_cor(Scene& s, const TerrainParams& tp, const float* sun, float* d_out, cudaStream_t st) {
     const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
     if (ncell <= 0) return 0;
-    static const bool simple = getenv("HZB_SHADOW_KERNEL") && !strcmp(getenv("HZB_SHADOW_KERNEL"), "simple");
+    const bool simple = getenv("HZB_SHADOW_KERNEL") && !strcmp(getenv("HZB_SHADOW_KERNEL"), "simple");
     if (simple) k_terrain<true><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters);
     else {
         HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-        k_terrain_wq4<true><<<sm_count() * 6, TW_THREADS, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 6);
+        k_terrain_wq<true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 6);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;

@@ -47,6 +47,34 @@ def test_horizon_gridded_cfg1(mods, alg):
     assert st["units"] == c["ny"] * c["nx"] * c["azim_num"]
 
 
+@pytest.mark.parametrize("env", [{"HZB_KERNEL": "simple"}, {"HZB_TOPSMEM": "1"}, {"HZB_NO_OVERLAP": "1"},
+                                 {"HZB_WREFILL": "32", "HZB_WWAIT": "1"}])
+def test_horizon_kernel_variants_agree(mods, monkeypatch, env):
+    """The reference-shaped per-lane kernel (binary BVH), the TMA-staged variant,
+    the non-overlapped host path and other scheduling thresholds must all give
+    the oracle's bits: decisions do not depend on traversal order or BVH layout."""
+    hb, oracle = mods
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c, args = _cfg(hb, "cfg1")
+    h_gpu, _ = hb.horizon.horizon_gridded(*args, azim_num=c["azim_num"])
+    h_cpu, _ = oracle.horizon_gridded(*args, azim_num=c["azim_num"])
+    _assert_same(h_gpu, h_cpu, "variant %s" % env)
+
+
+def test_shadow_kernel_variants_agree(mods, monkeypatch):
+    hb, oracle = mods
+    vg, n, rim, tilt, norm, enl, elev, mask = _terrain_inputs(hb)
+    t = hb.shadow.Terrain()
+    t.initialise(vg, n, n, rim, rim, tilt, norm, enl, elev, mask)
+    sun = hb.synthetic.sun_positions_diurnal(8)[2]
+    a = np.empty(mask.shape, np.uint8); b = np.empty(mask.shape, np.uint8)
+    t.shadow(sun, a)
+    monkeypatch.setenv("HZB_SHADOW_KERNEL", "simple")
+    t.shadow(sun, b)
+    assert np.array_equal(a, b)
+
+
 def test_horizon_gridded_cfg2_shrunk(mods):
     hb, oracle = mods
     c, args = _cfg(hb, "cfg2", n=301)
