@@ -347,27 +347,54 @@ int hzb_terrain_sw_dir_cor_dev(hzb_terrain* t, const float* sun, float* d_out, v
     HZB_CUDA(cudaSetDevice(t->s.device));
     return launch_sw_dir_cor(t->s, t->tp, sun, d_out, (cudaStream_t)stream);
 }
-int hzb_terrain_shadow_batch(hzb_terrain* t, const float* suns, int n_sun, uint8_t* out) {
+}  // extern "C"
+
+// n_sun positions: kernel k runs on one stream while the result of position k-1 is
+// copied to the caller's array on another (D2H and its page faults hide behind compute).
+template <typename T, typename Launch>
+static int terrain_batch(hzb_terrain* t, const float* suns, int n_sun, T* out, Launch launch) {
     if (!t || !t->ready) { set_error("terrain not initialised"); return 1; }
     if (n_sun <= 0) return 0;
     const size_t nc = (size_t)t->tp.dim_in_0 * t->tp.dim_in_1;
     HZB_CUDA(cudaSetDevice(t->s.device));
-    HZB_TRY(terrain_out(t, nc * (size_t)n_sun));
-    for (int k = 0; k < n_sun; ++k)
-        HZB_TRY(launch_shadow(t->s, t->tp, suns + 3 * k, (uint8_t*)t->d_out + nc * k, nullptr));
-    HZB_CUDA(cudaMemcpy(out, t->d_out, nc * (size_t)n_sun, cudaMemcpyDeviceToHost));
+    const int nbuf = n_sun > 1 ? 2 : 1;
+    HZB_TRY(terrain_out(t, nc * sizeof(T) * nbuf));
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+    cudaEvent_t done[2], freed[2];
+    for (int b = 0; b < 2; ++b) { cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming); }
+    struct Guard { cudaStream_t a, b; cudaEvent_t* d; cudaEvent_t* f; ~Guard() { cudaStreamDestroy(a); cudaStreamDestroy(b); for (int i = 0; i < 2; ++i) { cudaEventDestroy(d[i]); cudaEventDestroy(f[i]); } } } guard{s_comp, s_copy, done, freed};
+    int rc = 0;
+    for (int k = 0; k <= n_sun && rc == 0; ++k) {
+        if (k < n_sun) {
+            const int b = k % nbuf;
+            if (k >= nbuf) cudaStreamWaitEvent(s_comp, freed[b], 0);       // buffer b was copied out
+            rc = launch(t, suns + 3 * k, (T*)t->d_out + nc * b, s_comp);
+            cudaEventRecord(done[b], s_comp);
+        }
+        if (k >= 1 && rc == 0) {
+            const int b = (k - 1) % nbuf;
+            cudaStreamWaitEvent(s_copy, done[b], 0);
+            if (cudaMemcpyAsync(out + nc * (size_t)(k - 1), (T*)t->d_out + nc * b, nc * sizeof(T), cudaMemcpyDeviceToHost, s_copy) != cudaSuccess) rc = 1;
+            cudaEventRecord(freed[b], s_copy);
+            if (cudaStreamSynchronize(s_copy) != cudaSuccess) rc = 1;       // pageable destination: host-synchronous anyway
+        }
+    }
+    cudaStreamSynchronize(s_comp);
+    if (rc) { if (g_error.empty()) set_error("terrain batch failed"); cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) set_error(cudaGetErrorString(e)); return 1; }
+    HZB_CUDA(cudaGetLastError());
     return 0;
 }
+extern "C" {
+
+int hzb_terrain_shadow_batch(hzb_terrain* t, const float* suns, int n_sun, uint8_t* out) {
+    return terrain_batch<uint8_t>(t, suns, n_sun, out, [](hzb_terrain* tt, const float* sun, uint8_t* d, cudaStream_t st) {
+        return launch_shadow(tt->s, tt->tp, sun, d, st); });
+}
 int hzb_terrain_sw_dir_cor_batch(hzb_terrain* t, const float* suns, int n_sun, float* out) {
-    if (!t || !t->ready) { set_error("terrain not initialised"); return 1; }
-    if (n_sun <= 0) return 0;
-    const size_t nc = (size_t)t->tp.dim_in_0 * t->tp.dim_in_1;
-    HZB_CUDA(cudaSetDevice(t->s.device));
-    HZB_TRY(terrain_out(t, nc * (size_t)n_sun * sizeof(float)));
-    for (int k = 0; k < n_sun; ++k)
-        HZB_TRY(launch_sw_dir_cor(t->s, t->tp, suns + 3 * k, (float*)t->d_out + nc * k, nullptr));
-    HZB_CUDA(cudaMemcpy(out, t->d_out, nc * (size_t)n_sun * sizeof(float), cudaMemcpyDeviceToHost));
-    return 0;
+    return terrain_batch<float>(t, suns, n_sun, out, [](hzb_terrain* tt, const float* sun, float* d, cudaStream_t st) {
+        return launch_sw_dir_cor(tt->s, tt->tp, sun, d, st); });
 }
 int hzb_terrain_shadow(hzb_terrain* t, const float* sun, uint8_t* out) { return hzb_terrain_shadow_batch(t, sun, 1, out); }
 int hzb_terrain_sw_dir_cor(hzb_terrain* t, const float* sun, float* out) { return hzb_terrain_sw_dir_cor_batch(t, sun, 1, out); }

@@ -114,6 +114,7 @@ struct Scene {
     std::vector<Tri> tris;
     std::vector<BNode> nodes;
     std::vector<int> order;  // triangle permutation referenced by leaves
+    std::vector<Tri> ltris;  // triangles in leaf order (filled by build(); leaves index this directly)
     float pad = 0.f;
     double build_s = 0.0;
 
@@ -212,6 +213,9 @@ struct Scene {
 #pragma omp single
             build_rec(0, (int)n, cen);
         }
+        ltris.resize(n);
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < (long long)n; ++k) ltris[k] = tris[order[k]];
         build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
 
@@ -243,15 +247,23 @@ struct Scene {
         }
         if (nodes.empty()) return false;
         float inv[3]; safe_inv(D, inv);
+        float tn;
+        if (!slab(nodes[0], O, inv, tfar, &tn)) return false;
         int stack[128], sp = 0; stack[sp++] = 0;
-        while (sp) {
+        while (sp) {   // every node on the stack has already passed its box test; near child first
             const BNode& nd = nodes[stack[--sp]];
-            float tn;
-            if (!slab(nd, O, inv, tfar, &tn)) continue;
             if (nd.left < 0) {
                 for (int k = 0; k < nd.count; ++k)
-                    if (tri_hit(tris[order[nd.first + k]], O, D, tfar, &t)) return true;
-            } else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+                    if (tri_hit(ltris[nd.first + k], O, D, tfar, &t)) return true;
+            } else {
+                float tl, tr;
+                const bool hl = slab(nodes[nd.left], O, inv, tfar, &tl), hr = slab(nodes[nd.right], O, inv, tfar, &tr);
+                if (hl && hr) {
+                    if (tl <= tr) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+                    else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+                } else if (hl) stack[sp++] = nd.left;
+                else if (hr) stack[sp++] = nd.right;
+            }
         }
         return false;
     }
@@ -273,8 +285,16 @@ struct Scene {
                 if (!slab(nd, O, inv, best, &tn)) continue;
                 if (nd.left < 0) {
                     for (int k = 0; k < nd.count; ++k)
-                        if (tri_hit(tris[order[nd.first + k]], O, D, best, &t)) { best = t; any = true; }
-                } else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+                        if (tri_hit(ltris[nd.first + k], O, D, best, &t)) { best = t; any = true; }
+                } else {
+                    float tl, tr;
+                    const bool hl = slab(nodes[nd.left], O, inv, best, &tl), hr = slab(nodes[nd.right], O, inv, best, &tr);
+                    if (hl && hr) {
+                        if (tl <= tr) { stack[sp++] = nd.right; stack[sp++] = nd.left; }
+                        else { stack[sp++] = nd.left; stack[sp++] = nd.right; }
+                    } else if (hl) stack[sp++] = nd.left;
+                    else if (hr) stack[sp++] = nd.right;
+                }
             }
         }
         *dist = best; return any;
@@ -468,7 +488,9 @@ int orc_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
     Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
     uint64_t rays = 0;
     auto t0 = std::chrono::steady_clock::now();
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : rays)
+    // rows in parallel like the reference's tbb::blocked_range over dim_in_0 (:739-744);
+    // collapse(2) so that a bounded row sample still occupies every core
+#pragma omp parallel for collapse(2) schedule(dynamic, 8) reduction(+ : rays)
     for (int i = 0; i < dim_in_0; ++i) {
         for (int j = 0; j < dim_in_1; ++j) {
             const size_t c = (size_t)i * dim_in_1 + j;
@@ -632,7 +654,7 @@ static void terrain_pass(const OrcTerrain& t, const float* sunpos, uint8_t* shad
     const float dot_min = SW ? cosf(deg2rad_f(t.ang_max)) : 0.0f;  // :498
     const float inf = std::numeric_limits<float>::infinity();
     auto t0 = std::chrono::steady_clock::now();
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for collapse(2) schedule(dynamic, 64)
     for (int i = 0; i < t.ny; ++i)
         for (int j = 0; j < t.nx; ++j) {
             const size_t c = (size_t)i * t.nx + j;
