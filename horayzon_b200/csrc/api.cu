@@ -217,7 +217,7 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
             HZB_CUDA(cudaMemcpyAsync(h_done, d_done.p, (size_t)tiles_y * sizeof(unsigned int), cudaMemcpyDeviceToHost, s_copy));
             HZB_CUDA(cudaStreamSynchronize(s_copy));
             int ready = copied_blocks;
-            while (ready < tiles_y && h_done[ready] == (unsigned int)tiles_x) ++ready;
+            while (ready < tiles_y && h_done[ready] == (unsigned int)tiles_x * 32u) ++ready;   // counts cells (32 per tile)
             if (finished && ready < tiles_y) {
                 cudaError_t e = cudaGetLastError();
                 set_error(std::string("horizon kernel ended with unfinished rows") + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : ""));

@@ -373,67 +373,88 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
     if (TOPS) wq_tma_stage_top(top_nodes, sv.nodes4, n_top, &top_mbar);
     const Search s = make_search(sv, p, counters);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
-    const unsigned int FULL = 0xffffffffu;
+    const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     const int rows = p.row_end - p.row_begin;
     const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
     const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int units = 0;
     if (lane == 0) sh.hitmask[warp] = 0u;
     WqWarp W; W.pushed = 0; W.tested = 0;
     __syncwarp();
 
+    // warp-uniform work source: cells of the current 8x4 tile are handed to lanes one by
+    // one; when the tile is used up the warp pulls the next tile from the global queue
+    unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
+    // per-lane cell and search state
+    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
+    Frame f; OutBuf ob; ob.init(nullptr, false);
+    bool has_cell = false, have_result = false;
+    int my_ty = 0;
+    WqLane L; L.state = 0; L.hit = false; L.queued = false; L.node = WQ_NONE; L.sp = 0; L.my_last = 0;
+    L.Ax = L.Ay = L.Az = L.Bx = L.By = L.Bz = 0.f; L.selnx = L.selny = L.selnz = 0x7410u;
+
     while (true) {
-        unsigned int tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= num_tiles) break;
-        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int ci = p.row_begin + ty * 4 + (lane >> 3), cj = tx * 8 + (lane & 7);
-
-        LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
-        Frame f; OutBuf ob; ob.init(nullptr, false);
-        bool has_cell = false, have_result = false;
-        unsigned int units = 0;
-        if (ci < p.row_end && cj < p.dim_in_1) {
-            const size_t c = (size_t)ci * p.dim_in_1 + cj;
-            float* out = p.hori + c * p.azim_num;
-            if (p.mask[c] == 1) {
-                const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
-                const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
-                const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
-                f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
-                ob.init(out, vec);
-                has_cell = true; units = p.azim_num;
-            } else {
-                for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
-            }
-        }
-        WqLane L; L.state = 0; L.hit = false; L.queued = false; L.node = WQ_NONE; L.sp = 0; L.my_last = 0;
-        L.Ax = L.Ay = L.Az = L.Bx = L.By = L.Bz = 0.f; L.selnx = L.selny = L.selnz = 0x7410u;
-
+        // (A) hand out cells to lanes that have none
         while (true) {
-            // refill: lanes with a cell but no ray in flight advance their search
-            if (has_cell && L.state == 0) {
-                int ie;
-                if (sm_advance<ALG>(s, m, have_result, L.hit, ob, ie)) {
-                    wq_start_ray(sv, sh, warp, lane, L, f.org, ray_dir(s, f, ie, m.k));
-                    have_result = true; cnt.rays++;
-                } else has_cell = false;
+            const bool want = !has_cell;
+            const unsigned int wmask = __ballot_sync(FULL, want);
+            if (wmask == 0u) break;
+            if (next_cell >= 32) {
+                if (!more_tiles) break;
+                unsigned int t = 0;
+                if (lane == 0) t = atomicAdd(tile_counter, 1u);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= num_tiles) { more_tiles = false; break; }
+                cur_tile = t; next_cell = 0;
             }
-            const unsigned int cell_mask = __ballot_sync(FULL, has_cell);
-            if (cell_mask == 0u) break;
-            const int thr = min(refill_thr, __popc(cell_mask));
-            __syncwarp();
-            while (__popc(wq_step<TOPS>(sv, sh, top_nodes, n_top, warp, lane, tid, L, W, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
+            const int mine = next_cell + __popc(wmask & lt_mask);
+            next_cell += __popc(wmask);
+            if (want && mine < 32) {
+                const int ty = cur_tile / tiles_x, tx = cur_tile - ty * tiles_x;
+                const int ci = p.row_begin + ty * 4 + (mine >> 3), cj = tx * 8 + (mine & 7);
+                bool done_now = true;
+                if (ci < p.row_end && cj < p.dim_in_1) {
+                    const size_t c = (size_t)ci * p.dim_in_1 + cj;
+                    float* out = p.hori + c * p.azim_num;
+                    if (p.mask[c] == 1) {
+                        const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
+                        const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
+                        const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
+                        f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+                        ob.init(out, vec);
+                        m.phase = 0; m.k = 0;
+                        has_cell = true; have_result = false; my_ty = ty; units += p.azim_num;
+                        done_now = false;
+                    } else {
+                        for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+                    }
+                }
+                if (done_now && p.row_done) { __threadfence_system(); atomicAdd(p.row_done + ty, 1u); }
+            }
         }
-        flush_counters(cnt, units, counters);
-        if (p.row_done) {  // publish: this tile's outputs are complete and visible
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) atomicAdd(p.row_done + ty, 1u);
+        // (B) lanes with a cell but no ray in flight advance their search
+        bool finished_cell = false;
+        if (has_cell && L.state == 0) {
+            int ie;
+            if (sm_advance<ALG>(s, m, have_result, L.hit, ob, ie)) {
+                wq_start_ray(sv, sh, warp, lane, L, f.org, ray_dir(s, f, ie, m.k));
+                have_result = true; cnt.rays++;
+            } else {
+                has_cell = false; finished_cell = true;
+                if (p.row_done) { __threadfence_system(); atomicAdd(p.row_done + my_ty, 1u); }  // this cell's outputs are visible
+            }
         }
+        if (__any_sync(FULL, finished_cell) && (more_tiles || next_cell < 32)) continue;   // give them a new cell first
+        const unsigned int cell_mask = __ballot_sync(FULL, has_cell);
+        if (cell_mask == 0u) break;
+        const int thr = min(refill_thr, __popc(cell_mask));
+        __syncwarp();
+        // (C) shared traversal loop
+        while (__popc(wq_step<TOPS>(sv, sh, top_nodes, n_top, warp, lane, tid, L, W, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
     }
+    flush_counters(cnt, units, counters);
 }
 
 // ---- arbitrary locations (horizon_comp.cpp:828-1094)

@@ -126,7 +126,7 @@ struct HorizonParams {
     int offset_0, offset_1, dim_in_0, dim_in_1, row_begin, row_end;
     float hori_fill, ray_org_elev;
     float* hori;
-    unsigned int* row_done;  // optional [ceil(rows/4)]: +1 per finished 8x4 tile of that row block (host overlaps D2H)
+    unsigned int* row_done;  // optional [ceil(rows/4)]: +1 per finished cell slot of that row block, 32 per 8x4 tile (host overlaps D2H)
 };
 
 int parse_algorithm(const char* s);  // -1 if unknown
