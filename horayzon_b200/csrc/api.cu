@@ -427,6 +427,25 @@ static int integral_host(int kind, const float* azim, const float* hori, const f
     HZB_CUDA(cudaMemcpy(out, d_o.p, nc * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }
+static int slope_host(int method, const float* x, const float* y, const float* z, const float* rot, int ny, int nx, int output_rot, float* out) {
+    if (require_device()) return 1;
+    if (ny < 0 || nx < 0) { set_error("invalid dimensions"); return 1; }
+    const size_t n = (size_t)ny * nx;
+    if (n == 0) return 0;
+    DevBuf<float> dx, dy, dz, dr, d_o;
+    HZB_TRY(dx.upload(x, n)); HZB_TRY(dy.upload(y, n)); HZB_TRY(dz.upload(z, n));
+    if (rot) HZB_TRY(dr.upload(rot, n * 9));
+    HZB_TRY(d_o.alloc(n * 3));
+    HZB_TRY(launch_slope(method, dx.p, dy.p, dz.p, rot ? dr.p : nullptr, ny, nx, output_rot, d_o.p, nullptr));
+    HZB_CUDA(cudaMemcpy(out, d_o.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+int hzb_slope_plane_meth(const float* x, const float* y, const float* z, const float* rot, int ny, int nx, int output_rot, float* out) {
+    return slope_host(0, x, y, z, rot, ny, nx, output_rot, out);
+}
+int hzb_slope_vector_meth(const float* x, const float* y, const float* z, const float* rot, int ny, int nx, int output_rot, float* out) {
+    return slope_host(1, x, y, z, rot, ny, nx, output_rot, out);
+}
 int hzb_sky_view_factor(const float* azim, const float* hori, const float* tilt, int ny, int nx, int K, float* out) {
     return integral_host(0, azim, hori, tilt, ny, nx, K, out);
 }

@@ -157,6 +157,9 @@ int launch_sw_dir_cor(Scene& s, const TerrainParams& tp, const float* sun_xyz /*
 int launch_svf(int kind, const float* d_azim, const float* d_hori, const float* d_tilt, long long cells,
                int K, float* d_out, cudaStream_t st);
 
+int launch_slope(int method, const float* d_x, const float* d_y, const float* d_z, const float* d_rot, int ny, int nx,
+                 int output_rot, float* d_out, cudaStream_t st);
+
 // number of SMs of the current device (cached)
 int sm_count();
 

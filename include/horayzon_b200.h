@@ -128,6 +128,14 @@ int hzb_visible_sky_fraction(const float* azim, const float* hori, const float* 
 int hzb_topographic_openness(const float* azim, const float* hori,
                              int ny, int nx, int K, float* out);
 
+/* "Next" row 8f-1: tilted-surface normals on the device.  Replace _slope_plane_meth_cy /
+ * _slope_vector_meth_cy (topo_param.pyx:84-225, 284-372).  x, y, z: [ny][nx]; rot_mat:
+ * [ny][nx][3][3] or NULL (identity / none); out: [ny][nx][3], border cells NaN. */
+int hzb_slope_plane_meth(const float* x, const float* y, const float* z, const float* rot_mat,
+                         int ny, int nx, int output_rot, float* out);
+int hzb_slope_vector_meth(const float* x, const float* y, const float* z, const float* rot_mat,
+                          int ny, int nx, int output_rot, float* out);
+
 /* ----------------------------------------------------------- resident tier */
 
 /* A scene = DEM vertices (+ optional TIN) and their BVH, resident on `device`.

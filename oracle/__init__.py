@@ -206,3 +206,23 @@ def visible_sky_fraction(azim, hori, vec_tilt):
 
 def topographic_openness(azim, hori):
     return _integral(lib().orc_topographic_openness, azim, hori, None)
+
+
+def _slope(fn, x, y, z, rot_mat, output_rot):
+    x, y, z = (np.ascontiguousarray(a, np.float32) for a in (x, y, z))
+    ny, nx = x.shape
+    out = np.empty((ny, nx, 3), np.float32)
+    rm = None if rot_mat is None else np.ascontiguousarray(rot_mat, np.float32)
+    _check(fn(_p(x, _f32p), _p(y, _f32p), _p(z, _f32p), None if rm is None else _p(rm, _f32p), ny, nx,
+              int(bool(output_rot)), _p(out, _f32p)))
+    return out
+
+
+def slope_plane_meth(x, y, z, rot_mat=None, output_rot=False):
+    """Oracle twin of ``topo_param.slope_plane_meth`` (topo_param.pyx:16-225)."""
+    return _slope(lib().orc_slope_plane_meth, x, y, z, rot_mat, output_rot)
+
+
+def slope_vector_meth(x, y, z, rot_mat=None, output_rot=False):
+    """Oracle twin of ``topo_param.slope_vector_meth`` (topo_param.pyx:230-372)."""
+    return _slope(lib().orc_slope_vector_meth, x, y, z, rot_mat, output_rot)

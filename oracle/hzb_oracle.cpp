@@ -15,6 +15,7 @@
 // reference's own compiled topo_param.pyx (tests/golden/, oracle/build_ref.py).
 //
 // What follows the reference (file:line, relative to /root/reference/horayzon):
+//   slope (plane fit / 4-triangle average) topo_param.pyx:84-225, 284-372   [scope row 8f-1]
 //   unit conversion, trig tables ........ horizon_comp.cpp:36-44, 667-670, 711-731
 //   per-cell frame, origin, driver ...... horizon_comp.cpp:739-800
 //   discrete_sampling ................... horizon_comp.cpp:302-333
@@ -745,6 +746,104 @@ int orc_topographic_openness(const float* azim, const float* hori, int ny, int n
         for (int k = 0; k < K; ++k) agg = (float)(((double)agg + (M_PI / 2.0)) - (double)h[k]);
         out[c] = agg / (float)K;
     }
+    return 0;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Slope: tilted-surface normals.  Restates
+// _slope_plane_meth_cy (topo_param.pyx:84-225: 3x3 least-squares plane through the
+// 9 neighbours in a locally rotated frame; the reference solves the normal equations
+// with LAPACK sgesv = LU with partial pivoting, restated here in float) and
+// _slope_vector_meth_cy (:284-372: average of the 4 adjacent triangle normals).
+// rot_mat: [ny][nx][3][3] or NULL (identity).  Border cells are NaN like the reference.
+// ---------------------------------------------------------------------------
+extern "C" {
+
+static inline void solve3_partial_pivot(float A[3][3], float b[3]) {
+    for (int c = 0; c < 3; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < 3; ++r) if (fabsf(A[r][c]) > fabsf(A[piv][c])) piv = r;
+        if (piv != c) { for (int k = 0; k < 3; ++k) std::swap(A[c][k], A[piv][k]); std::swap(b[c], b[piv]); }
+        for (int r = c + 1; r < 3; ++r) {
+            const float f = A[r][c] / A[c][c];
+            for (int k = c; k < 3; ++k) A[r][k] -= f * A[c][k];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int r = 2; r >= 0; --r) {
+        float v = b[r];
+        for (int k = r + 1; k < 3; ++k) v -= A[r][k] * b[k];
+        b[r] = v / A[r][r];
+    }
+}
+
+int orc_slope_plane_meth(const float* x, const float* y, const float* z, const float* rot_mat, int ny, int nx,
+                         int output_rot, float* out) {
+    const float nanv = std::numeric_limits<float>::quiet_NaN();
+    for (size_t k = 0; k < (size_t)ny * nx * 3; ++k) out[k] = nanv;
+    const float ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma omp parallel for schedule(static)
+    for (int i = 1; i < ny - 1; ++i)
+        for (int j = 1; j < nx - 1; ++j) {
+            const size_t c = (size_t)i * nx + j;
+            const float* R = rot_mat ? rot_mat + 9 * c : ident;
+            float sx = 0, sy = 0, sz = 0, sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0;
+            for (int k = i - 1; k <= i + 1; ++k)
+                for (int l = j - 1; l <= j + 1; ++l) {
+                    const size_t q = (size_t)k * nx + l;
+                    const float dx = x[q] - x[c], dy = y[q] - y[c], dz = z[q] - z[c];
+                    const float lx = R[0] * dx + R[1] * dy + R[2] * dz;
+                    const float ly = R[3] * dx + R[4] * dy + R[5] * dz;
+                    const float lz = R[6] * dx + R[7] * dy + R[8] * dz;
+                    sx += lx; sy += ly; sz += lz;
+                    sxx += lx * lx; sxy += lx * ly; sxz += lx * lz; syy += ly * ly; syz += ly * lz;
+                }
+            float A[3][3] = {{sxx, sxy, sx}, {sxy, syy, sy}, {sx, sy, 9.0f}};
+            float b[3] = {sxz, syz, sz};
+            solve3_partial_pivot(A, b);
+            float vx = b[0], vy = b[1], vz = -1.0f;
+            const float mag = sqrtf(vx * vx + vy * vy + vz * vz);
+            vx /= mag; vy /= mag; vz /= mag;
+            if (vz < 0.0f) { vx = -vx; vy = -vy; vz = -vz; }
+            if (!output_rot) {  // back to the input frame: transpose of rot_mat (:208-223)
+                const float tx = R[0] * vx + R[3] * vy + R[6] * vz;
+                const float ty = R[1] * vx + R[4] * vy + R[7] * vz;
+                const float tz = R[2] * vx + R[5] * vy + R[8] * vz;
+                vx = tx; vy = ty; vz = tz;
+            }
+            out[3 * c] = vx; out[3 * c + 1] = vy; out[3 * c + 2] = vz;
+        }
+    return 0;
+}
+
+int orc_slope_vector_meth(const float* x, const float* y, const float* z, const float* rot_mat, int ny, int nx,
+                          int output_rot, float* out) {
+    const float nanv = std::numeric_limits<float>::quiet_NaN();
+    for (size_t k = 0; k < (size_t)ny * nx * 3; ++k) out[k] = nanv;
+#pragma omp parallel for schedule(static)
+    for (int i = 1; i < ny - 1; ++i)
+        for (int j = 1; j < nx - 1; ++j) {
+            const size_t c = (size_t)i * nx + j;
+            auto D = [&](size_t q, float* v) { v[0] = x[q] - x[c]; v[1] = y[q] - y[c]; v[2] = z[q] - z[c]; };
+            float a[3], b[3], cc[3], d[3];
+            D(c - 1, a); D(c + nx, b); D(c + 1, cc); D(c - nx, d);
+            float vx = ((a[1] * b[2] - a[2] * b[1]) + (b[1] * cc[2] - b[2] * cc[1]) + (cc[1] * d[2] - cc[2] * d[1]) + (d[1] * a[2] - d[2] * a[1])) / 4.0f;
+            float vy = ((a[2] * b[0] - a[0] * b[2]) + (b[2] * cc[0] - b[0] * cc[2]) + (cc[2] * d[0] - cc[0] * d[2]) + (d[2] * a[0] - d[0] * a[2])) / 4.0f;
+            float vz = ((a[0] * b[1] - a[1] * b[0]) + (b[0] * cc[1] - b[1] * cc[0]) + (cc[0] * d[1] - cc[1] * d[0]) + (d[0] * a[1] - d[1] * a[0])) / 4.0f;
+            const float mag = sqrtf(vx * vx + vy * vy + vz * vz);
+            vx /= mag; vy /= mag; vz /= mag;
+            if (vz < 0.0f) { vx = -vx; vy = -vy; vz = -vz; }
+            if (output_rot && rot_mat) {  // :354-370
+                const float* R = rot_mat + 9 * c;
+                const float tx = R[0] * vx + R[1] * vy + R[2] * vz;
+                const float ty = R[3] * vx + R[4] * vy + R[5] * vz;
+                const float tz = R[6] * vx + R[7] * vy + R[8] * vz;
+                vx = tx; vy = ty; vz = tz;
+            }
+            out[3 * c] = vx; out[3 * c + 1] = vy; out[3 * c + 2] = vz;
+        }
     return 0;
 }
 

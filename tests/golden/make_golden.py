@@ -38,6 +38,23 @@ def integral_inputs(seed, ny, nx, K):
     return azim, hori, tilt
 
 
+def slope_inputs(n=40, seed=9):
+    """Seeded DEM in a slightly rotated 'global' frame + per-cell rotation matrices."""
+    rng = np.random.default_rng(seed)
+    xs = np.arange(n, dtype=np.float64) * 30.0
+    X, Y = np.meshgrid(xs, xs)
+    Z = 200.0 * np.sin(X / 300.0) * np.cos(Y / 250.0) + rng.normal(0, 1.0, X.shape)
+    # rotate everything by small angles so that local up != z (as in global ENU far from the origin)
+    a, b = 0.03, -0.02
+    Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+    Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+    G = Rx @ Ry
+    P = np.stack([X, Y, Z], axis=-1) @ G.T
+    rot = np.broadcast_to(G.T.astype(np.float32), (n, n, 3, 3)).copy()   # global -> local
+    return (np.ascontiguousarray(P[..., 0].astype(np.float32)), np.ascontiguousarray(P[..., 1].astype(np.float32)),
+            np.ascontiguousarray(P[..., 2].astype(np.float32)), rot)
+
+
 def main():
     br = _load(os.path.join(ROOT, "oracle", "build_ref.py"), "build_ref")
     br.build()
@@ -50,6 +67,18 @@ def main():
         out[tag + "_vsf"] = np.asarray(tp.visible_sky_fraction(azim, hori, tilt))
         out[tag + "_top"] = np.asarray(tp.topographic_openness(azim, hori))
     np.savez_compressed(os.path.join(HERE, "integrals_ref.npz"), **out)
+
+    # slope: unmodified reference slope_plane_meth / slope_vector_meth on a seeded DEM,
+    # with identity and with per-cell rotation matrices (curved-grid style)
+    x, y, z, rot = slope_inputs()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        sl = {"plane_id": np.asarray(tp.slope_plane_meth(x, y, z)),
+              "plane_rot": np.asarray(tp.slope_plane_meth(x, y, z, rot_mat=rot, output_rot=False)),
+              "plane_rot_out": np.asarray(tp.slope_plane_meth(x, y, z, rot_mat=rot, output_rot=True)),
+              "vector_id": np.asarray(tp.slope_vector_meth(x, y, z)),
+              "vector_rot_out": np.asarray(tp.slope_vector_meth(x, y, z, rot_mat=rot, output_rot=True))}
+    np.savez_compressed(os.path.join(HERE, "slope_ref.npz"), **sl)
 
     import oracle
     syn = _load(os.path.join(ROOT, "horayzon_b200", "synthetic.py"), "synthetic")

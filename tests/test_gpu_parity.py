@@ -217,3 +217,28 @@ def test_integrals_against_oracle(mods):
         o = getattr(oracle, name)(*args)
         assert g.shape == o.shape and g.dtype == np.float32
         assert np.abs(g - o).max() <= 5e-6, name  # stated tolerance
+
+
+def test_slope_against_oracle_and_reference_golden(mods):
+    """Scope row 'next 1': slope on the device vs the oracle (<= 2e-6: same float
+    operation order, LU with partial pivoting) and vs the compiled reference's golden
+    vectors (<= 2e-5)."""
+    import os
+    hb, oracle = mods
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    x, y, z, rot = mg.slope_inputs()
+    g = np.load(os.path.join(gold, "slope_ref.npz"))
+    runs = {"plane_id": (hb.topo_param.slope_plane_meth, oracle.slope_plane_meth, dict()),
+            "plane_rot": (hb.topo_param.slope_plane_meth, oracle.slope_plane_meth, dict(rot_mat=rot, output_rot=False)),
+            "plane_rot_out": (hb.topo_param.slope_plane_meth, oracle.slope_plane_meth, dict(rot_mat=rot, output_rot=True)),
+            "vector_id": (hb.topo_param.slope_vector_meth, oracle.slope_vector_meth, dict()),
+            "vector_rot_out": (hb.topo_param.slope_vector_meth, oracle.slope_vector_meth, dict(rot_mat=rot, output_rot=True))}
+    for name, (f_gpu, f_cpu, kw) in runs.items():
+        a = f_gpu(x, y, z, **kw); b = f_cpu(x, y, z, **kw)
+        assert a.shape == b.shape == g[name].shape and a.dtype == np.float32
+        assert np.array_equal(np.isnan(a), np.isnan(b)), name
+        assert np.nanmax(np.abs(a - b)) <= 2e-6, (name, float(np.nanmax(np.abs(a - b))))
+        assert np.nanmax(np.abs(a - g[name])) <= 2e-5, name

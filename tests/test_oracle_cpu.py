@@ -194,3 +194,32 @@ def test_hemisphere_shadow_partition_and_energy_conservation():
         yy, xx = np.nonzero(code == 2)
         cx = x[rim:-rim, rim:-rim][yy, xx].mean(); cy = y[rim:-rim, rim:-rim][yy, xx].mean()
         assert cx * np.sin(a) + cy * np.cos(a) < 0.0
+
+
+def _slope_inputs():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    return mg.slope_inputs()
+
+
+def test_slope_matches_reference_golden():
+    """Oracle restatement of slope_plane_meth / slope_vector_meth vs the unmodified
+    compiled reference (tests/golden/slope_ref.npz).  The reference solves with LAPACK
+    sgesv and is built -ffast-math: unit-vector components agree to 2e-5."""
+    g = np.load(os.path.join(GOLD, "slope_ref.npz"))
+    x, y, z, rot = _slope_inputs()
+    cases = {"plane_id": oracle.slope_plane_meth(x, y, z),
+             "plane_rot": oracle.slope_plane_meth(x, y, z, rot_mat=rot, output_rot=False),
+             "plane_rot_out": oracle.slope_plane_meth(x, y, z, rot_mat=rot, output_rot=True),
+             "vector_id": oracle.slope_vector_meth(x, y, z),
+             "vector_rot_out": oracle.slope_vector_meth(x, y, z, rot_mat=rot, output_rot=True)}
+    for name, got in cases.items():
+        want = g[name]
+        assert got.shape == want.shape
+        assert np.array_equal(np.isnan(got), np.isnan(want)), name
+        assert np.nanmax(np.abs(got - want)) <= 2e-5, (name, float(np.nanmax(np.abs(got - want))))
+    # known answer (SURVEY.md 8c): z = 0.5 x  ->  (-0.4472136, 0, 0.8944272)
+    xs = np.arange(5, dtype=np.float32); X, Y = np.meshgrid(xs, xs)
+    v = oracle.slope_plane_meth(X, Y, (0.5 * X).astype(np.float32))[2, 2]
+    assert np.allclose(v, [-0.4472136, 0.0, 0.8944272], atol=1e-6)
