@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <chrono>
 
@@ -106,12 +107,44 @@ __device__ __forceinline__ unsigned long long expand21(unsigned int v) {
     return x;
 }
 
-__global__ void k_morton(PrimGeom g, uint32_t n, float lox, float loy, float loz, float inv_extent,
+__device__ __forceinline__ unsigned long long expand31(unsigned int v) {   // spread 31 bits to even positions
+    unsigned long long x = v & 0x7fffffffu;
+    x = (x | x << 16) & 0x0000ffff0000ffffull;
+    x = (x | x << 8) & 0x00ff00ff00ff00ffull;
+    x = (x | x << 4) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | x << 2) & 0x3333333333333333ull;
+    x = (x | x << 1) & 0x5555555555555555ull;
+    return x;
+}
+
+// mode 0: 3-D Morton code (21 bits per axis) of the box centre in the scene cube.
+// mode 1: 2-D Morton code (31 bits for x and y): for height fields the radix tree becomes a
+//         quadtree in the horizontal plane, which collapses into fuller 4-wide nodes.
+// mode 2: grid quads are keyed on their integer cell indices (i, j): the quadtree is aligned
+//         with the grid (2^k x 2^k blocks of cells), every 4-wide node is full.  Used when the
+//         scene has no TIN (TIN triangles have no cell index; then mode 1 is used for all).
+__global__ void k_morton(PrimGeom g, uint32_t n, float lox, float loy, float loz, float inv_extent, int mode,
                          unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     float lo[3], hi[3];
     prim_box(g, p, lo, hi);
+    if (mode == 2 && p < g.num_quads) {   // grid quad: key on the integer cell indices -> aligned quadtree
+        const uint32_t wq = (uint32_t)(g.W - 1);
+        const uint32_t qi = p / wq, qj = p - qi * wq;
+        keys[p] = (expand31(qj) << 1) | expand31(qi);
+        vals[p] = p;
+        return;
+    }
+    if (mode >= 1) {
+        const double s2 = 2147483648.0 * (double)inv_extent;  // 2^31 / square edge
+        const double fx2 = (0.5 * ((double)lo[0] + hi[0]) - lox) * s2, fy2 = (0.5 * ((double)lo[1] + hi[1]) - loy) * s2;
+        const unsigned int qx2 = (unsigned int)fmin(fmax(fx2, 0.0), 2147483647.0);
+        const unsigned int qy2 = (unsigned int)fmin(fmax(fy2, 0.0), 2147483647.0);
+        keys[p] = (expand31(qx2) << 1) | expand31(qy2);
+        vals[p] = p;
+        return;
+    }
     const float s = 2097152.0f * inv_extent;  // 2^21 / cube edge
     const float fx = (0.5f * (lo[0] + hi[0]) - lox) * s;
     const float fy = (0.5f * (lo[1] + hi[1]) - loy) * s;
@@ -292,18 +325,21 @@ __global__ void k_refit(PrimGeom g, const uint32_t* __restrict__ sorted_prims, u
     }
     uint32_t link = leaf_parent[i];
     int code = ~(int)prim;
+    int height = 0;   // height of the subtree carried upwards (leaf = 0); stored per child in pad0 / pad1
     while (true) {
         const uint32_t p = link >> 1, side = link & 1u;
         Bvh2Node* nd = nodes + p;
         float* blo = side ? nd->lo1 : nd->lo0;
         float* bhi = side ? nd->hi1 : nd->hi0;
         for (int a = 0; a < 3; ++a) { blo[a] = lo[a]; bhi[a] = hi[a]; }
-        if (side) nd->c1 = code; else nd->c0 = code;
+        if (side) { nd->c1 = code; nd->pad1 = height; } else { nd->c0 = code; nd->pad0 = height; }
         __threadfence();
         if (atomicAdd(&visit[p], 1u) == 0u) return;
         const volatile float* slo = side ? nd->lo0 : nd->lo1;
         const volatile float* shi = side ? nd->hi0 : nd->hi1;
         for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], slo[a]); hi[a] = fmaxf(hi[a], shi[a]); }
+        const volatile int* sh = side ? &nd->pad0 : &nd->pad1;
+        height = max(height, *sh) + 1;
         code = (int)p;
         link = node_parent[p];
         if (link == 0xffffffffu) {
@@ -391,7 +427,10 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
     PrimGeom g{s.d_vert4, s.d_tin4, W, s.num_quads};
     unsigned long long *d_k0 = nullptr, *d_k1 = nullptr; uint32_t *d_v0 = nullptr, *d_v1 = nullptr;
     HZB_TRY(dalloc(&d_k0, n)); HZB_TRY(dalloc(&d_k1, n)); HZB_TRY(dalloc(&d_v0, n)); HZB_TRY(dalloc(&d_v1, n));
-    k_morton<<<(n + 255) / 256, 256, 0, st>>>(g, n, s.lo[0], s.lo[1], s.lo[2], 1.0f / extent, d_k0, d_v0);
+    int morton_mode = getenv("HZB_MORTON") ? atoi(getenv("HZB_MORTON")) : 2;
+    if (morton_mode == 2 && s.num_tin > 0) morton_mode = 1;
+    const float extent_key = morton_mode >= 1 ? std::max(s.hi[0] - s.lo[0], s.hi[1] - s.lo[1]) : extent;
+    k_morton<<<(n + 255) / 256, 256, 0, st>>>(g, n, s.lo[0], s.lo[1], s.lo[2], 1.0f / std::max(extent_key, 1e-20f), morton_mode, d_k0, d_v0);
     HZB_CUDA(cudaGetLastError());
 
     const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;

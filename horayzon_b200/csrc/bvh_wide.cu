@@ -33,21 +33,26 @@ __global__ void k_collapse4(const Bvh2Node* __restrict__ nodes2, const uint32_t*
                             unsigned int* __restrict__ next_count, uint32_t next_base, QGrid g) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
-    int code[4]; float lo[4][3], hi[4][3];
+    int code[4], hgt[4]; float lo[4][3], hi[4][3];
     int n = 2;
     {
         const Bvh2Node nd = nodes2[frontier[t]];
-        code[0] = nd.c0; code[1] = nd.c1;
+        code[0] = nd.c0; code[1] = nd.c1; hgt[0] = nd.pad0; hgt[1] = nd.pad1;
         for (int a = 0; a < 3; ++a) { lo[0][a] = nd.lo0[a]; hi[0][a] = nd.hi0[a]; lo[1][a] = nd.lo1[a]; hi[1][a] = nd.hi1[a]; }
         if (nd.c0 == nd.c1 && nd.c0 < 0) n = 1;  // degenerate single-primitive scene
     }
+    // Absorb up to two binary nodes.  Only children of ODD height are absorbed, so that
+    // wide nodes sit at even heights above the leaves: the bottom wide level then holds
+    // four leaves per node instead of stranding two-leaf nodes whenever a subtree has an
+    // odd number of binary levels (1200 x 1200 quads: 2.6 -> ~4 children per node).
+    // Among the candidates the largest box goes first.
     for (int round = 0; round < 2 && n < 4; ++round) {
         int best = -1; float best_area = -1.f;
         for (int k = 0; k < n; ++k)
-            if (code[k] >= 0) { const float ar = box_area(lo[k], hi[k]); if (ar > best_area) { best_area = ar; best = k; } }
+            if (code[k] >= 0 && (hgt[k] & 1)) { const float ar = box_area(lo[k], hi[k]); if (ar > best_area) { best_area = ar; best = k; } }
         if (best < 0) break;
         const Bvh2Node nd = nodes2[code[best]];
-        code[best] = nd.c0; code[n] = nd.c1;
+        code[best] = nd.c0; code[n] = nd.c1; hgt[best] = nd.pad0; hgt[n] = nd.pad1;
         for (int a = 0; a < 3; ++a) { lo[best][a] = nd.lo0[a]; hi[best][a] = nd.hi0[a]; lo[n][a] = nd.lo1[a]; hi[n][a] = nd.hi1[a]; }
         ++n;
     }
