@@ -111,7 +111,7 @@ __device__ __forceinline__ unsigned int wq_step(const SceneView& sv, WqShared& s
     cnt.nodes += trav ? 1u : 0u;
     const unsigned int hm = trav ? ((h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u)) : 0u;
     const unsigned int lfm = (r0.w >> 31) | ((r1.w >> 31) << 1) | ((r2.w >> 31) << 2) | ((r3.w >> 31) << 3);
-    unsigned int lm = hm & lfm;
+    const unsigned int lm = hm & lfm;
     const unsigned int im = hm & ~lfm;
     {   // nearest internal child next, the rest onto the stack
         const float k0 = (im & 1u) ? t0 : INFINITY, k1 = (im & 2u) ? t1 : INFINITY;
@@ -139,19 +139,18 @@ __device__ __forceinline__ unsigned int wq_step(const SceneView& sv, WqShared& s
             if (next == WQ_NONE) L.state = 2;
         }
     }
-    // ---- 2. leaf hits -> warp ring (one entry per lane per round; usually one or two rounds)
-    while (__any_sync(FULL, lm != 0u)) {
-        const bool has = lm != 0u;
-        const unsigned int bal = __ballot_sync(FULL, has);
-        if (has) {
-            const unsigned int low = lm & (0u - lm);
-            const uint32_t w = (low & 1u) ? r0.w : ((low & 2u) ? r1.w : ((low & 4u) ? r2.w : r3.w));
-            const unsigned int q = W.pushed + __popc(bal & lt_mask);
-            ring[q & (WQ_RING_N - 1)] = make_uint2(w & 0x7FFFFFFFu, (unsigned int)lane);
-            L.my_last = q; L.queued = true;
-            lm ^= low;
-        }
-        W.pushed += __popc(bal);
+    // ---- 2. leaf hits -> warp ring: slot = exclusive prefix of the per-lane hit counts
+    //         (count <= 4: three ballots, one per bit of the count), straight-line code
+    {
+        const unsigned int nl = __popc(lm);
+        const unsigned int c0 = __ballot_sync(FULL, nl & 1u), c1 = __ballot_sync(FULL, nl & 2u), c2 = __ballot_sync(FULL, nl & 4u);
+        unsigned int q = W.pushed + __popc(c0 & lt_mask) + 2u * __popc(c1 & lt_mask) + 4u * __popc(c2 & lt_mask);
+        if (lm & 1u) { ring[q & (WQ_RING_N - 1)] = make_uint2(r0.w & 0x7FFFFFFFu, (unsigned int)lane); ++q; }
+        if (lm & 2u) { ring[q & (WQ_RING_N - 1)] = make_uint2(r1.w & 0x7FFFFFFFu, (unsigned int)lane); ++q; }
+        if (lm & 4u) { ring[q & (WQ_RING_N - 1)] = make_uint2(r2.w & 0x7FFFFFFFu, (unsigned int)lane); ++q; }
+        if (lm & 8u) { ring[q & (WQ_RING_N - 1)] = make_uint2(r3.w & 0x7FFFFFFFu, (unsigned int)lane); ++q; }
+        if (lm) { L.my_last = q - 1u; L.queued = true; }
+        W.pushed += __popc(c0) + 2u * __popc(c1) + 4u * __popc(c2);
     }
     // ---- 3. leaf batches
     {
