@@ -21,8 +21,10 @@ __device__ __forceinline__ float box_area(const float* lo, const float* hi) {
 }
 
 __device__ __forceinline__ uint32_t quant_pair(float lo, float hi, double org, double inv_step) {
-    double ql = floor(((double)lo - org) * inv_step);
-    double qh = ceil(((double)hi - org) * inv_step);
+    // one extra quantum on each side: the traversal folds the 2^23 decode bias into the ray
+    // constant (hzb_wq2.cuh), which costs up to half a quantum of accuracy
+    double ql = floor(((double)lo - org) * inv_step) - 1.0;
+    double qh = ceil(((double)hi - org) * inv_step) + 1.0;
     ql = fmin(fmax(ql, 0.0), 65535.0);
     qh = fmin(fmax(qh, 0.0), 65535.0);
     return (uint32_t)ql | ((uint32_t)qh << 16);
@@ -80,13 +82,13 @@ __global__ void k_collapse4(const Bvh2Node* __restrict__ nodes2, const uint32_t*
 int build_wide_bvh(Scene& s, cudaStream_t st) {
     const uint32_t n = s.num_prims;
     const uint32_t cap = n > 1 ? n - 1 : 1;  // a wide node absorbs >= 1 binary node
-    // quantisation grid: scene box (plus padding and one step of margin) over 65534 steps
+    // quantisation grid: scene box (plus padding and three steps of margin) over 65535 steps
     QGrid g;
     for (int a = 0; a < 3; ++a) {
         const double lo = (double)s.lo[a] - 2.0 * (double)s.pad, hi = (double)s.hi[a] + 2.0 * (double)s.pad;
-        const double step = std::max(hi - lo, 1e-6) / 65533.0;
+        const double step = std::max(hi - lo, 1e-6) / 65529.0;
         s.qstep[a] = (float)step;
-        s.qorg[a] = (float)(lo - step);
+        s.qorg[a] = (float)(lo - 3.0 * step);
         // the traversal decodes with the float values: quantise against exactly those
         g.org[a] = (double)s.qorg[a];
         g.inv_step[a] = 1.0 / (double)s.qstep[a];

@@ -16,6 +16,7 @@
 //   k_loc_*            arbitrary locations (closest-hit queries, binary BVH)
 #include "hzb_geom.cuh"
 #include "hzb_wq.cuh"
+#include "hzb_wq2.cuh"
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -285,10 +286,11 @@ struct LaneSM {
     int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
     int k, cur, prev, count, prev_az;
     float lim_up, lim_low, samp;
+    bool have_lo, lo_hit;   // packet kernels: the cast at prev-5 travelled with the cast at prev+5
 };
 
-template <int ALG>
-__device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int& cast_ie) {
+template <int ALG, bool PK>
+__device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int& cast_ie, int& lo_ie) {
     // returns true if a cast is required (cast_ie set), false if the azimuth needs none
     const int top = s.elev_num - 1;
     if (ALG == 0) {
@@ -302,19 +304,27 @@ __device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int
         return false;
     } else {
         m.phase = 2; m.count = 0;
-        m.prev = max(m.prev_az - 5, 0); m.cur = min(m.prev + 10, top); cast_ie = m.cur; return true;
+        m.prev = max(m.prev_az - 5, 0); m.cur = min(m.prev + 10, top); cast_ie = m.cur;
+        if (PK) lo_ie = max(min(m.prev_az + 5, top) - 10, 0);   // first index of the downward search (:472-476)
+        return true;
     }
 }
 
 // Consume the result of the last cast (if any) and move on until the next cast
 // is known or the cell is finished.  Returns true with cast_ie set when a ray
 // must be traced; false when the cell is complete.
-template <int ALG>
-__device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have_result, bool hit, OutBuf& ob, int& cast_ie) {
+// PK (packet kernels): the first cast of a guess_constant azimuth (index prev+5) may be
+// traced together with the first cast of the downward search (prev-5): lo_ie >= 0 names
+// it, the kernel sets m.have_lo / m.lo_hit, and the downward search consumes that result
+// instead of casting (counted in extra_rays exactly when the reference would have cast).
+template <int ALG, bool PK>
+__device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have_result, bool hit, OutBuf& ob, int& cast_ie,
+                                           int& lo_ie, unsigned int& extra_rays) {
     const int top = s.elev_num - 1;
+    lo_ie = -1;
     while (true) {
         if (!have_result) {  // start of an azimuth
-            if (sm_begin_azimuth<ALG>(s, m, cast_ie)) return true;
+            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie)) return true;
             // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
             hit = false; have_result = true;
             // (emulate loop exit below)
@@ -338,7 +348,9 @@ __device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have
             if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); cast_ie = m.cur; return true; }
             if (m.count <= 1) {                       // first upward cast missed: search downwards (:471-488)
                 m.phase = 3;
-                m.prev = min(m.prev_az + 5, top); m.cur = max(m.prev - 10, 0); cast_ie = m.cur; return true;
+                m.prev = min(m.prev_az + 5, top); m.cur = max(m.prev - 10, 0);
+                if (PK && m.have_lo) { m.have_lo = false; hit = m.lo_hit; ++extra_rays; continue; }
+                cast_ie = m.cur; return true;
             }
             const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
             ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
@@ -389,6 +401,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
     unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
     // per-lane cell and search state
     LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
+    m.have_lo = m.lo_hit = false;
     Frame f; OutBuf ob; ob.init(nullptr, false);
     bool has_cell = false, have_result = false;
     int my_ty = 0;
@@ -437,8 +450,8 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
         // (B) lanes with a cell but no ray in flight advance their search
         bool finished_cell = false;
         if (has_cell && L.state == 0) {
-            int ie;
-            if (sm_advance<ALG>(s, m, have_result, L.hit, ob, ie)) {
+            int ie, lo_ie; unsigned int extra = 0;
+            if (sm_advance<ALG, false>(s, m, have_result, L.hit, ob, ie, lo_ie, extra)) {
                 wq_start_ray(sv, sh, warp, lane, L, f.org, ray_dir(s, f, ie, m.k));
                 have_result = true; cnt.rays++;
             } else {
@@ -453,6 +466,110 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
         __syncwarp();
         // (C) shared traversal loop
         while (__popc(wq_step<TOPS>(sv, sh, top_nodes, n_top, warp, lane, tid, L, W, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
+    }
+    flush_counters(cnt, units, counters);
+}
+
+// ===========================================================================
+// k_horizon_wq6: production kernel.  Same work distribution and search state
+// machine as k_horizon_wq5, on the two-ray packet traversal of hzb_wq2.cuh: the
+// casts at prev+5 and prev-5 of a guess_constant azimuth share one traversal.
+// ===========================================================================
+template <int ALG, int MINB>
+__global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, HorizonParams p, Counters* counters,
+                                                                unsigned int* tile_counter, int refill_thr, int wait_thr) {
+    __shared__ Wq2Shared sh;
+    const Search s = make_search(sv, p, counters);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    const int rows = p.row_end - p.row_begin;
+    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int units = 0;
+    if (lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
+    unsigned int pend_est = 0;
+    __syncwarp();
+
+    unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
+    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
+    m.have_lo = m.lo_hit = false;
+    Frame f; OutBuf ob; ob.init(nullptr, false);
+    bool has_cell = false, have_result = false;
+    int my_ty = 0;
+    Wq2Lane L; L.state = 0; L.hit1 = L.hit2 = false; L.node = WQ_NONE; L.sp = 0; L.pc = 0;
+    L.A1x = L.A1y = L.A1z = L.B1x = L.B1y = L.B1z = 0.f; L.A2x = L.A2y = L.A2z = L.B2x = L.B2y = L.B2z = 0.f;
+    L.selxy = 0x74107410u;
+
+    while (true) {
+        // (A) hand out cells to lanes that have none
+        while (true) {
+            const bool want = !has_cell;
+            const unsigned int wmask = __ballot_sync(FULL, want);
+            if (wmask == 0u) break;
+            if (next_cell >= 32) {
+                if (!more_tiles) break;
+                unsigned int t = 0;
+                if (lane == 0) t = atomicAdd(tile_counter, 1u);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= num_tiles) { more_tiles = false; break; }
+                cur_tile = t; next_cell = 0;
+            }
+            const int mine = next_cell + __popc(wmask & lt_mask);
+            next_cell += __popc(wmask);
+            if (want && mine < 32) {
+                const int ty = cur_tile / tiles_x, tx = cur_tile - ty * tiles_x;
+                const int ci = p.row_begin + ty * 4 + (mine >> 3), cj = tx * 8 + (mine & 7);
+                bool done_now = true;
+                if (ci < p.row_end && cj < p.dim_in_1) {
+                    const size_t c = (size_t)ci * p.dim_in_1 + cj;
+                    float* out = p.hori + c * p.azim_num;
+                    if (p.mask[c] == 1) {
+                        const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
+                        const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
+                        const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
+                        f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+                        ob.init(out, vec);
+                        m.phase = 0; m.k = 0; m.have_lo = false;
+                        has_cell = true; have_result = false; my_ty = ty; units += p.azim_num;
+                        done_now = false;
+                    } else {
+                        for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+                    }
+                }
+                if (done_now && p.row_done) { __threadfence_system(); atomicAdd(p.row_done + ty, 1u); }
+            }
+        }
+        // (B) lanes with a cell but no packet in flight advance their search; the ray set-up
+        //     runs after the lanes have reconverged (sm_advance leaves through many exits)
+        bool finished_cell = false, need_ray = false;
+        int ie = 0, lo_ie = -1;
+        if (has_cell && L.state == 0) {
+            unsigned int extra = 0;
+            m.lo_hit = L.hit2;
+            need_ray = sm_advance<ALG, true>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
+            cnt.rays += extra + (need_ray ? 1u : 0u);
+            if (!need_ray) {
+                has_cell = false; finished_cell = true;
+                if (p.row_done) { __threadfence_system(); atomicAdd(p.row_done + my_ty, 1u); }  // this cell's outputs are visible
+            }
+        }
+        __syncwarp();
+        if (need_ray) {
+            const F3 D1 = ray_dir(s, f, ie, m.k);
+            const F3 D2 = lo_ie >= 0 ? ray_dir(s, f, lo_ie, m.k) : D1;
+            const bool two = wq2_start(sv, sh, warp, lane, L, f.org, D1, D2);
+            m.have_lo = two && lo_ie >= 0;
+            have_result = true;
+        }
+        if (__any_sync(FULL, finished_cell) && (more_tiles || next_cell < 32)) continue;   // give them a new cell first
+        const unsigned int cell_mask = __ballot_sync(FULL, has_cell);
+        if (cell_mask == 0u) break;
+        const int thr = min(refill_thr, __popc(cell_mask));
+        __syncwarp();
+        // (C) shared traversal loop
+        while (__popc(wq2_step(sv, sh, warp, lane, tid, L, pend_est, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
     }
     flush_counters(cnt, units, counters);
 }
@@ -561,6 +678,19 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
             case 1: k_horizon_gridded<1><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
             default: k_horizon_gridded<2><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
         }
+    } else if (!(kern_env && !strcmp(kern_env, "wq5"))) {
+        const int w_refill = getenv("HZB_WREFILL") ? atoi(getenv("HZB_WREFILL")) : 24;   // refill when fewer lanes hold a packet
+        const int w_wait = getenv("HZB_WWAIT") ? atoi(getenv("HZB_WWAIT")) : 2;          // flush the lists when this many lanes wait
+        const int minb = getenv("HZB_MINB") ? atoi(getenv("HZB_MINB")) : 5;
+#define HZB_LAUNCH6(ALG_, MB_) k_horizon_wq6<ALG_, MB_><<<sm_count() * MB_, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait)
+        if (minb >= 6) {
+            switch (p.algorithm) { case 0: HZB_LAUNCH6(0, 6); break; case 1: HZB_LAUNCH6(1, 6); break; default: HZB_LAUNCH6(2, 6); break; }
+        } else if (minb == 5) {
+            switch (p.algorithm) { case 0: HZB_LAUNCH6(0, 5); break; case 1: HZB_LAUNCH6(1, 5); break; default: HZB_LAUNCH6(2, 5); break; }
+        } else {
+            switch (p.algorithm) { case 0: HZB_LAUNCH6(0, 4); break; case 1: HZB_LAUNCH6(1, 4); break; default: HZB_LAUNCH6(2, 4); break; }
+        }
+#undef HZB_LAUNCH6
     } else {
         const int w_refill = getenv("HZB_WREFILL") ? atoi(getenv("HZB_WREFILL")) : 24;   // refill when fewer lanes hold a ray
         const int w_wait = getenv("HZB_WWAIT") ? atoi(getenv("HZB_WWAIT")) : 6;          // flush the ring when this many lanes wait

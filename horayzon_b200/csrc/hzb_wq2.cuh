@@ -1,0 +1,293 @@
+// hzb_wq2.cuh -- second-generation warp-queue traversal step: TWO rays per lane.
+//
+// The guess_constant search (horizon_comp.cpp:387-498) needs, for almost every
+// azimuth, the decisions of the two casts at table index prev+5 and prev-5.  They
+// share the origin and the azimuth and differ by 0.5 deg in elevation, so their
+// paths through the BVH are nearly the same: this step walks both with ONE
+// traversal (a node is entered if either ray meets its box, a leaf candidate is
+// tested against both rays).  Every decision is still tri_hit() of that ray on a
+// primitive whose conservative boxes the ray meets -- bit-identical to two
+// separate casts; only the number of node fetches, decodes and control
+// instructions is shared.  A single ray is a packet whose rays coincide.
+//
+// Differences to hzb_wq.cuh (kept for the shadow kernel and for A/B runs):
+//   * the 2^23 bias of the quantised planes is folded into the ray constant
+//     (t = qb*A + B', B' = fma(-2^23, A, B)): one FFMA per plane, no FADD.  The
+//     fold costs at most half a quantum of accuracy, which is why bvh_wide.cu
+//     widens every quantised box by one quantum on each side;
+//   * x/y planes are picked by the (shared) direction signs, z by min/max, so the
+//     two rays may point to different sides of the horizontal;
+//   * leaf candidates go to a per-lane pending list (plain shared-memory stores);
+//     the warp-wide compaction (prefix scan of the list lengths, redux.or of the
+//     start bits) runs once per flush instead of three ballots per step;
+//   * the two triangles of a grid quad share their diagonal: the Pluecker edge
+//     function of the reversed edge is the exact negative, so five edge functions
+//     serve both triangles, and their cross products serve both rays.
+#pragma once
+#include "hzb_geom.cuh"
+#include "hzb_wq.cuh"
+
+namespace hzb {
+
+constexpr int WQ2_PEND_N = 12;   // per-lane pending leaf candidates (a flush is forced above PEND_N - 4)
+
+struct Wq2Shared {
+    uint32_t stack[WQ_STACK_N][WQ_BLOCK];
+    uint32_t pend[WQ2_PEND_N][WQ_BLOCK];
+    float ray[WQ_NWARPS][9][32];              // O.xyz, D1.xyz, D2.xyz per lane
+    unsigned int hit1[WQ_NWARPS], hit2[WQ_NWARPS];
+    unsigned int rank_owner[WQ_NWARPS][32];
+};
+
+struct Wq2Lane {
+    int state;            // 0 no ray, 1 traversing, 2 traversal over, waiting for its pending candidates
+    bool hit1, hit2;
+    uint32_t node; int sp, pc;
+    float A1x, A1y, A1z, B1x, B1y, B1z;      // ray 1 (upper): t = qb * A + B, bias folded into B
+    float A2x, A2y, A2z, B2x, B2y, B2z;      // ray 2 (lower)
+    unsigned int selxy;                       // PRMT selectors of the near x (low half) / y (high half) planes, shared by both rays
+};
+
+// Reciprocal for the box tests only (never for a hit decision): the clamp keeps
+// 2^23 * A finite, the approximate reciprocal (2 ulp) is far inside the box padding.
+__device__ __forceinline__ float safe_rcp2(float d) {
+    if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+    return __fdividef(1.0f, d);
+}
+
+__device__ __forceinline__ void wq2_ray_consts(const SceneView& sv, F3 O, float ix, float iy, float iz,
+                                               float& Ax, float& Ay, float& Az, float& Bx, float& By, float& Bz) {
+    const float M = 8388608.0f;
+    Ax = sv.qstep[0] * ix; Ay = sv.qstep[1] * iy; Az = sv.qstep[2] * iz;
+    Bx = fmaf(-M, Ax, (sv.qorg[0] - O.x) * ix);
+    By = fmaf(-M, Ay, (sv.qorg[1] - O.y) * iy);
+    Bz = fmaf(-M, Az, (sv.qorg[2] - O.z) * iz);
+}
+
+// Start the packet (D1, D2).  Returns false when the two rays cannot share the
+// plane selectors (different x or y direction signs): ray 2 is then a copy of ray 1.
+__device__ __forceinline__ bool wq2_start(const SceneView& sv, Wq2Shared& sh, int warp, int lane, Wq2Lane& L, F3 O, F3 D1, F3 D2) {
+    const float i1x = safe_rcp2(D1.x), i1y = safe_rcp2(D1.y), i1z = safe_rcp2(D1.z);
+    float i2x = safe_rcp2(D2.x), i2y = safe_rcp2(D2.y), i2z = safe_rcp2(D2.z);
+    const bool same = ((i1x >= 0.f) == (i2x >= 0.f)) && ((i1y >= 0.f) == (i2y >= 0.f));
+    if (!same) { D2 = D1; i2x = i1x; i2y = i1y; i2z = i1z; }
+    wq2_ray_consts(sv, O, i1x, i1y, i1z, L.A1x, L.A1y, L.A1z, L.B1x, L.B1y, L.B1z);
+    wq2_ray_consts(sv, O, i2x, i2y, i2z, L.A2x, L.A2y, L.A2z, L.B2x, L.B2y, L.B2z);
+    L.selxy = (i1x >= 0.f ? 0x7410u : 0x7432u) | (i1y >= 0.f ? 0x74100000u : 0x74320000u);
+    float* r = &sh.ray[warp][0][lane];
+    r[0] = O.x; r[32] = O.y; r[64] = O.z;
+    r[96] = D1.x; r[128] = D1.y; r[160] = D1.z;
+    r[192] = D2.x; r[224] = D2.y; r[256] = D2.z;
+    L.node = 0u; L.sp = 0; L.pc = 0; L.state = 1; L.hit1 = false; L.hit2 = false;
+    return same;
+}
+
+// Box test of one child for both rays.
+__device__ __forceinline__ bool wide2_child_test(const uint4 r, const Wq2Lane& L, float tfar) {
+    const unsigned int selx = L.selxy, sely = L.selxy >> 16;       // PRMT reads the low 16 selector bits only
+    const float qnx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selx));
+    const float qfx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selx ^ 0x0022u));
+    const float qny = __uint_as_float(__byte_perm(r.y, 0x4B000000u, sely));
+    const float qfy = __uint_as_float(__byte_perm(r.y, 0x4B000000u, sely ^ 0x0022u));
+    const float qzl = __uint_as_float(__byte_perm(r.z, 0x4B000000u, 0x7410u));
+    const float qzh = __uint_as_float(__byte_perm(r.z, 0x4B000000u, 0x7432u));
+    float za = fmaf(qzl, L.A1z, L.B1z), zb = fmaf(qzh, L.A1z, L.B1z);
+    const float tmin1 = fmaxf(fmaxf(fmaf(qnx, L.A1x, L.B1x), fmaf(qny, L.A1y, L.B1y)), fmaxf(fminf(za, zb), 0.0f));
+    const float tmax1 = fminf(fminf(fmaf(qfx, L.A1x, L.B1x), fmaf(qfy, L.A1y, L.B1y)), fminf(fmaxf(za, zb), tfar));
+    za = fmaf(qzl, L.A2z, L.B2z); zb = fmaf(qzh, L.A2z, L.B2z);
+    const float tmin2 = fmaxf(fmaxf(fmaf(qnx, L.A2x, L.B2x), fmaf(qny, L.A2y, L.B2y)), fmaxf(fminf(za, zb), 0.0f));
+    const float tmax2 = fminf(fminf(fmaf(qfx, L.A2x, L.B2x), fmaf(qfy, L.A2y, L.B2y)), fminf(fmaxf(za, zb), tfar));
+    // no relative slack on tmax: the extra quantum on every plane (bvh_wide.cu) leaves half a
+    // quantum (7.6e-6 of the scene extent) beyond the fold error, the rounding of t is ~1e-7 of it
+    return ((tmin1 <= tmax1) || (tmin2 <= tmax2)) && (r.w != WIDE_EMPTY);
+}
+
+// ---- two rays against one primitive -------------------------------------------------
+// Edge test of tri_hit() from the three edge functions of one ray.
+__device__ __forceinline__ bool edges_accept(float U, float V, float W) {
+    const float UVW = __fadd_rn(__fadd_rn(U, V), W);
+    const float eps = __fmul_rn(FLT_EPSILON, fabsf(UVW));
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    return (mn >= -eps) || (mx <= eps);
+}
+// The stable geometric normal of tri_depth() (ray independent).
+__device__ __forceinline__ F3 tri_ng(F3 e0, F3 e1, F3 e2) {
+    const float ab_x = __fmul_rn(e0.z, e1.y), ab_y = __fmul_rn(e0.x, e1.z), ab_z = __fmul_rn(e0.y, e1.x);
+    const float bc_x = __fmul_rn(e1.z, e2.y), bc_y = __fmul_rn(e1.x, e2.z), bc_z = __fmul_rn(e1.y, e2.x);
+    const float cab_x = __fmaf_rn(e0.y, e1.z, -ab_x), cab_y = __fmaf_rn(e0.z, e1.x, -ab_y), cab_z = __fmaf_rn(e0.x, e1.y, -ab_z);
+    const float cbc_x = __fmaf_rn(e1.y, e2.z, -bc_x), cbc_y = __fmaf_rn(e1.z, e2.x, -bc_y), cbc_z = __fmaf_rn(e1.x, e2.y, -bc_z);
+    return f3(fabsf(ab_x) < fabsf(bc_x) ? cab_x : cbc_x, fabsf(ab_y) < fabsf(bc_y) ? cab_y : cbc_y,
+              fabsf(ab_z) < fabsf(bc_z) ? cab_z : cbc_z);
+}
+__device__ __forceinline__ bool depth_ok(F3 v0, F3 Ng, F3 D, float tfar) {
+    const float dn = dot_f(Ng, D);
+    const float den = __fadd_rn(dn, dn);
+    if (den == 0.0f) return false;
+    const float tn = dot_f(v0, Ng);
+    const float t = __fdiv_rn(__fadd_rn(tn, tn), den);
+    return t >= 0.0f && t <= tfar;
+}
+
+// Same decisions as prim_hit<false>(.., D1, ..) and prim_hit<false>(.., D2, ..).
+__device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 O, F3 D1, F3 D2, float tfar, bool& h1, bool& h2) {
+    h1 = false; h2 = false;
+    if (prim < s.num_quads) {
+        const uint32_t wq = (uint32_t)(s.W - 1);
+        const uint32_t i = prim / wq, j = prim - i * wq;
+        const float4* r0 = s.vert4 + (size_t)i * s.W + j;
+        const float4* r1 = r0 + s.W;
+        // triangle 1 = (p00, p01, p10) = (a, b, c); triangle 2 = (p11, p10, p01) = (d, c, b)
+        const F3 a = sub_rn(ld_vert(r0), O), b = sub_rn(ld_vert(r0 + 1), O), c = sub_rn(ld_vert(r1), O), d = sub_rn(ld_vert(r1 + 1), O);
+        const F3 e0 = sub_rn(c, a), e1 = sub_rn(a, b), e2 = sub_rn(b, c);          // triangle 1
+        const F3 f0 = sub_rn(b, d), f1 = sub_rn(d, c);                             // triangle 2 (its e2 = c - b = -e2)
+        const F3 C0 = cross_f(e0, add_rn(c, a)), C1 = cross_f(e1, add_rn(a, b)), C2 = cross_f(e2, add_rn(b, c));
+        const F3 G0 = cross_f(f0, add_rn(b, d)), G1 = cross_f(f1, add_rn(d, c));
+        const float W1 = dot_f(C2, D1), W2 = dot_f(C2, D2);
+        const bool a11 = edges_accept(dot_f(C0, D1), dot_f(C1, D1), W1);
+        const bool a12 = edges_accept(dot_f(C0, D2), dot_f(C1, D2), W2);
+        const bool a21 = edges_accept(dot_f(G0, D1), dot_f(G1, D1), -W1);   // reversed diagonal: exact negative
+        const bool a22 = edges_accept(dot_f(G0, D2), dot_f(G1, D2), -W2);
+        // depth tests (rare): one (triangle, ray) combination per round, shared code
+        unsigned int acc = (a11 ? 1u : 0u) | (a12 ? 2u : 0u) | (a21 ? 4u : 0u) | (a22 ? 8u : 0u);
+        while (acc) {
+            const bool second = (acc & 3u) == 0u;                     // triangle 2 once triangle 1 is done
+            const unsigned int pair = second ? (acc >> 2) : (acc & 3u);
+            const F3 g0 = second ? f0 : e0, g1 = second ? f1 : e1;
+            const F3 g2 = second ? f3(-e2.x, -e2.y, -e2.z) : e2;
+            const F3 v0 = second ? d : a;
+            const F3 Ng = tri_ng(g0, g1, g2);
+            if ((pair & 1u) && !h1) h1 = depth_ok(v0, Ng, D1, tfar);
+            if ((pair & 2u) && !h2) h2 = depth_ok(v0, Ng, D2, tfar);
+            acc &= second ? 0u : 0xCu;
+        }
+    } else {
+        const float4* q = s.tin4 + 3 * (size_t)(prim - s.num_quads);
+        const F3 p0 = ld_vert(q), p1 = ld_vert(q + 1), p2 = ld_vert(q + 2);
+        float t;
+        h1 = tri_hit(p0, p1, p2, O, D1, tfar, t);
+        h2 = tri_hit(p0, p1, p2, O, D2, tfar, t);
+    }
+}
+
+// One iteration of the warp's traversal loop.  pend_est: warp-uniform estimate of
+// the number of pending candidates.  Returns the ballot of lanes that still own a packet.
+__device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared& sh, const int warp, const int lane, const int tid,
+                                                 Wq2Lane& L, unsigned int& pend_est, const float tfar, const int wait_thr,
+                                                 LaneCounters& cnt, unsigned int* overflow) {
+    const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    // ---- 1. node step (all lanes; lanes without a traversing packet read the root and are masked)
+    const bool trav = L.state == 1;
+    const uint32_t nidx = trav ? L.node : 0u;
+    const uint4* np = reinterpret_cast<const uint4*>(sv.nodes4 + nidx);
+    const uint4 r0 = __ldg(np), r1 = __ldg(np + 1), r2 = __ldg(np + 2), r3 = __ldg(np + 3);
+    const bool h0 = wide2_child_test(r0, L, tfar), h1 = wide2_child_test(r1, L, tfar);
+    const bool h2 = wide2_child_test(r2, L, tfar), h3 = wide2_child_test(r3, L, tfar);
+    cnt.nodes += trav ? 1u : 0u;
+    const unsigned int hm = trav ? ((h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u)) : 0u;
+    const unsigned int lfm = (r0.w >> 31) | ((r1.w >> 31) << 1) | ((r2.w >> 31) << 2) | ((r3.w >> 31) << 3);
+    const unsigned int lm = hm & lfm;
+    const unsigned int im = hm & ~lfm;
+    {   // first hit internal child next, the rest onto the stack.  No distance order: the upper ray of
+        // a packet usually misses and has to visit every box it meets anyway (measured on B200: the
+        // nearest-first selection cost 9 % and visited MORE nodes)
+        const unsigned int first = im & (0u - im);     // lowest set bit (0 if no internal hit)
+        const uint32_t firstc = (first & 1u) ? r0.w : ((first & 2u) ? r1.w : ((first & 4u) ? r2.w : r3.w));
+        const unsigned int others = im & ~first;
+        int sp = L.sp;
+        if (sp + 3 > WQ_STACK_N) { if (others) atomicAdd(overflow, 1u); }
+        else {
+            if (others & 1u) { sh.stack[sp][tid] = r0.w; ++sp; }
+            if (others & 2u) { sh.stack[sp][tid] = r1.w; ++sp; }
+            if (others & 4u) { sh.stack[sp][tid] = r2.w; ++sp; }
+            if (others & 8u) { sh.stack[sp][tid] = r3.w; ++sp; }
+        }
+        if (trav) {
+            uint32_t next = firstc;
+            if (!im) {
+                next = WQ_NONE;
+                if (sp > 0) { --sp; next = sh.stack[sp][tid]; }
+            }
+            L.sp = sp; L.node = next;
+            if (next == WQ_NONE) L.state = 2;
+        }
+    }
+    // ---- 2. leaf hits -> the lane's own pending list (room for 4 is guaranteed by the flush rule)
+    {
+        int pc = L.pc;
+        if (lm & 1u) { sh.pend[pc][tid] = r0.w & 0x7FFFFFFFu; ++pc; }
+        if (lm & 2u) { sh.pend[pc][tid] = r1.w & 0x7FFFFFFFu; ++pc; }
+        if (lm & 4u) { sh.pend[pc][tid] = r2.w & 0x7FFFFFFFu; ++pc; }
+        if (lm & 8u) { sh.pend[pc][tid] = r3.w & 0x7FFFFFFFu; ++pc; }
+        L.pc = pc;
+        pend_est += __popc(__ballot_sync(FULL, lm != 0u));   // lower bound: one per lane with new candidates
+    }
+    // ---- 3. leaf batches
+    {
+        const unsigned int b_wait = __ballot_sync(FULL, L.state == 2 && L.pc > 0);
+        const unsigned int b_trav = __ballot_sync(FULL, L.state == 1);
+        const bool any_full = __any_sync(FULL, L.pc > WQ2_PEND_N - 4);
+        const bool forced = any_full || (pend_est > 0u && (__popc(b_wait) >= wait_thr || b_trav == 0u));
+        if (pend_est >= 32u || forced) {
+            // exclusive prefix of the list lengths: scan position p of lane o's list is its entry pc-1-(p-excl)
+            unsigned int incl = (unsigned int)L.pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned int excl = incl - (unsigned int)L.pc;
+            const unsigned int total = __shfl_sync(FULL, incl, 31);
+            unsigned int base = 0;
+            __syncwarp();
+            while (total - base >= 32u || (forced && total > base)) {
+                const unsigned int nb = min(total - base, 32u);
+                const bool contrib = L.pc > 0 && incl > base && excl < base + 32u;
+                const unsigned int s0 = (excl > base ? excl : base) - base;
+                const unsigned int startmask = __reduce_or_sync(FULL, contrib ? (1u << s0) : 0u);
+                const unsigned int cm = __ballot_sync(FULL, contrib);
+                if (contrib) sh.rank_owner[warp][__popc(cm & lt_mask)] = (unsigned int)lane;
+                __syncwarp();
+                unsigned int owner = 0;
+                if ((unsigned int)lane < nb) owner = sh.rank_owner[warp][__popc(startmask & (FULL >> (31 - lane))) - 1];
+                const unsigned int ex_o = __shfl_sync(FULL, excl, owner);
+                const unsigned int pc_o = __shfl_sync(FULL, (unsigned int)L.pc, owner);
+                bool q1 = false, q2 = false;
+                if ((unsigned int)lane < nb) {
+                    const unsigned int k = base + (unsigned int)lane - ex_o;
+                    const uint32_t prim = sh.pend[pc_o - 1u - k][(tid & ~31) + owner];
+                    const float* r = &sh.ray[warp][0][owner];
+                    const F3 O = f3(r[0], r[32], r[64]);
+                    const F3 D1 = f3(r[96], r[128], r[160]), D2 = f3(r[192], r[224], r[256]);
+                    prim_hit2(sv, prim, O, D1, D2, tfar, q1, q2);
+                    cnt.prims++;
+                }
+                if (q1) atomicOr(&sh.hit1[warp], 1u << owner);
+                if (q2) atomicOr(&sh.hit2[warp], 1u << owner);
+                base += nb;
+                __syncwarp();
+            }
+            // what is left of this lane's list sits at its bottom
+            const unsigned int end_o = excl + (unsigned int)L.pc;
+            L.pc = (int)(end_o > base ? min(end_o - base, (unsigned int)L.pc) : 0u);
+            pend_est = total - base;
+            const unsigned int m1 = sh.hit1[warp], m2 = sh.hit2[warp];
+            __syncwarp();
+            if ((m1 | m2) != 0u && lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
+            if ((m1 >> lane) & 1u) L.hit1 = true;
+            if ((m2 >> lane) & 1u) L.hit2 = true;
+            if (L.state != 0) {
+                if (L.hit1 && L.hit2) { L.state = 2; L.pc = 0; }          // both decided: drop the rest
+                else if (L.hit2 && ((m2 >> lane) & 1u)) {                 // lower ray decided: walk on with the upper one only
+                    L.A2x = L.A1x; L.A2y = L.A1y; L.A2z = L.A1z; L.B2x = L.B1x; L.B2y = L.B1y; L.B2z = L.B1z;
+                } else if (L.hit1 && ((m1 >> lane) & 1u)) {
+                    L.A1x = L.A2x; L.A1y = L.A2y; L.A1z = L.A2z; L.B1x = L.B2x; L.B1y = L.B2y; L.B1z = L.B2z;
+                }
+            }
+        }
+    }
+    // ---- 4. retire
+    if (L.state == 2 && L.pc == 0) L.state = 0;
+    return __ballot_sync(FULL, L.state != 0);
+}
+
+}  // namespace hzb

@@ -48,7 +48,8 @@ def test_horizon_gridded_cfg1(mods, alg):
 
 
 @pytest.mark.parametrize("env", [{"HZB_KERNEL": "simple"}, {"HZB_TOPSMEM": "1"}, {"HZB_NO_OVERLAP": "1"},
-                                 {"HZB_WREFILL": "32", "HZB_WWAIT": "1"}])
+                                 {"HZB_WREFILL": "32", "HZB_WWAIT": "1"}, {"HZB_KERNEL": "wq5"},
+                                 {"HZB_MINB": "6"}, {"HZB_MINB": "4", "HZB_WREFILL": "8", "HZB_WWAIT": "32"}])
 def test_horizon_kernel_variants_agree(mods, monkeypatch, env):
     """The reference-shaped per-lane kernel (binary BVH), the TMA-staged variant,
     the non-overlapped host path and other scheduling thresholds must all give
