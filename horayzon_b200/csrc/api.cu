@@ -6,6 +6,7 @@
 // compute entry point needs a CUDA device and fails with a status otherwise.
 #include "hzb_common.cuh"
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 #include <chrono>
 #include <limits>
@@ -173,14 +174,17 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
                         float hori_fill, float ray_org_elev) {
     memset(&g_stats, 0, sizeof(g_stats));
     const double t_start = now_s();
+    const bool timing = getenv("HZB_TIMING") != nullptr;   // stderr breakdown of this call
     if (require_device()) return 1;
     if (parse_geom_type(geom_type) < 0) { set_error("invalid input argument for geom_type"); return 1; }
     if (!vert_grid || !vec_norm || !vec_north || !hori_buffer || !mask) { set_error("null pointer argument"); return 1; }
     int dev = 0; cudaGetDevice(&dev);
+    const double t_scene0 = now_s();
     hzb_scene* h = hzb_scene_create(vert_grid, dem_dim_0, dem_dim_1, vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp, dev);
     if (!h) return 1;
     struct Guard { hzb_scene* h; ~Guard() { hzb_scene_destroy(h); } } guard{h};
     const size_t nc = (size_t)dim_in_0 * dim_in_1;
+    const double t_scene = now_s() - t_scene0;
     double t0 = now_s();
     DevBuf<float> d_norm, d_north, d_hori; DevBuf<uint8_t> d_mask;
     HZB_TRY(d_norm.upload(vec_norm, nc * 3)); HZB_TRY(d_north.upload(vec_north, nc * 3)); HZB_TRY(d_mask.upload(mask, nc));
@@ -205,6 +209,9 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
                                    ray_org_elev, d_hori.p, overlap ? d_done.p : nullptr, s_comp));
     double t_d2h = 0.0, t_trace = 0.0;
     const size_t row_elems = (size_t)dim_in_1 * (size_t)azim_num;
+    const double t_pf0 = now_s();
+    host_prefault(hori_buffer, nc * (size_t)azim_num * sizeof(float));   // the kernel is running meanwhile
+    const double t_prefault = now_s() - t_pf0;
     if (overlap) {
         unsigned int* h_done = nullptr;
         HZB_CUDA(cudaMallocHost((void**)&h_done, (size_t)tiles_y * sizeof(unsigned int)));
@@ -226,9 +233,7 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
             if (ready - copied_blocks >= min_blocks || (ready == tiles_y && ready > copied_blocks)) {
                 const size_t r0 = (size_t)copied_blocks * 4, r1 = std::min<size_t>((size_t)ready * 4, (size_t)dim_in_0);
                 const double tc = now_s();
-                HZB_CUDA(cudaMemcpyAsync(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float),
-                                         cudaMemcpyDeviceToHost, s_copy));
-                HZB_CUDA(cudaStreamSynchronize(s_copy));
+                HZB_TRY(staged_d2h(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float), s_copy));
                 t_d2h += now_s() - tc;
                 copied_blocks = ready;
             } else {
@@ -242,12 +247,15 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
         HZB_CUDA(cudaStreamSynchronize(s_comp));
         t_trace = now_s() - t0;
         const double tc = now_s();
-        HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
+        HZB_TRY(staged_d2h(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), nullptr));
         t_d2h = now_s() - tc;
     }
     HZB_CUDA(cudaGetLastError());
     HZB_TRY(read_counters(h->s, g_stats));
     g_stats.t_h2d += t_h2d_extra; g_stats.t_trace = t_trace; g_stats.t_d2h = t_d2h; g_stats.t_total = now_s() - t_start;
+    if (timing)
+        fprintf(stderr, "[hzb] horizon_gridded: scene %.3f (h2d %.3f build %.3f) inputs+alloc %.3f launch..end %.3f (prefault %.3f, kernel seen done %.3f, staged d2h %.3f) total %.3f s\n",
+                t_scene, h->s.t_h2d, h->s.t_build, t_h2d_extra, now_s() - t0, t_prefault, t_trace, t_d2h, g_stats.t_total);
     return 0;
 }
 
@@ -419,11 +427,31 @@ static int integral_host(int kind, const float* azim, const float* hori, const f
     if (ny < 0 || nx < 0 || K < 1) { set_error("invalid dimensions"); return 1; }
     const size_t nc = (size_t)ny * nx;
     if (nc == 0) return 0;
-    DevBuf<float> d_a, d_h, d_t, d_o;
-    HZB_TRY(d_a.upload(azim, K)); HZB_TRY(d_h.upload(hori, nc * (size_t)K));
+    // The horizon array (nc x K floats, 2 GB for cfg2) streams through two device chunks:
+    // staged H2D of chunk i+1 overlaps the integral kernel of chunk i.
+    const size_t chunk_cells = std::min(nc, std::max<size_t>(1, ((size_t)64 << 20) / ((size_t)K * sizeof(float))));
+    DevBuf<float> d_a, d_t, d_o, d_h[2];
+    HZB_TRY(d_a.upload(azim, K));
     if (kind != 2) HZB_TRY(d_t.upload(tilt, nc * 3));
     HZB_TRY(d_o.alloc(nc));
-    HZB_TRY(launch_svf(kind, d_a.p, d_h.p, d_t.p, (long long)nc, K, d_o.p, nullptr));
+    HZB_TRY(d_h[0].alloc(chunk_cells * (size_t)K));
+    if (chunk_cells < nc) HZB_TRY(d_h[1].alloc(chunk_cells * (size_t)K));
+    cudaStream_t st = nullptr;
+    HZB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sguard{st};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    HZB_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    HZB_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } eguard{done};
+    int slot = 0;
+    for (size_t c0 = 0; c0 < nc; c0 += chunk_cells, slot ^= 1) {
+        const size_t cells = std::min(chunk_cells, nc - c0);
+        if (c0 >= 2 * chunk_cells) HZB_CUDA(cudaEventSynchronize(done[slot]));   // the kernel two chunks back has read this buffer
+        HZB_TRY(staged_h2d(d_h[slot].p, hori + c0 * (size_t)K, cells * (size_t)K * sizeof(float), st));
+        HZB_TRY(launch_svf(kind, d_a.p, d_h[slot].p, kind != 2 ? d_t.p + 3 * c0 : nullptr, (long long)cells, K, d_o.p + c0, st));
+        HZB_CUDA(cudaEventRecord(done[slot], st));
+    }
+    HZB_CUDA(cudaStreamSynchronize(st));
     HZB_CUDA(cudaMemcpy(out, d_o.p, nc * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }

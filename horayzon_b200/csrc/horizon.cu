@@ -284,8 +284,7 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
 struct LaneSM {
     // search state (horizon_comp.cpp:387-498 unrolled into states)
     int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
-    int k, cur, prev, count, prev_az;
-    float lim_up, lim_low, samp;
+    int k, cur, prev, count, prev_az;   // during a bisection (phase 1) prev / count hold the bits of lim_up / lim_low
     bool have_lo, lo_hit;   // packet kernels: the cast at prev-5 travelled with the cast at prev+5
 };
 
@@ -296,11 +295,10 @@ __device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int
     if (ALG == 0) {
         m.phase = 4; m.prev = 0; m.cur = min(10, top); cast_ie = m.cur; return true;
     } else if (ALG == 1 || m.k == 0) {
-        m.phase = 1; m.lim_up = s.up; m.lim_low = s.low;
-        m.samp = midpoint(m.lim_up, m.lim_low);
-        m.cur = index_of(s, m.samp);
+        m.phase = 1; m.prev = __float_as_int(s.up); m.count = __float_as_int(s.low);
+        m.cur = index_of(s, midpoint(s.up, s.low));
         const float ea = __ldg(s.elev_ang + m.cur);
-        if (fmaxf(__fsub_rn(m.lim_up, ea), __fsub_rn(ea, m.lim_low)) > s.acc) { cast_ie = m.cur; return true; }
+        if (fmaxf(__fsub_rn(s.up, ea), __fsub_rn(ea, s.low)) > s.acc) { cast_ie = m.cur; return true; }
         return false;
     } else {
         m.phase = 2; m.count = 0;
@@ -333,14 +331,14 @@ __device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have
         if (m.phase == 1) {
             {
                 const float ea = __ldg(s.elev_ang + m.cur);
-                if (hit) m.lim_low = ea; else m.lim_up = ea;
-                m.samp = midpoint(m.lim_up, m.lim_low);
-                m.cur = index_of(s, m.samp);
+                if (hit) m.count = __float_as_int(ea); else m.prev = __float_as_int(ea);
+                const float lim_up = __int_as_float(m.prev), lim_low = __int_as_float(m.count);
+                m.cur = index_of(s, midpoint(lim_up, lim_low));
                 const float ea2 = __ldg(s.elev_ang + m.cur);
-                if (fmaxf(__fsub_rn(m.lim_up, ea2), __fsub_rn(ea2, m.lim_low)) > s.acc) { cast_ie = m.cur; return true; }
+                if (fmaxf(__fsub_rn(lim_up, ea2), __fsub_rn(ea2, lim_low)) > s.acc) { cast_ie = m.cur; return true; }
             }
         bisect_done:
-            ob.put(m.k, m.samp);          // un-quantised midpoint (:377, :428)
+            ob.put(m.k, midpoint(__int_as_float(m.prev), __int_as_float(m.count)));   // un-quantised midpoint (:377, :428)
             m.prev_az = m.cur;            // seeds the chain (:429)
         } else if (m.phase == 2) {
             m.count++;
@@ -400,7 +398,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
     // one; when the tile is used up the warp pulls the next tile from the global queue
     unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
     // per-lane cell and search state
-    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
+    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
     m.have_lo = m.lo_hit = false;
     Frame f; OutBuf ob; ob.init(nullptr, false);
     bool has_cell = false, have_result = false;
@@ -485,7 +483,6 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
     const int rows = p.row_end - p.row_begin;
     const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
     const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
-    const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
     unsigned int units = 0;
     if (lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
@@ -493,11 +490,11 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
     __syncwarp();
 
     unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
-    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.lim_up = m.lim_low = m.samp = 0.f;
+    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
     m.have_lo = m.lo_hit = false;
-    Frame f; OutBuf ob; ob.init(nullptr, false);
+    OutBuf ob; ob.init(nullptr, false);
+    unsigned int my_cell = 0;   // (row << 16) | column of the lane's cell: its frame is rebuilt at every ray set-up
     bool has_cell = false, have_result = false;
-    int my_ty = 0;
     Wq2Lane L; L.state = 0; L.hit1 = L.hit2 = false; L.node = WQ_NONE; L.sp = 0; L.pc = 0;
     L.A1x = L.A1y = L.A1z = L.B1x = L.B1y = L.B1z = 0.f; L.A2x = L.A2y = L.A2z = L.B2x = L.B2y = L.B2z = 0.f;
     L.selxy = 0x74107410u;
@@ -526,13 +523,10 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                     const size_t c = (size_t)ci * p.dim_in_1 + cj;
                     float* out = p.hori + c * p.azim_num;
                     if (p.mask[c] == 1) {
-                        const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
-                        const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
-                        const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
-                        f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
-                        ob.init(out, vec);
+                        my_cell = ((unsigned int)ci << 16) | (unsigned int)cj;    // dims <= 32767 (horizon.pyx:149-151)
+                        ob.init(out, false);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
                         m.phase = 0; m.k = 0; m.have_lo = false;
-                        has_cell = true; have_result = false; my_ty = ty; units += p.azim_num;
+                        has_cell = true; have_result = false; units += p.azim_num;
                         done_now = false;
                     } else {
                         for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
@@ -552,11 +546,18 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
             cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
                 has_cell = false; finished_cell = true;
-                if (p.row_done) { __threadfence_system(); atomicAdd(p.row_done + my_ty, 1u); }  // this cell's outputs are visible
+                if (p.row_done) { __threadfence_system(); atomicAdd(p.row_done + (((int)(my_cell >> 16) - p.row_begin) >> 2), 1u); }  // this cell's outputs are visible
             }
         }
         __syncwarp();
         if (need_ray) {
+            // the cell's frame (12 registers) is not kept across the traversal loop: three cached loads rebuild it
+            const int ci = (int)(my_cell >> 16), cj = (int)(my_cell & 0xFFFFu);
+            const size_t c = (size_t)ci * p.dim_in_1 + cj;
+            const F3 nrm = f3(__ldg(p.vec_norm + 3 * c), __ldg(p.vec_norm + 3 * c + 1), __ldg(p.vec_norm + 3 * c + 2));
+            const F3 nth = f3(__ldg(p.vec_north + 3 * c), __ldg(p.vec_north + 3 * c + 1), __ldg(p.vec_north + 3 * c + 2));
+            const float4 v = __ldg(sv.vert4 + (size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1));
+            const Frame f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
             const F3 D1 = ray_dir(s, f, ie, m.k);
             const F3 D2 = lo_ie >= 0 ? ray_dir(s, f, lo_ie, m.k) : D1;
             const bool two = wq2_start(sv, sh, warp, lane, L, f.org, D1, D2);

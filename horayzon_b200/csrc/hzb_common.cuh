@@ -160,6 +160,11 @@ int launch_svf(int kind, const float* d_azim, const float* d_hori, const float* 
 int launch_slope(int method, const float* d_x, const float* d_y, const float* d_z, const float* d_rot, int ny, int nx,
                  int output_rot, float* d_out, cudaStream_t st);
 
+// hostcopy.cu: staging engine of the host tier (pinned ring + worker threads)
+void host_prefault(void* p, size_t bytes);                                       // populate fresh pages (content untouched)
+int staged_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst_host is complete
+int staged_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);   // returns when src_host has been read
+
 // number of SMs of the current device (cached)
 int sm_count();
 
