@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         const int thr = min(refill_thr, __popc(cell_mask));
         __syncwarp();
         // (C) shared traversal loop
-        while (__popc(wq2_step(sv, sh, warp, lane, tid, L, pend_est, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
+        while (__popc(wq2_step<true, false>(sv, sh, warp, lane, tid, L, pend_est, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
     }
     flush_counters(cnt, units, counters);
 }

@@ -82,8 +82,9 @@ __device__ __forceinline__ bool wq2_start(const SceneView& sv, Wq2Shared& sh, in
     return same;
 }
 
-// Box test of one child for both rays.
-__device__ __forceinline__ bool wide2_child_test(const uint4 r, const Wq2Lane& L, float tfar) {
+// Box test of one child for both rays (TWO) or for ray 1 only.  key = entry distance.
+template <bool TWO>
+__device__ __forceinline__ bool wide2_child_test(const uint4 r, const Wq2Lane& L, float tfar, float& key) {
     const unsigned int selx = L.selxy, sely = L.selxy >> 16;       // PRMT reads the low 16 selector bits only
     const float qnx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selx));
     const float qfx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selx ^ 0x0022u));
@@ -94,12 +95,18 @@ __device__ __forceinline__ bool wide2_child_test(const uint4 r, const Wq2Lane& L
     float za = fmaf(qzl, L.A1z, L.B1z), zb = fmaf(qzh, L.A1z, L.B1z);
     const float tmin1 = fmaxf(fmaxf(fmaf(qnx, L.A1x, L.B1x), fmaf(qny, L.A1y, L.B1y)), fmaxf(fminf(za, zb), 0.0f));
     const float tmax1 = fminf(fminf(fmaf(qfx, L.A1x, L.B1x), fmaf(qfy, L.A1y, L.B1y)), fminf(fmaxf(za, zb), tfar));
-    za = fmaf(qzl, L.A2z, L.B2z); zb = fmaf(qzh, L.A2z, L.B2z);
-    const float tmin2 = fmaxf(fmaxf(fmaf(qnx, L.A2x, L.B2x), fmaf(qny, L.A2y, L.B2y)), fmaxf(fminf(za, zb), 0.0f));
-    const float tmax2 = fminf(fminf(fmaf(qfx, L.A2x, L.B2x), fmaf(qfy, L.A2y, L.B2y)), fminf(fmaxf(za, zb), tfar));
     // no relative slack on tmax: the extra quantum on every plane (bvh_wide.cu) leaves half a
     // quantum (7.6e-6 of the scene extent) beyond the fold error, the rounding of t is ~1e-7 of it
-    return ((tmin1 <= tmax1) || (tmin2 <= tmax2)) && (r.w != WIDE_EMPTY);
+    bool hit = tmin1 <= tmax1;
+    key = tmin1;
+    if (TWO) {
+        za = fmaf(qzl, L.A2z, L.B2z); zb = fmaf(qzh, L.A2z, L.B2z);
+        const float tmin2 = fmaxf(fmaxf(fmaf(qnx, L.A2x, L.B2x), fmaf(qny, L.A2y, L.B2y)), fmaxf(fminf(za, zb), 0.0f));
+        const float tmax2 = fminf(fminf(fmaf(qfx, L.A2x, L.B2x), fmaf(qfy, L.A2y, L.B2y)), fminf(fmaxf(za, zb), tfar));
+        hit = hit || (tmin2 <= tmax2);
+        key = fminf(tmin1, tmin2);
+    }
+    return hit && (r.w != WIDE_EMPTY);
 }
 
 // ---- two rays against one primitive -------------------------------------------------
@@ -128,7 +135,8 @@ __device__ __forceinline__ bool depth_ok(F3 v0, F3 Ng, F3 D, float tfar) {
     return t >= 0.0f && t <= tfar;
 }
 
-// Same decisions as prim_hit<false>(.., D1, ..) and prim_hit<false>(.., D2, ..).
+// Same decisions as prim_hit<false>(.., D1, ..) and (TWO) prim_hit<false>(.., D2, ..).
+template <bool TWO>
 __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 O, F3 D1, F3 D2, float tfar, bool& h1, bool& h2) {
     h1 = false; h2 = false;
     if (prim < s.num_quads) {
@@ -142,11 +150,15 @@ __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 
         const F3 f0 = sub_rn(b, d), f1 = sub_rn(d, c);                             // triangle 2 (its e2 = c - b = -e2)
         const F3 C0 = cross_f(e0, add_rn(c, a)), C1 = cross_f(e1, add_rn(a, b)), C2 = cross_f(e2, add_rn(b, c));
         const F3 G0 = cross_f(f0, add_rn(b, d)), G1 = cross_f(f1, add_rn(d, c));
-        const float W1 = dot_f(C2, D1), W2 = dot_f(C2, D2);
+        const float W1 = dot_f(C2, D1);
         const bool a11 = edges_accept(dot_f(C0, D1), dot_f(C1, D1), W1);
-        const bool a12 = edges_accept(dot_f(C0, D2), dot_f(C1, D2), W2);
         const bool a21 = edges_accept(dot_f(G0, D1), dot_f(G1, D1), -W1);   // reversed diagonal: exact negative
-        const bool a22 = edges_accept(dot_f(G0, D2), dot_f(G1, D2), -W2);
+        bool a12 = false, a22 = false;
+        if (TWO) {
+            const float W2 = dot_f(C2, D2);
+            a12 = edges_accept(dot_f(C0, D2), dot_f(C1, D2), W2);
+            a22 = edges_accept(dot_f(G0, D2), dot_f(G1, D2), -W2);
+        }
         // depth tests (rare): one (triangle, ray) combination per round, shared code
         unsigned int acc = (a11 ? 1u : 0u) | (a12 ? 2u : 0u) | (a21 ? 4u : 0u) | (a22 ? 8u : 0u);
         while (acc) {
@@ -165,12 +177,15 @@ __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 
         const F3 p0 = ld_vert(q), p1 = ld_vert(q + 1), p2 = ld_vert(q + 2);
         float t;
         h1 = tri_hit(p0, p1, p2, O, D1, tfar, t);
-        h2 = tri_hit(p0, p1, p2, O, D2, tfar, t);
+        if (TWO) h2 = tri_hit(p0, p1, p2, O, D2, tfar, t);
     }
 }
 
 // One iteration of the warp's traversal loop.  pend_est: warp-uniform estimate of
 // the number of pending candidates.  Returns the ballot of lanes that still own a packet.
+// TWO: both rays of the packet are live (horizon search); otherwise ray 1 only (shadow).
+// SORT: nearest hit child first (pays off for single any-hit rays that are often occluded).
+template <bool TWO, bool SORT>
 __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared& sh, const int warp, const int lane, const int tid,
                                                  Wq2Lane& L, unsigned int& pend_est, const float tfar, const int wait_thr,
                                                  LaneCounters& cnt, unsigned int* overflow) {
@@ -180,8 +195,9 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
     const uint32_t nidx = trav ? L.node : 0u;
     const uint4* np = reinterpret_cast<const uint4*>(sv.nodes4 + nidx);
     const uint4 r0 = __ldg(np), r1 = __ldg(np + 1), r2 = __ldg(np + 2), r3 = __ldg(np + 3);
-    const bool h0 = wide2_child_test(r0, L, tfar), h1 = wide2_child_test(r1, L, tfar);
-    const bool h2 = wide2_child_test(r2, L, tfar), h3 = wide2_child_test(r3, L, tfar);
+    float t0, t1, t2, t3;
+    const bool h0 = wide2_child_test<TWO>(r0, L, tfar, t0), h1 = wide2_child_test<TWO>(r1, L, tfar, t1);
+    const bool h2 = wide2_child_test<TWO>(r2, L, tfar, t2), h3 = wide2_child_test<TWO>(r3, L, tfar, t3);
     cnt.nodes += trav ? 1u : 0u;
     const unsigned int hm = trav ? ((h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u)) : 0u;
     const unsigned int lfm = (r0.w >> 31) | ((r1.w >> 31) << 1) | ((r2.w >> 31) << 2) | ((r3.w >> 31) << 3);
@@ -190,7 +206,14 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
     {   // first hit internal child next, the rest onto the stack.  No distance order: the upper ray of
         // a packet usually misses and has to visit every box it meets anyway (measured on B200: the
         // nearest-first selection cost 9 % and visited MORE nodes)
-        const unsigned int first = im & (0u - im);     // lowest set bit (0 if no internal hit)
+        unsigned int first = im & (0u - im);     // lowest set bit (0 if no internal hit)
+        if (SORT) {
+            const float k0 = (im & 1u) ? t0 : INFINITY, k1 = (im & 2u) ? t1 : INFINITY;
+            const float k2 = (im & 4u) ? t2 : INFINITY, k3 = (im & 8u) ? t3 : INFINITY;
+            const float kmin = fminf(fminf(k0, k1), fminf(k2, k3));
+            const unsigned int eq = ((k0 == kmin) ? 1u : 0u) | ((k1 == kmin) ? 2u : 0u) | ((k2 == kmin) ? 4u : 0u) | ((k3 == kmin) ? 8u : 0u);
+            first = (im & eq) & (0u - (im & eq));
+        }
         const uint32_t firstc = (first & 1u) ? r0.w : ((first & 2u) ? r1.w : ((first & 4u) ? r2.w : r3.w));
         const unsigned int others = im & ~first;
         int sp = L.sp;
@@ -258,7 +281,7 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
                     const float* r = &sh.ray[warp][0][owner];
                     const F3 O = f3(r[0], r[32], r[64]);
                     const F3 D1 = f3(r[96], r[128], r[160]), D2 = f3(r[192], r[224], r[256]);
-                    prim_hit2(sv, prim, O, D1, D2, tfar, q1, q2);
+                    prim_hit2<TWO>(sv, prim, O, D1, D2, tfar, q1, q2);
                     cnt.prims++;
                 }
                 if (q1) atomicOr(&sh.hit1[warp], 1u << owner);
@@ -274,9 +297,10 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
             __syncwarp();
             if ((m1 | m2) != 0u && lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
             if ((m1 >> lane) & 1u) L.hit1 = true;
-            if ((m2 >> lane) & 1u) L.hit2 = true;
+            if (((TWO ? m2 : m1) >> lane) & 1u) L.hit2 = true;
             if (L.state != 0) {
                 if (L.hit1 && L.hit2) { L.state = 2; L.pc = 0; }          // both decided: drop the rest
+                else if (!TWO) {}
                 else if (L.hit2 && ((m2 >> lane) & 1u)) {                 // lower ray decided: walk on with the upper one only
                     L.A2x = L.A1x; L.A2y = L.A1y; L.A2z = L.A1z; L.B2x = L.B1x; L.B2y = L.B1y; L.B2z = L.B1z;
                 } else if (L.hit1 && ((m1 >> lane) & 1u)) {

@@ -8,6 +8,7 @@
 // closest available stand-in for glibc's float functions).
 #include "hzb_geom.cuh"
 #include "hzb_wq.cuh"
+#include "hzb_wq2.cuh"
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -233,6 +234,89 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq(SceneView sv, Terrai
     }
 }
 
+// Same kernel on the second-generation step (hzb_wq2.cuh, single-ray mode): folded decode bias,
+// per-lane pending lists, shared-diagonal quad test.
+template <bool SW, bool SORT>
+__global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, TerrainParams tp, float sunx, float suny, float sunz,
+                                                            uint8_t* __restrict__ shadow, float* __restrict__ swc,
+                                                            Counters* counters, unsigned int* block_counter, int refill_thr,
+                                                            int wait_thr) {
+    __shared__ Wq2Shared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
+    const unsigned int num_blocks = (unsigned int)((ncell + TW_BLOCK - 1) / TW_BLOCK);
+    const float dot_min = SW ? tp.dot_prod_min : 0.0f;
+    const float tfar = INFINITY;   // shadow_comp.cpp:462, 572
+    unsigned int* overflow = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int units = 0;
+    if (lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
+    unsigned int pend_est = 0;
+    __syncwarp();
+
+    long long next = 0, end = 0;          // warp-uniform: unassigned cells of the current block
+    bool more_blocks = true;
+    long long cell = -1; float dts = 0.f, dns = 0.f;
+    Wq2Lane L; L.state = 0; L.hit1 = L.hit2 = false; L.node = WQ_NONE; L.sp = 0; L.pc = 0;
+    L.A1x = L.A1y = L.A1z = L.B1x = L.B1y = L.B1z = 0.f; L.A2x = L.A2y = L.A2z = L.B2x = L.B2y = L.B2z = 0.f;
+    L.selxy = 0x74107410u;
+
+    while (true) {
+        // (1) retire finished rays (shadow_comp.cpp:468-472 / 578-586) and hand out new cells
+        if (cell >= 0 && L.state == 0) {
+            if (SW) {
+                if (L.hit1) swc[cell] = 0.0f;
+                else { if (dns < dot_min) dns = dot_min; swc[cell] = __fmul_rn(__fdiv_rn(dts, dns), tp.surf_enl_fac[cell]); }
+            } else shadow[cell] = L.hit1 ? 2 : 0;
+            cell = -1;
+        }
+        while (true) {
+            const bool want = L.state == 0;
+            const unsigned int wmask = __ballot_sync(FULL, want);
+            if (wmask == 0u) break;
+            if (next >= end) {
+                if (!more_blocks) break;
+                unsigned int b = 0;
+                if (lane == 0) b = atomicAdd(block_counter, 1u);
+                b = __shfl_sync(FULL, b, 0);
+                if (b >= num_blocks) { more_blocks = false; break; }
+                next = (long long)b * TW_BLOCK; end = min(next + (long long)TW_BLOCK, ncell);
+            }
+            const long long mine = next + __popc(wmask & lt_mask);
+            next += __popc(wmask);
+            if (want && mine < end) {
+                if (tp.mask[mine] != 1) {
+                    if (SW) swc[mine] = tp.sw_dir_cor_fill; else shadow[mine] = 3;
+                } else {
+                    units++;
+                    F3 org, sun;
+                    if (terrain_cell_setup<SW>(sv, tp, mine, sunx, suny, sunz, org, sun, dts, dns)) {
+                        wq2_start(sv, sh, warp, lane, L, org, sun, sun);
+                        cell = mine; cnt.rays++;
+                    } else {
+                        if (SW) swc[mine] = 0.0f; else shadow[mine] = 1;   // self-shaded (:474-478 / :588-592)
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, L.state != 0) == 0u) break;
+        const int thr = (more_blocks || next < end) ? refill_thr : 1;
+        __syncwarp();
+        // (2) shared warp-queue traversal (hzb_wq2.cuh)
+        while (__popc(wq2_step<false, SORT>(sv, sh, warp, lane, tid, L, pend_est, tfar, wait_thr, cnt, overflow)) >= thr) {}
+    }
+    unsigned int r = cnt.rays, n = cnt.nodes, pp = cnt.prims, u = units;
+    for (int o = 16; o > 0; o >>= 1) {
+        r += __shfl_xor_sync(FULL, r, o); n += __shfl_xor_sync(FULL, n, o);
+        pp += __shfl_xor_sync(FULL, pp, o); u += __shfl_xor_sync(FULL, u, o);
+    }
+    if (lane == 0 && (r | n | pp | u)) {
+        atomicAdd(&counters->rays, (unsigned long long)r); atomicAdd(&counters->node_visits, (unsigned long long)n);
+        atomicAdd(&counters->prim_tests, (unsigned long long)pp); atomicAdd(&counters->units, (unsigned long long)u);
+    }
+}
+
 }  // namespace
 
 int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* d_out, cudaStream_t st) {
@@ -242,7 +326,10 @@ int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* 
     if (simple) k_terrain<false><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters);
     else {
         HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-        k_terrain_wq<false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 6);
+        const char* kv = getenv("HZB_SHADOW_KERNEL");
+        if (kv && !strcmp(kv, "wq1")) k_terrain_wq<false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 6);
+        else if (!(kv && !strcmp(kv, "sort"))) k_terrain_wq2<false, false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 3);
+        else k_terrain_wq2<false, true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 3);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;
@@ -254,7 +341,10 @@ int launch_sw_dir_cor(Scene& s, const TerrainParams& tp, const float* sun, float
     if (simple) k_terrain<true><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters);
     else {
         HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-        k_terrain_wq<true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 6);
+        const char* kv = getenv("HZB_SHADOW_KERNEL");
+        if (kv && !strcmp(kv, "wq1")) k_terrain_wq<true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 6);
+        else if (!(kv && !strcmp(kv, "sort"))) k_terrain_wq2<true, false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 3);
+        else k_terrain_wq2<true, true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 3);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;

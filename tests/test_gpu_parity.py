@@ -71,9 +71,10 @@ def test_shadow_kernel_variants_agree(mods, monkeypatch):
     sun = hb.synthetic.sun_positions_diurnal(8)[2]
     a = np.empty(mask.shape, np.uint8); b = np.empty(mask.shape, np.uint8)
     t.shadow(sun, a)
-    monkeypatch.setenv("HZB_SHADOW_KERNEL", "simple")
-    t.shadow(sun, b)
-    assert np.array_equal(a, b)
+    for variant in ("simple", "wq1", "sort"):   # per-lane BVH2 kernel, first-generation step, nearest-first traversal
+        monkeypatch.setenv("HZB_SHADOW_KERNEL", variant)
+        t.shadow(sun, b)
+        assert np.array_equal(a, b), variant
 
 
 def test_horizon_gridded_cfg2_shrunk(mods):
