@@ -284,12 +284,12 @@ def run_ours(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         if it > 0:  # first call is warm-up (context, allocator)
             e2e_times.append(float(dt[0]))
-    e2e_s = statistics.mean(e2e_times) if e2e_times else float('nan')
+    e2e_s = statistics.median(e2e_times) if e2e_times else float('nan')
 
     if rank == 0:
         peak, peak_src = measured_peak()
         algo_bytes_per_unit = 4.0 + 37.0 / K          # compulsory traffic
-        # dominant kernel = k_horizon_gridded; at N > 1 each rank launches it on units/N
+        # dominant kernel = k_horizon_wq6 (launched by hzb_horizon_gridded_dev); at N > 1 each rank launches it on units/N
         achieved = algo_bytes_per_unit * (units_step / world) / (kern_ms_max * 1e-3) / 1e9
         rays = float(ssum[2])
         line = {
@@ -303,11 +303,12 @@ def run_ours(args):
             "e2e": {"value": units_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3,
                     "api": "horayzon_b200.horizon.horizon_gridded + topo_param.sky_view_factor (host ndarray in/out, "
-                           "pageable like the reference wrapper; H2D + BVH build + kernels + D2H timed)"},
+                           "pageable like the reference wrapper; H2D + BVH build + kernels + D2H timed; median of %d calls "
+                           "after one warm-up call)" % len(e2e_times)},
             "gpu_launches": int(2 * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
-                         "kernel": "k_horizon_gridded", "kernel_ms": kern_ms_max,
+                         "kernel": "k_horizon_wq6", "kernel_ms": kern_ms_max,
                          "algorithmic_bytes_per_unit": algo_bytes_per_unit,
                          "note": "compulsory bytes only (output store + per-cell inputs); BVH traversal is "
                                  "latency/L2-bound, see DESIGN.md"},
@@ -333,7 +334,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -285,7 +285,7 @@ struct LaneSM {
     // search state (horizon_comp.cpp:387-498 unrolled into states)
     int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
     int k, cur, prev, count, prev_az;   // during a bisection (phase 1) prev / count hold the bits of lim_up / lim_low
-    bool have_lo, lo_hit;   // packet kernels: the cast at prev-5 travelled with the cast at prev+5
+    int spec_ie; bool spec_hit;   // packet kernels: table index / result of the cast that travelled with the last one (-1: none)
 };
 
 template <int ALG, bool PK>
@@ -293,7 +293,9 @@ __device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int
     // returns true if a cast is required (cast_ie set), false if the azimuth needs none
     const int top = s.elev_num - 1;
     if (ALG == 0) {
-        m.phase = 4; m.prev = 0; m.cur = min(10, top); cast_ie = m.cur; return true;
+        m.phase = 4; m.prev = 0; m.cur = min(10, top); cast_ie = m.cur;
+        if (PK) lo_ie = min(m.cur + 10, top);                   // the next sample, should this one hit
+        return true;
     } else if (ALG == 1 || m.k == 0) {
         m.phase = 1; m.prev = __float_as_int(s.up); m.count = __float_as_int(s.low);
         m.cur = index_of(s, midpoint(s.up, s.low));
@@ -311,18 +313,29 @@ __device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int
 // Consume the result of the last cast (if any) and move on until the next cast
 // is known or the cell is finished.  Returns true with cast_ie set when a ray
 // must be traced; false when the cell is complete.
-// PK (packet kernels): the first cast of a guess_constant azimuth (index prev+5) may be
-// traced together with the first cast of the downward search (prev-5): lo_ie >= 0 names
-// it, the kernel sets m.have_lo / m.lo_hit, and the downward search consumes that result
-// instead of casting (counted in extra_rays exactly when the reference would have cast).
+// PK (packet kernels): every cast of the stepping searches names a COMPANION in lo_ie --
+// the cast the reference makes next if this one goes the expected way (prev-5 beside the
+// first prev+5 of a guess_constant azimuth, otherwise the next index in the direction of
+// travel).  The kernel traces both as one packet and records the companion's index and
+// result in m.spec_ie / m.spec_hit; when the search then asks for exactly that index the
+// stored result is consumed instead of casting, and counted in extra_rays -- i.e. only
+// when the reference would have cast it.  An unused companion result is dropped.
 template <int ALG, bool PK>
 __device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have_result, bool hit, OutBuf& ob, int& cast_ie,
                                            int& lo_ie, unsigned int& extra_rays) {
     const int top = s.elev_num - 1;
     lo_ie = -1;
+#define HZB_SM_CAST(COMPANION)                                                                        \
+    do {                                                                                              \
+        if (PK && m.spec_ie == m.cur) { m.spec_ie = -1; hit = m.spec_hit; ++extra_rays; goto again; } \
+        cast_ie = m.cur;                                                                              \
+        if (PK) { lo_ie = (COMPANION); if (lo_ie == cast_ie) lo_ie = -1; }                            \
+        return true;                                                                                  \
+    } while (0)
+again:
     while (true) {
         if (!have_result) {  // start of an azimuth
-            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie)) return true;
+            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie)) { if (lo_ie == cast_ie) lo_ie = -1; return true; }
             // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
             hit = false; have_result = true;
             // (emulate loop exit below)
@@ -343,30 +356,30 @@ __device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have
         } else if (m.phase == 2) {
             m.count++;
             if (m.cur == top) hit = false;            // termination rule
-            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); cast_ie = m.cur; return true; }
+            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }
             if (m.count <= 1) {                       // first upward cast missed: search downwards (:471-488)
                 m.phase = 3;
                 m.prev = min(m.prev_az + 5, top); m.cur = max(m.prev - 10, 0);
-                if (PK && m.have_lo) { m.have_lo = false; hit = m.lo_hit; ++extra_rays; continue; }
-                cast_ie = m.cur; return true;
+                HZB_SM_CAST(max(m.cur - 10, 0));
             }
             const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
             ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
         } else if (m.phase == 3) {
             if (m.cur == 0) hit = true;               // termination rule
-            if (!hit) { m.prev = m.cur; m.cur = max(m.cur - 10, 0); cast_ie = m.cur; return true; }
+            if (!hit) { m.prev = m.cur; m.cur = max(m.cur - 10, 0); HZB_SM_CAST(max(m.cur - 10, 0)); }
             const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
             ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
         } else {  // phase 4: discrete sampling (:309-331)
             if (m.cur == top) hit = false;
-            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); cast_ie = m.cur; return true; }
+            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }
             ob.put(m.k, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
         }
         // azimuth finished
-        m.k++;
+        m.k++; m.spec_ie = -1;
         if (m.k >= s.azim_num) { m.phase = 0; return false; }
         have_result = false;
     }
+#undef HZB_SM_CAST
 }
 
 // ===========================================================================
@@ -399,7 +412,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
     unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
     // per-lane cell and search state
     LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
-    m.have_lo = m.lo_hit = false;
+    m.spec_ie = -1; m.spec_hit = false;
     Frame f; OutBuf ob; ob.init(nullptr, false);
     bool has_cell = false, have_result = false;
     int my_ty = 0;
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
 
     unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
     LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
-    m.have_lo = m.lo_hit = false;
+    m.spec_ie = -1; m.spec_hit = false;
     OutBuf ob; ob.init(nullptr, false);
     unsigned int my_cell = 0;   // (row << 16) | column of the lane's cell: its frame is rebuilt at every ray set-up
     bool has_cell = false, have_result = false;
@@ -525,7 +538,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                     if (p.mask[c] == 1) {
                         my_cell = ((unsigned int)ci << 16) | (unsigned int)cj;    // dims <= 32767 (horizon.pyx:149-151)
                         ob.init(out, false);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
-                        m.phase = 0; m.k = 0; m.have_lo = false;
+                        m.phase = 0; m.k = 0; m.spec_ie = -1;
                         has_cell = true; have_result = false; units += p.azim_num;
                         done_now = false;
                     } else {
@@ -541,7 +554,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         int ie = 0, lo_ie = -1;
         if (has_cell && L.state == 0) {
             unsigned int extra = 0;
-            m.lo_hit = L.hit2;
+            m.spec_hit = L.hit2;
             need_ray = sm_advance<ALG, true>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
             cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
@@ -561,7 +574,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
             const F3 D1 = ray_dir(s, f, ie, m.k);
             const F3 D2 = lo_ie >= 0 ? ray_dir(s, f, lo_ie, m.k) : D1;
             const bool two = wq2_start(sv, sh, warp, lane, L, f.org, D1, D2);
-            m.have_lo = two && lo_ie >= 0;
+            m.spec_ie = (two && lo_ie >= 0) ? lo_ie : -1;
             have_result = true;
         }
         if (__any_sync(FULL, finished_cell) && (more_tiles || next_cell < 32)) continue;   // give them a new cell first
