@@ -34,6 +34,8 @@ class Workers {   // persistent pool: run(f, n) executes f(0..n-1) on the pool a
     Workers() {
         unsigned hc = std::thread::hardware_concurrency();
         int n = (int)(hc ? hc : 8) / 2;
+        const char* lw = getenv("LOCAL_WORLD_SIZE");     // one process per GPU (torchrun): share the host cores
+        if (lw && atoi(lw) > 1) n /= atoi(lw);
         n = std::max(2, std::min(n, 12));
         const char* e = getenv("HZB_HOST_THREADS");
         if (e && atoi(e) > 0) n = std::min(atoi(e), 64);
