@@ -1,12 +1,12 @@
 """horayzon_b200 -- B200-native drop-in for HORAYZON's horizon / shadow / SVF path.
 
-``horizon``, ``shadow`` and ``topo_param`` mirror the reference modules of the
-same names (``horayzon/__init__.py:1-12``); ``resident`` is the additive
+``horizon``, ``shadow``, ``topo_param``, ``transform`` and ``direction`` mirror the
+reference modules of the same names (``horayzon/__init__.py:1-12``); ``resident`` is the additive
 device-pointer tier used for benchmarking and multi-GPU sharding; ``synthetic``
 holds the synthetic DEM recipes and the vertex-buffer wire format.
 """
 try:
-    from . import horizon, shadow, topo_param  # noqa: F401  (compiled Cython wrappers)
+    from . import horizon, shadow, topo_param, transform, direction  # noqa: F401  (compiled Cython wrappers)
 except ImportError as exc:  # fail loudly: there is no Python/CPU fallback
     raise ImportError(
         "horayzon_b200 extension modules are not built (" + str(exc) + "); run "

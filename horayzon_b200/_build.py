@@ -4,7 +4,7 @@
 
 1. ``csrc/*.cu`` -> ``libhorayzon_b200.so`` with nvcc for sm_100a
    (``-gencode arch=compute_100a,code=sm_100a -lineinfo``).
-2. ``horizon.pyx``, ``shadow.pyx``, ``topo_param.pyx`` -> C (Cython) -> extension
+2. ``horizon.pyx``, ``shadow.pyx``, ``topo_param.pyx``, ``transform.pyx``, ``direction.pyx`` -> C (Cython) -> extension
    modules next to this file, linked against the library with rpath $ORIGIN.
 The build products stay in-tree (git-ignored) so that they travel to the GPU box.
 """
@@ -15,7 +15,7 @@ import sysconfig
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-PYX = ("horizon", "shadow", "topo_param")
+PYX = ("horizon", "shadow", "topo_param", "transform", "direction")
 GCC = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
 
 

@@ -49,6 +49,14 @@ int parse_geom_type(const char* s) {
     return -1;
 }
 
+int parse_ellps(const char* s) {
+    if (!s) return -1;
+    if (!strcmp(s, "sphere")) return 0;
+    if (!strcmp(s, "GRS80")) return 1;
+    if (!strcmp(s, "WGS84")) return 2;
+    return -1;
+}
+
 static int require_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -83,6 +91,23 @@ struct DevBuf {  // RAII device buffer
         return 0;
     }
 };
+
+// ------------------------------------------------- coordinate preparation (row "next 3")
+// Host-tier helpers: upload / download through the staging engine when the array is large.
+template <typename T>
+static int up_big(DevBuf<T>& d, const T* h, size_t n) {
+    HZB_TRY(d.alloc(n));
+    if (n * sizeof(T) >= ((size_t)8 << 20)) { HZB_TRY(staged_h2d(d.p, h, n * sizeof(T), nullptr)); }
+    else HZB_CUDA(cudaMemcpy(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+template <typename T>
+static int down_big(T* h, const DevBuf<T>& d, size_t n) {
+    HZB_CUDA(cudaStreamSynchronize(nullptr));
+    if (n * sizeof(T) >= ((size_t)8 << 20)) { HZB_TRY(staged_d2h(h, d.p, n * sizeof(T), nullptr)); }
+    else HZB_CUDA(cudaMemcpy(h, d.p, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 }  // namespace hzb
 
@@ -484,4 +509,99 @@ int hzb_topographic_openness(const float* azim, const float* hori, int ny, int n
     return integral_host(2, azim, hori, nullptr, ny, nx, K, out);
 }
 
+
+// ---- coordinate preparation, host tier (transform.pyx / direction.pyx loops)
+int hzb_lonlat2ecef(const double* lon, const double* lat, const float* h, long long n, const char* ellps,
+                    double* x_ecef, double* y_ecef, double* z_ecef) {
+    if (require_device()) return 1;
+    const int el = parse_ellps(ellps);
+    if (el < 0) { set_error("Unknown value for 'ellps'"); return 1; }
+    if (n <= 0) return 0;
+    DevBuf<double> a, b, x, y, z; DevBuf<float> c;
+    HZB_TRY(up_big(a, lon, (size_t)n)); HZB_TRY(up_big(b, lat, (size_t)n)); HZB_TRY(up_big(c, h, (size_t)n));
+    HZB_TRY(x.alloc((size_t)n)); HZB_TRY(y.alloc((size_t)n)); HZB_TRY(z.alloc((size_t)n));
+    HZB_TRY(launch_lonlat2ecef(el, a.p, b.p, c.p, n, x.p, y.p, z.p, nullptr));
+    HZB_TRY(down_big(x_ecef, x, (size_t)n)); HZB_TRY(down_big(y_ecef, y, (size_t)n)); HZB_TRY(down_big(z_ecef, z, (size_t)n));
+    return 0;
+}
+int hzb_ecef2enu(const double* x_ecef, const double* y_ecef, const double* z_ecef, long long n, double x_ecef_or,
+                 double y_ecef_or, double z_ecef_or, double lon_or, double lat_or, float* x_enu, float* y_enu, float* z_enu) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DevBuf<double> a, b, c; DevBuf<float> x, y, z;
+    HZB_TRY(up_big(a, x_ecef, (size_t)n)); HZB_TRY(up_big(b, y_ecef, (size_t)n)); HZB_TRY(up_big(c, z_ecef, (size_t)n));
+    HZB_TRY(x.alloc((size_t)n)); HZB_TRY(y.alloc((size_t)n)); HZB_TRY(z.alloc((size_t)n));
+    HZB_TRY(launch_ecef2enu(a.p, b.p, c.p, n, x_ecef_or, y_ecef_or, z_ecef_or, lon_or, lat_or, x.p, y.p, z.p, nullptr));
+    HZB_TRY(down_big(x_enu, x, (size_t)n)); HZB_TRY(down_big(y_enu, y, (size_t)n)); HZB_TRY(down_big(z_enu, z, (size_t)n));
+    return 0;
+}
+int hzb_ecef2enu_vector(const float* vec_ecef, long long n, double lon_or, double lat_or, float* vec_enu) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DevBuf<float> v, o;
+    HZB_TRY(up_big(v, vec_ecef, (size_t)n * 3)); HZB_TRY(o.alloc((size_t)n * 3));
+    HZB_TRY(launch_ecef2enu_vector(v.p, n, lon_or, lat_or, o.p, nullptr));
+    return down_big(vec_enu, o, (size_t)n * 3);
+}
+int hzb_surf_norm(const double* lon, const double* lat, long long n, float* vec_norm_ecef) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DevBuf<double> a, b; DevBuf<float> o;
+    HZB_TRY(up_big(a, lon, (size_t)n)); HZB_TRY(up_big(b, lat, (size_t)n)); HZB_TRY(o.alloc((size_t)n * 3));
+    HZB_TRY(launch_surf_norm(a.p, b.p, n, o.p, nullptr));
+    return down_big(vec_norm_ecef, o, (size_t)n * 3);
+}
+int hzb_north_dir(const double* x_ecef, const double* y_ecef, const double* z_ecef, const float* vec_norm_ecef, long long n,
+                  const char* ellps, float* vec_north_ecef) {
+    if (require_device()) return 1;
+    const int el = parse_ellps(ellps);
+    if (el < 0) { set_error("Unknown value for 'ellps'"); return 1; }
+    if (n <= 0) return 0;
+    DevBuf<double> a, b, c; DevBuf<float> v, o;
+    HZB_TRY(up_big(a, x_ecef, (size_t)n)); HZB_TRY(up_big(b, y_ecef, (size_t)n)); HZB_TRY(up_big(c, z_ecef, (size_t)n));
+    HZB_TRY(up_big(v, vec_norm_ecef, (size_t)n * 3)); HZB_TRY(o.alloc((size_t)n * 3));
+    HZB_TRY(launch_north_dir(el, a.p, b.p, c.p, v.p, n, o.p, nullptr));
+    return down_big(vec_north_ecef, o, (size_t)n * 3);
+}
+int hzb_wgs2swiss(const double* lon, const double* lat, const float* h_wgs, long long n, double* e, double* nn, float* h_ch) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DevBuf<double> a, b, x, y; DevBuf<float> c, z;
+    HZB_TRY(up_big(a, lon, (size_t)n)); HZB_TRY(up_big(b, lat, (size_t)n)); HZB_TRY(up_big(c, h_wgs, (size_t)n));
+    HZB_TRY(x.alloc((size_t)n)); HZB_TRY(y.alloc((size_t)n)); HZB_TRY(z.alloc((size_t)n));
+    HZB_TRY(launch_wgs2swiss(a.p, b.p, c.p, n, x.p, y.p, z.p, nullptr));
+    HZB_TRY(down_big(e, x, (size_t)n)); HZB_TRY(down_big(nn, y, (size_t)n)); HZB_TRY(down_big(h_ch, z, (size_t)n));
+    return 0;
+}
+int hzb_swiss2wgs(const double* e, const double* nn, const float* h_ch, long long n, double* lon, double* lat, float* h_wgs) {
+    if (require_device()) return 1;
+    if (n <= 0) return 0;
+    DevBuf<double> a, b, x, y; DevBuf<float> c, z;
+    HZB_TRY(up_big(a, e, (size_t)n)); HZB_TRY(up_big(b, nn, (size_t)n)); HZB_TRY(up_big(c, h_ch, (size_t)n));
+    HZB_TRY(x.alloc((size_t)n)); HZB_TRY(y.alloc((size_t)n)); HZB_TRY(z.alloc((size_t)n));
+    HZB_TRY(launch_swiss2wgs(a.p, b.p, c.p, n, x.p, y.p, z.p, nullptr));
+    HZB_TRY(down_big(lon, x, (size_t)n)); HZB_TRY(down_big(lat, y, (size_t)n)); HZB_TRY(down_big(h_wgs, z, (size_t)n));
+    return 0;
+}
+int hzb_rotation_matrix_glob2loc(const float* vec_north_enu, const float* vec_norm_enu, int ny, int nx, float* rot_mat) {
+    if (require_device()) return 1;
+    if (ny < 0 || nx < 0) { set_error("invalid dimensions"); return 1; }
+    const size_t nc = (size_t)ny * nx, no = (size_t)(ny + 2) * (nx + 2) * 9;
+    DevBuf<float> a, b, o;
+    HZB_TRY(up_big(a, vec_north_enu, nc * 3)); HZB_TRY(up_big(b, vec_norm_enu, nc * 3)); HZB_TRY(o.alloc(no));
+    HZB_TRY(launch_rotmat(a.p, b.p, ny, nx, o.p, nullptr));
+    return down_big(rot_mat, o, no);
+}
+// additive, resident tier: the whole preparation chain fused, inputs and outputs in HBM
+int hzb_prep_enu_dev(const double* d_lon, const double* d_lat, const float* d_elev, int ny, int nx, const char* ellps,
+                     double x_ecef_or, double y_ecef_or, double z_ecef_or, double lon_or, double lat_or, int offset_0,
+                     int offset_1, int dim_in_0, int dim_in_1, float* d_vert_grid, float* d_vec_norm, float* d_vec_north,
+                     void* stream) {
+    const int el = parse_ellps(ellps);
+    if (el < 0) { set_error("Unknown value for 'ellps'"); return 1; }
+    if (!d_lon || !d_lat || !d_elev || !d_vert_grid) { set_error("null pointer argument"); return 1; }
+    if ((d_vec_norm == nullptr) != (d_vec_north == nullptr)) { set_error("vec_norm and vec_north go together"); return 1; }
+    return launch_prep_enu(el, d_lon, d_lat, d_elev, ny, nx, x_ecef_or, y_ecef_or, z_ecef_or, lon_or, lat_or, offset_0, offset_1,
+                           dim_in_0, dim_in_1, d_vert_grid, d_vec_norm, d_vec_north, (cudaStream_t)stream);
+}
 }  // extern "C"

@@ -160,6 +160,21 @@ int launch_svf(int kind, const float* d_azim, const float* d_hori, const float* 
 int launch_slope(int method, const float* d_x, const float* d_y, const float* d_z, const float* d_rot, int ny, int nx,
                  int output_rot, float* d_out, cudaStream_t st);
 
+// transform.cu (scope row "next 3"): coordinate preparation; all pointers are DEVICE pointers
+int launch_lonlat2ecef(int ellps, const double* lon, const double* lat, const float* h, long long n, double* x, double* y, double* z, cudaStream_t st);
+int launch_ecef2enu(const double* x, const double* y, const double* z, long long n, double x0, double y0, double z0, double lon_or,
+                    double lat_or, float* xe, float* ye, float* ze, cudaStream_t st);
+int launch_ecef2enu_vector(const float* v, long long n, double lon_or, double lat_or, float* o, cudaStream_t st);
+int launch_surf_norm(const double* lon, const double* lat, long long n, float* o, cudaStream_t st);
+int launch_north_dir(int ellps, const double* x, const double* y, const double* z, const float* nrm, long long n, float* o, cudaStream_t st);
+int launch_wgs2swiss(const double* lon, const double* lat, const float* h, long long n, double* e, double* nn, float* hc, cudaStream_t st);
+int launch_swiss2wgs(const double* e, const double* nn, const float* hc, long long n, double* lon, double* lat, float* h, cudaStream_t st);
+int launch_rotmat(const float* north, const float* norm, int ny, int nx, float* out, cudaStream_t st);
+int launch_prep_enu(int ellps, const double* lon, const double* lat, const float* elev, int ny, int nx, double x0, double y0, double z0,
+                    double lon_or, double lat_or, int off0, int off1, int in0, int in1, float* vert_grid, float* vec_norm,
+                    float* vec_north, cudaStream_t st);
+int parse_ellps(const char* s);      // sphere 0, GRS80 1, WGS84 2, unknown -1
+
 // hostcopy.cu: staging engine of the host tier (pinned ring + worker threads)
 void host_prefault(void* p, size_t bytes);                                       // populate fresh pages (content untouched)
 int staged_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst_host is complete

@@ -165,3 +165,23 @@ def topographic_openness_dev(azim, hori, out, stream=None):
     _check(lib().hzb_topographic_openness_dev(ctypes.c_void_p(azim.data_ptr()), ctypes.c_void_p(hori.data_ptr()),
                                               cells, int(hori.shape[-1]), ctypes.c_void_p(out.data_ptr()),
                                               _stream_ptr(stream)))
+
+
+def prep_enu_dev(lon, lat, elev, ellps, trans, offset_0, offset_1, dim_in_0, dim_in_1, vert_grid, vec_norm=None,
+                 vec_north=None, stream=None):
+    """Fused coordinate preparation in HBM (``hzb_prep_enu_dev``): ``lon`` [nx], ``lat`` [ny] (float64 tensors),
+    ``elev`` [ny][nx] (float32) -> ``vert_grid`` [ny][nx][3] and the inner-domain ``vec_norm`` / ``vec_north``
+    [dim_in_0][dim_in_1][3] in ENU coordinates.  ``trans`` carries the TransformerEcef2enu attributes."""
+    L = lib()
+    L.hzb_prep_enu_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_char_p, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                   ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    ny, nx = int(elev.shape[0]), int(elev.shape[1])
+    _check(L.hzb_prep_enu_dev(lon.data_ptr(), lat.data_ptr(), elev.data_ptr(), ny, nx, ellps.encode(),
+                              float(trans.x_ecef_or), float(trans.y_ecef_or), float(trans.z_ecef_or),
+                              float(trans.lon_or), float(trans.lat_or), int(offset_0), int(offset_1), int(dim_in_0),
+                              int(dim_in_1), vert_grid.data_ptr(),
+                              vec_norm.data_ptr() if vec_norm is not None else None,
+                              vec_north.data_ptr() if vec_north is not None else None, _stream_ptr(stream)))
+

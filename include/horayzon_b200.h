@@ -136,6 +136,29 @@ int hzb_slope_plane_meth(const float* x, const float* y, const float* z, const f
 int hzb_slope_vector_meth(const float* x, const float* y, const float* z, const float* rot_mat,
                           int ny, int nx, int output_rot, float* out);
 
+/* "Next" row 8f-3: coordinate preparation on the device.  Replace the loops of
+ * _lonlat2ecef_1d (transform.pyx:60-103), _ecef2enu_1d (:152-189), _ecef2enu_vector_1d
+ * (:231-261), _wgs2swiss_1d (:306-344), _swiss2wgs_1d (:390-432),
+ * rotation_matrix_glob2loc (:490-530), _surf_norm_1d (direction.pyx:48-70) and
+ * _north_dir_1d (direction.pyx:125-178).  n = number of points; vectors are [n][3];
+ * ellps is "sphere", "GRS80" or "WGS84"; *_or are the TransformerEcef2enu attributes
+ * (transform.pyx:437-485).  rot_mat: [(ny+2)][(nx+2)][3][3] with a NaN rim. */
+int hzb_lonlat2ecef(const double* lon, const double* lat, const float* h, long long n, const char* ellps,
+                    double* x_ecef, double* y_ecef, double* z_ecef);
+int hzb_ecef2enu(const double* x_ecef, const double* y_ecef, const double* z_ecef, long long n,
+                 double x_ecef_or, double y_ecef_or, double z_ecef_or, double lon_or, double lat_or,
+                 float* x_enu, float* y_enu, float* z_enu);
+int hzb_ecef2enu_vector(const float* vec_ecef, long long n, double lon_or, double lat_or, float* vec_enu);
+int hzb_surf_norm(const double* lon, const double* lat, long long n, float* vec_norm_ecef);
+int hzb_north_dir(const double* x_ecef, const double* y_ecef, const double* z_ecef, const float* vec_norm_ecef,
+                  long long n, const char* ellps, float* vec_north_ecef);
+int hzb_wgs2swiss(const double* lon, const double* lat, const float* h_wgs, long long n,
+                  double* e, double* nn, float* h_ch);
+int hzb_swiss2wgs(const double* e, const double* nn, const float* h_ch, long long n,
+                  double* lon, double* lat, float* h_wgs);
+int hzb_rotation_matrix_glob2loc(const float* vec_north_enu, const float* vec_norm_enu, int ny, int nx,
+                                 float* rot_mat);
+
 /* ----------------------------------------------------------- resident tier */
 
 /* A scene = DEM vertices (+ optional TIN) and their BVH, resident on `device`.
@@ -174,6 +197,17 @@ int hzb_visible_sky_fraction_dev(const float* d_azim, const float* d_hori,
                                  float* d_out, void* stream);
 int hzb_topographic_openness_dev(const float* d_azim, const float* d_hori,
                                  long long num_cells, int K, float* d_out, void* stream);
+
+/* Additive (no counterpart in the reference): the whole preparation chain of
+ * examples/horizon/gridded_curved_DEM.py:60-90 fused into one kernel with inputs and
+ * outputs in HBM -- lon [nx], lat [ny] (degree, double), elevation [ny][nx] (float) ->
+ * vert_grid [ny][nx][3] (ENU, the wire format of hzb_scene_create / hzb_horizon_gridded
+ * without the padding) and, for the inner domain, vec_norm / vec_north [dim_in_0][dim_in_1][3]
+ * in ENU (both may be NULL).  Same device functions as the step-by-step entry points. */
+int hzb_prep_enu_dev(const double* d_lon, const double* d_lat, const float* d_elev, int ny, int nx,
+                     const char* ellps, double x_ecef_or, double y_ecef_or, double z_ecef_or,
+                     double lon_or, double lat_or, int offset_0, int offset_1, int dim_in_0, int dim_in_1,
+                     float* d_vert_grid, float* d_vec_norm, float* d_vec_north, void* stream);
 
 /* Shadow / sw_dir_cor with a DEVICE output buffer (terrain already resident). */
 int hzb_terrain_shadow_dev(hzb_terrain* t, const float* sun_position_host,

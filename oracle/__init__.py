@@ -226,3 +226,86 @@ def slope_plane_meth(x, y, z, rot_mat=None, output_rot=False):
 def slope_vector_meth(x, y, z, rot_mat=None, output_rot=False):
     """Oracle twin of ``topo_param.slope_vector_meth`` (topo_param.pyx:230-372)."""
     return _slope(lib().orc_slope_vector_meth, x, y, z, rot_mat, output_rot)
+
+
+# ---------------------------------------------------------------------------
+# coordinate preparation (scope row 8f-3): call shapes of horayzon.transform /
+# horayzon.direction (transform.pyx:15-57, 108-149, 194-228, 266-303, 349-387,
+# 490-530; direction.pyx:15-45, 75-122)
+# ---------------------------------------------------------------------------
+_f64p = ctypes.POINTER(ctypes.c_double)
+
+
+def _c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64).ravel()
+
+
+def _c32(a):
+    return np.ascontiguousarray(a, dtype=np.float32).ravel()
+
+
+def lonlat2ecef(lon, lat, h, ellps):
+    a, b, c = _c64(lon), _c64(lat), _c32(h)
+    x, y, z = (np.empty(a.size, np.float64) for _ in range(3))
+    _check(lib().orc_lonlat2ecef(_p(a, _f64p), _p(b, _f64p), _p(c, _f32p), ctypes.c_longlong(a.size), ellps.encode(),
+                                 _p(x, _f64p), _p(y, _f64p), _p(z, _f64p)))
+    return x.reshape(lon.shape), y.reshape(lon.shape), z.reshape(lon.shape)
+
+
+def ecef2enu(x_ecef, y_ecef, z_ecef, trans):
+    a, b, c = _c64(x_ecef), _c64(y_ecef), _c64(z_ecef)
+    x, y, z = (np.empty(a.size, np.float32) for _ in range(3))
+    _check(lib().orc_ecef2enu(_p(a, _f64p), _p(b, _f64p), _p(c, _f64p), ctypes.c_longlong(a.size),
+                              ctypes.c_double(trans.x_ecef_or), ctypes.c_double(trans.y_ecef_or),
+                              ctypes.c_double(trans.z_ecef_or), ctypes.c_double(trans.lon_or), ctypes.c_double(trans.lat_or),
+                              _p(x, _f32p), _p(y, _f32p), _p(z, _f32p)))
+    return x.reshape(x_ecef.shape), y.reshape(x_ecef.shape), z.reshape(x_ecef.shape)
+
+
+def ecef2enu_vector(vec_ecef, trans):
+    v = _c32(vec_ecef)
+    o = np.empty(v.size, np.float32)
+    _check(lib().orc_ecef2enu_vector(_p(v, _f32p), ctypes.c_longlong(v.size // 3), ctypes.c_double(trans.lon_or),
+                                     ctypes.c_double(trans.lat_or), _p(o, _f32p)))
+    return o.reshape(vec_ecef.shape)
+
+
+def surf_norm(lon, lat):
+    a, b = _c64(lon), _c64(lat)
+    o = np.empty(a.size * 3, np.float32)
+    _check(lib().orc_surf_norm(_p(a, _f64p), _p(b, _f64p), ctypes.c_longlong(a.size), _p(o, _f32p)))
+    return o.reshape(lon.shape + (3,))
+
+
+def north_dir(x_ecef, y_ecef, z_ecef, vec_norm_ecef, ellps):
+    a, b, c, v = _c64(x_ecef), _c64(y_ecef), _c64(z_ecef), _c32(vec_norm_ecef)
+    o = np.empty(a.size * 3, np.float32)
+    _check(lib().orc_north_dir(_p(a, _f64p), _p(b, _f64p), _p(c, _f64p), _p(v, _f32p), ctypes.c_longlong(a.size),
+                               ellps.encode(), _p(o, _f32p)))
+    return o.reshape(x_ecef.shape + (3,))
+
+
+def wgs2swiss(lon, lat, h_wgs):
+    a, b, c = _c64(lon), _c64(lat), _c32(h_wgs)
+    e, n = np.empty(a.size, np.float64), np.empty(a.size, np.float64)
+    h = np.empty(a.size, np.float32)
+    _check(lib().orc_wgs2swiss(_p(a, _f64p), _p(b, _f64p), _p(c, _f32p), ctypes.c_longlong(a.size), _p(e, _f64p),
+                               _p(n, _f64p), _p(h, _f32p)))
+    return e.reshape(lon.shape), n.reshape(lon.shape), h.reshape(lon.shape)
+
+
+def swiss2wgs(e, n, h_ch):
+    a, b, c = _c64(e), _c64(n), _c32(h_ch)
+    lon, lat = np.empty(a.size, np.float64), np.empty(a.size, np.float64)
+    h = np.empty(a.size, np.float32)
+    _check(lib().orc_swiss2wgs(_p(a, _f64p), _p(b, _f64p), _p(c, _f32p), ctypes.c_longlong(a.size), _p(lon, _f64p),
+                               _p(lat, _f64p), _p(h, _f32p)))
+    return lon.reshape(e.shape), lat.reshape(e.shape), h.reshape(e.shape)
+
+
+def rotation_matrix_glob2loc(vec_north_enu, vec_norm_enu):
+    ny, nx = vec_north_enu.shape[:2]
+    a, b = _c32(vec_north_enu), _c32(vec_norm_enu)
+    o = np.empty((ny + 2, nx + 2, 3, 3), np.float32)
+    _check(lib().orc_rotation_matrix_glob2loc(_p(a, _f32p), _p(b, _f32p), ny, nx, _p(o, _f32p)))
+    return o

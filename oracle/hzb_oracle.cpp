@@ -28,6 +28,8 @@
 //   shadow helpers ...................... shadow_comp.cpp:96-159
 //   Terrain initialise/shadow/sw_dir_cor  shadow_comp.cpp:318-380, 386-491, 495-605
 //   SVF / VSF / openness ................ topo_param.pyx:412-460, 499-543, 577-603
+//   coordinate preparation .............. transform.pyx:60-103, 152-189, 231-261, 306-344, 390-432, 490-530;
+//                                         direction.pyx:48-70, 125-178                 [scope row 8f-3]
 //
 // What replaces Embree (third-party, absent): any BVH gives the same any-hit
 // DECISION as long as its box test is conservative, so the oracle uses a plain
@@ -847,4 +849,125 @@ int orc_slope_vector_meth(const float* x, const float* y, const float* z, const 
     return 0;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Coordinate preparation (scope row 8f-3).  Double arithmetic in the reference's
+// operation order; pinned by golden vectors from the reference's own compiled
+// transform.pyx / direction.pyx (tests/golden/transform_ref.npz).
+// ---------------------------------------------------------------------------
+namespace {
+static inline double d2r(double a) { return a * (M_PI / 180.0); }          // transform.pyx:537-542
+struct EllpsP { bool sphere; double a, b2_a2, e_2, np_z; };
+static bool ellps_params(const char* ellps, EllpsP* E) {                    // transform.pyx:76-95, direction.pyx:141-154
+    if (!strcmp(ellps, "sphere")) { *E = {true, 6370997.0, 1.0, 0.0, 6370997.0}; return true; }
+    double f;
+    if (!strcmp(ellps, "GRS80")) f = 1.0 / 298.257222101;
+    else if (!strcmp(ellps, "WGS84")) f = 1.0 / 298.257223563;
+    else return false;
+    const double a = 6378137.0, b = a * (1.0 - f);
+    *E = {false, a, (b * b) / (a * a), 1.0 - (b * b) / (a * a), b};
+    return true;
+}
+}  // namespace
+
+extern "C" {
+// _lonlat2ecef_1d (transform.pyx:60-103)
+int orc_lonlat2ecef(const double* lon, const double* lat, const float* h, long long n, const char* ellps,
+                    double* x, double* y, double* z) {
+    EllpsP E;
+    if (!ellps_params(ellps, &E)) { g_err = "Unknown value for 'ellps'"; return 1; }
+    for (long long i = 0; i < n; ++i) {
+        const double sl = sin(d2r(lat[i])), cl = cos(d2r(lat[i])), so = sin(d2r(lon[i])), co = cos(d2r(lon[i]));
+        if (E.sphere) {
+            const double r = E.a + (double)h[i];
+            x[i] = r * cl * co; y[i] = r * cl * so; z[i] = r * sl;
+        } else {
+            const double nn = E.a / sqrt(1.0 - E.e_2 * (sl * sl));
+            x[i] = (nn + (double)h[i]) * cl * co; y[i] = (nn + (double)h[i]) * cl * so;
+            z[i] = (E.b2_a2 * nn + (double)h[i]) * sl;
+        }
+    }
+    return 0;
+}
+// _ecef2enu_1d (transform.pyx:152-189)
+int orc_ecef2enu(const double* xe, const double* ye, const double* ze, long long n, double x0, double y0, double z0,
+                 double lon_or, double lat_or, float* x, float* y, float* z) {
+    const double so = sin(d2r(lon_or)), co = cos(d2r(lon_or)), sl = sin(d2r(lat_or)), cl = cos(d2r(lat_or));
+    for (long long i = 0; i < n; ++i) {
+        const double dx = xe[i] - x0, dy = ye[i] - y0, dz = ze[i] - z0;
+        x[i] = (float)(-so * dx + co * dy);
+        y[i] = (float)(-sl * co * dx - sl * so * dy + cl * dz);
+        z[i] = (float)(cl * co * dx + cl * so * dy + sl * dz);
+    }
+    return 0;
+}
+// _ecef2enu_vector_1d (transform.pyx:231-261)
+int orc_ecef2enu_vector(const float* v, long long n, double lon_or, double lat_or, float* o) {
+    const double so = sin(d2r(lon_or)), co = cos(d2r(lon_or)), sl = sin(d2r(lat_or)), cl = cos(d2r(lat_or));
+    for (long long i = 0; i < n; ++i) {
+        const double a = v[3 * i], b = v[3 * i + 1], c = v[3 * i + 2];
+        o[3 * i] = (float)(-so * a + co * b);
+        o[3 * i + 1] = (float)(-sl * co * a - sl * so * b + cl * c);
+        o[3 * i + 2] = (float)(cl * co * a + cl * so * b + sl * c);
+    }
+    return 0;
+}
+// _surf_norm_1d (direction.pyx:48-70)
+int orc_surf_norm(const double* lon, const double* lat, long long n, float* o) {
+    for (long long i = 0; i < n; ++i) {
+        const double so = sin(d2r(lon[i])), co = cos(d2r(lon[i])), sl = sin(d2r(lat[i])), cl = cos(d2r(lat[i]));
+        o[3 * i] = (float)(cl * co); o[3 * i + 1] = (float)(cl * so); o[3 * i + 2] = (float)sl;
+    }
+    return 0;
+}
+// _north_dir_1d (direction.pyx:125-178)
+int orc_north_dir(const double* x, const double* y, const double* z, const float* nv, long long n, const char* ellps, float* o) {
+    EllpsP E;
+    if (!ellps_params(ellps, &E)) { g_err = "Unknown value for 'ellps'"; return 1; }
+    for (long long i = 0; i < n; ++i) {
+        const double vx = 0.0 - x[i], vy = 0.0 - y[i], vz = E.np_z - z[i];
+        const double a = nv[3 * i], b = nv[3 * i + 1], c = nv[3 * i + 2];
+        const double dp = (vx * a) + (vy * b) + (vz * c);
+        const double px = vx - dp * a, py = vy - dp * b, pz = vz - dp * c;
+        const double nrm = sqrt(px * px + py * py + pz * pz);
+        o[3 * i] = (float)(px / nrm); o[3 * i + 1] = (float)(py / nrm); o[3 * i + 2] = (float)(pz / nrm);
+    }
+    return 0;
+}
+// _wgs2swiss_1d (transform.pyx:306-344)
+int orc_wgs2swiss(const double* lon, const double* lat, const float* h, long long n, double* e, double* nn, float* hc) {
+    for (long long i = 0; i < n; ++i) {
+        const double lo = ((lon[i] * 3600.0) - 26782.5) / 10000.0, la = ((lat[i] * 3600.0) - 169028.66) / 10000.0;
+        e[i] = 2600072.37 + 211455.93 * lo - 10938.51 * lo * la - 0.36 * lo * (la * la) - 44.54 * (lo * lo * lo);
+        nn[i] = 1200147.07 + 308807.95 * la + 3745.25 * (lo * lo) + 76.63 * (la * la) - 194.56 * (lo * lo) * la + 119.79 * (la * la * la);
+        hc[i] = (float)((double)h[i] - 49.55 + 2.73 * lo + 6.94 * la);
+    }
+    return 0;
+}
+// _swiss2wgs_1d (transform.pyx:390-432)
+int orc_swiss2wgs(const double* e, const double* nn, const float* hc, long long n, double* lon, double* lat, float* h) {
+    for (long long i = 0; i < n; ++i) {
+        const double ep = (e[i] - 2600000.0) / 1000000.0, np_ = (nn[i] - 1200000.0) / 1000000.0;
+        const double lo = 2.6779094 + 4.728982 * ep + 0.791484 * ep * np_ + 0.1306 * ep * (np_ * np_) - 0.0436 * (ep * ep * ep);
+        const double la = 16.9023892 + 3.238272 * np_ - 0.270978 * (ep * ep) - 0.002528 * (np_ * np_) - 0.0447 * (ep * ep) * np_ - 0.0140 * (np_ * np_ * np_);
+        h[i] = (float)((double)hc[i] + 49.55 - 12.60 * ep - 22.64 * np_);
+        lon[i] = lo * (100.0 / 36.); lat[i] = la * (100.0 / 36.);
+    }
+    return 0;
+}
+// rotation_matrix_glob2loc (transform.pyx:490-530): float32 cross product, NaN rim
+int orc_rotation_matrix_glob2loc(const float* north, const float* norm, int ny, int nx, float* out) {
+    const float nanv = std::numeric_limits<float>::quiet_NaN();
+    for (int r = 0; r < ny + 2; ++r)
+        for (int c = 0; c < nx + 2; ++c) {
+            float* o = out + 9 * ((size_t)r * (nx + 2) + c);
+            if (r == 0 || c == 0 || r == ny + 1 || c == nx + 1) { for (int k = 0; k < 9; ++k) o[k] = nanv; continue; }
+            const float* a = north + 3 * ((size_t)(r - 1) * nx + (c - 1));
+            const float* b = norm + 3 * ((size_t)(r - 1) * nx + (c - 1));
+            o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+            o[3] = a[0]; o[4] = a[1]; o[5] = a[2]; o[6] = b[0]; o[7] = b[1]; o[8] = b[2];
+        }
+    return 0;
+}
 }  // extern "C"

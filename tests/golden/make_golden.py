@@ -6,6 +6,9 @@
   ``topo_param.sky_view_factor / visible_sky_fraction / topographic_openness``
   (compiled from /root/reference by oracle/build_ref.py).  These pin the oracle's
   restatement of topo_param.pyx:412-603.
+* ``slope_ref.npz`` / ``transform_ref.npz`` -- likewise for the UNMODIFIED reference
+  ``topo_param.slope_*`` and ``transform`` / ``direction`` (lonlat2ecef, ecef2enu,
+  ecef2enu_vector, wgs2swiss, swiss2wgs, rotation_matrix_glob2loc, surf_norm, north_dir).
 * ``horizon_oracle_regression.npz`` -- outputs of the CPU ORACLE (not of the
   reference: Embree is unavailable, the ray path is "parity unpinned") for a
   small seeded DEM and all three search algorithms.  A regression anchor only.
@@ -55,10 +58,40 @@ def slope_inputs(n=40, seed=9):
             np.ascontiguousarray(P[..., 2].astype(np.float32)), rot)
 
 
+def transform_inputs(seed=11, ny=9, nx=13):
+    """A small lon/lat grid around the Alps plus elevations (float32)."""
+    rng = np.random.default_rng(seed)
+    lon = np.linspace(6.0, 11.5, nx) + rng.uniform(-0.01, 0.01, nx)
+    lat = np.linspace(48.2, 44.9, ny) + rng.uniform(-0.01, 0.01, ny)      # north -> south like a DEM
+    lon2, lat2 = np.meshgrid(lon, lat)
+    h = rng.uniform(-5.0, 4500.0, (ny, nx)).astype(np.float32)
+    return np.ascontiguousarray(lon2), np.ascontiguousarray(lat2), h
+
+
 def main():
     br = _load(os.path.join(ROOT, "oracle", "build_ref.py"), "build_ref")
     br.build()
-    tp, _, _ = br.load()
+    tp, tr, di = br.load()
+    # transform / direction: the chain of examples/horizon/gridded_curved_DEM.py:60-90 for each ellipsoid
+    lon, lat, h = transform_inputs()
+    tf = {}
+    for el in ("sphere", "GRS80", "WGS84"):
+        x, y, z = tr.lonlat2ecef(lon, lat, h, ellps=el)
+        t = tr.TransformerEcef2enu(lon_or=float(lon.mean()), lat_or=float(lat.mean()), ellps=el)
+        xe, ye, ze = tr.ecef2enu(x, y, z, t)
+        nrm = di.surf_norm(lon, lat)
+        nth = di.north_dir(x, y, z, nrm, ellps=el)
+        nrm_e, nth_e = tr.ecef2enu_vector(nrm, t), tr.ecef2enu_vector(nth, t)
+        rot = tr.rotation_matrix_glob2loc(nth_e, nrm_e)
+        for k, v in dict(x=x, y=y, z=z, xe=xe, ye=ye, ze=ze, nrm=nrm, nth=nth, nrm_e=nrm_e, nth_e=nth_e, rot=rot,
+                         orig=np.array([t.x_ecef_or, t.y_ecef_or, t.z_ecef_or, t.lon_or, t.lat_or])).items():
+            tf[el + "_" + k] = np.asarray(v)
+    e, n, hc = tr.wgs2swiss(lon, lat, h)
+    lo2, la2, hw = tr.swiss2wgs(e, n, hc)
+    tf.update(swiss_e=np.asarray(e), swiss_n=np.asarray(n), swiss_h=np.asarray(hc), back_lon=np.asarray(lo2),
+              back_lat=np.asarray(la2), back_h=np.asarray(hw))
+    np.savez_compressed(os.path.join(HERE, "transform_ref.npz"), **tf)
+
     out = {}
     for tag, (seed, ny, nx, K) in {"a": (0, 12, 16, 72), "b": (1, 6, 8, 360)}.items():
         azim, hori, tilt = integral_inputs(seed, ny, nx, K)

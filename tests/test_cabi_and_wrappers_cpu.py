@@ -150,6 +150,36 @@ def test_compute_fails_loudly_without_gpu():
         hb.topo_param.sky_view_factor(np.zeros(4, np.float32), np.zeros((2, 2, 4), np.float32), np.ones((2, 2, 3), np.float32))
     with pytest.raises(RuntimeError, match="no CUDA device"):
         resident.Scene(c["vert_grid"], 48, 48)
+    lon = np.array([[8.0, 8.1]]); lat = np.array([[46.0, 46.0]])
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.transform.lonlat2ecef(lon, lat, np.zeros((1, 2), np.float32), ellps="WGS84")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.direction.surf_norm(lon, lat)
+
+
+def test_transform_direction_validation_messages():
+    """Argument checks of transform.pyx:43-51, 129-139, 215-224 and direction.pyx:35-40, 104-115."""
+    lon = np.array([[8.0, 8.1]]); lat = np.array([[46.0, 46.0]]); h = np.zeros((1, 2), np.float32)
+    with pytest.raises(ValueError, match="Inconsistent shapes"):
+        hb.transform.lonlat2ecef(lon, lat[:, :1], h, ellps="WGS84")
+    with pytest.raises(ValueError, match="incorrect data type"):
+        hb.transform.lonlat2ecef(lon, lat, h.astype(np.float64), ellps="WGS84")
+    with pytest.raises(ValueError, match="Unknown value for 'ellps'"):
+        hb.transform.lonlat2ecef(lon, lat, h, ellps="clarke")
+    with pytest.raises(ValueError, match="must be instance of class 'TransformerEcef2enu'"):
+        hb.transform.ecef2enu(lon, lat, lon, None)
+    with pytest.raises(ValueError, match="Incorrect shape"):
+        hb.transform.ecef2enu_vector(np.zeros(3, np.float32), hb.transform.TransformerEcef2enu(8.0, 46.0, "sphere"))
+    with pytest.raises(ValueError, match="'lon_or' is outside of valid range"):
+        hb.transform.TransformerEcef2enu(181.0, 46.0, "sphere")
+    with pytest.raises(ValueError, match="Unknown value for 'ellps'"):
+        hb.transform.TransformerEcef2enu(8.0, 46.0, "clarke")
+    with pytest.raises(ValueError, match="incorrect data type"):
+        hb.direction.surf_norm(lon.astype(np.float32), lat)
+    with pytest.raises(ValueError, match="Inconsistent shapes"):
+        hb.direction.north_dir(lon, lat, lon, np.zeros((1, 3, 3), np.float32), ellps="WGS84")
+    t = hb.transform.TransformerEcef2enu(8.0, 46.0, "WGS84")   # attributes as in transform.pyx:455-483
+    assert abs(np.sqrt(t.x_ecef_or ** 2 + t.y_ecef_or ** 2 + t.z_ecef_or ** 2) - 6.3670e6) < 2e4
 
 
 def test_product_never_touches_the_oracle():

@@ -244,3 +244,73 @@ def test_slope_against_oracle_and_reference_golden(mods):
         assert np.array_equal(np.isnan(a), np.isnan(b)), name
         assert np.nanmax(np.abs(a - b)) <= 2e-6, (name, float(np.nanmax(np.abs(a - b))))
         assert np.nanmax(np.abs(a - g[name])) <= 2e-5, name
+
+
+def test_transform_direction_against_oracle_and_reference_golden(mods):
+    """Scope row 8f-3: coordinate preparation on the device through the reference-shaped
+    wrappers, against the CPU oracle (same operation order; sin/cos differ by <= 2 ulp) and the
+    golden outputs of the compiled reference.  float64: 4e-9 m; float32: 1 ulp / 1.2e-7 for
+    unit vectors.  The fused resident kernel must give the bits of the step-by-step chain."""
+    import importlib.util
+    import os
+    import torch
+    hb, oracle = mods
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g = np.load(os.path.join(gold, "transform_ref.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(gold, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    lon, lat, h = mg.transform_inputs()
+    ulp32 = lambda r: np.spacing(np.abs(r).astype(np.float32)).astype(np.float64)
+    for el in ("sphere", "GRS80", "WGS84"):
+        t = hb.transform.TransformerEcef2enu(lon_or=float(lon.mean()), lat_or=float(lat.mean()), ellps=el)
+        assert np.allclose([t.x_ecef_or, t.y_ecef_or, t.z_ecef_or, t.lon_or, t.lat_or], g[el + "_orig"], rtol=0, atol=2e-9)
+        x, y, z = hb.transform.lonlat2ecef(lon, lat, h, ellps=el)
+        for a, k in ((x, "x"), (y, "y"), (z, "z")):
+            assert a.dtype == np.float64 and a.shape == lon.shape
+            assert np.abs(a - g[el + "_" + k]).max() <= 4e-9, (el, k)
+        ox, oy, oz = oracle.lonlat2ecef(lon, lat, h, el)
+        assert max(np.abs(x - ox).max(), np.abs(y - oy).max(), np.abs(z - oz).max()) <= 4e-9
+        enu = hb.transform.ecef2enu(x, y, z, t)
+        for a, k in zip(enu, ("xe", "ye", "ze")):
+            assert a.dtype == np.float32
+            assert (np.abs(a.astype(np.float64) - g[el + "_" + k]) <= ulp32(g[el + "_" + k])).all(), (el, k)
+        nrm = hb.direction.surf_norm(lon, lat)
+        nth = hb.direction.north_dir(x, y, z, nrm, ellps=el)
+        nrm_e, nth_e = hb.transform.ecef2enu_vector(nrm, t), hb.transform.ecef2enu_vector(nth, t)
+        for a, k in ((nrm, "nrm"), (nth, "nth"), (nrm_e, "nrm_e"), (nth_e, "nth_e")):
+            assert a.shape == lon.shape + (3,) and np.abs(a.astype(np.float64) - g[el + "_" + k]).max() <= 1.2e-7, (el, k)
+        rot = hb.transform.rotation_matrix_glob2loc(nth_e, nrm_e)
+        assert np.array_equal(rot, oracle.rotation_matrix_glob2loc(nth_e, nrm_e), equal_nan=True)
+        assert np.nanmax(np.abs(rot - g[el + "_rot"])) <= 2.4e-7
+        # fused resident kernel: lon / lat are 1-D here, the grid is their outer product
+        lon1, lat1 = np.ascontiguousarray(lon[0]), np.ascontiguousarray(lat[:, 0])
+        lon2, lat2 = np.meshgrid(lon1, lat1)
+        xs, ys, zs = hb.transform.lonlat2ecef(lon2, lat2, h, ellps=el)
+        chain = np.stack(hb.transform.ecef2enu(xs, ys, zs, t), axis=2)
+        n_in = hb.direction.surf_norm(lon2[1:-1, 1:-1], lat2[1:-1, 1:-1])
+        t_in = hb.direction.north_dir(xs[1:-1, 1:-1], ys[1:-1, 1:-1], zs[1:-1, 1:-1], n_in, ellps=el)
+        dev = torch.device("cuda:0")
+        ny, nx = h.shape
+        vg = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+        vn = torch.empty((ny - 2, nx - 2, 3), dtype=torch.float32, device=dev)
+        vt = torch.empty_like(vn)
+        hb.resident.prep_enu_dev(torch.from_numpy(lon1).to(dev), torch.from_numpy(lat1).to(dev), torch.from_numpy(h).to(dev),
+                                 el, t, 1, 1, ny - 2, nx - 2, vg, vn, vt)
+        torch.cuda.synchronize()
+        assert np.array_equal(vg.cpu().numpy(), chain)
+        assert np.array_equal(vn.cpu().numpy(), hb.transform.ecef2enu_vector(n_in, t))
+        assert np.array_equal(vt.cpu().numpy(), hb.transform.ecef2enu_vector(t_in, t))
+    e, n, hc = hb.transform.wgs2swiss(lon, lat, h)
+    assert np.abs(e - g["swiss_e"]).max() <= 2e-9 and np.abs(n - g["swiss_n"]).max() <= 2e-9
+    assert (np.abs(hc.astype(np.float64) - g["swiss_h"]) <= ulp32(g["swiss_h"])).all()
+    lo2, la2, hw = hb.transform.swiss2wgs(e, n, hc)
+    assert np.abs(lo2 - g["back_lon"]).max() <= 5e-14 and np.abs(la2 - g["back_lat"]).max() <= 5e-14
+    assert (np.abs(hw.astype(np.float64) - g["back_h"]) <= ulp32(g["back_h"])).all()
+    # the reference's argument checks
+    with pytest.raises(ValueError, match="Unknown value for 'ellps'"):
+        hb.transform.lonlat2ecef(lon, lat, h, ellps="bessel")
+    with pytest.raises(ValueError, match="incorrect data type"):
+        hb.transform.lonlat2ecef(lon.astype(np.float32), lat, h, ellps="WGS84")
+    with pytest.raises(ValueError, match="TransformerEcef2enu"):
+        hb.transform.ecef2enu(lon, lat, lon, object())
+

@@ -1,5 +1,6 @@
 """CPU tests of the oracle: golden vectors from the compiled reference, analytic
 known-answer cases, cross-algorithm consistency.  No GPU."""
+import importlib.util
 import os
 
 import numpy as np
@@ -223,3 +224,57 @@ def test_slope_matches_reference_golden():
     xs = np.arange(5, dtype=np.float32); X, Y = np.meshgrid(xs, xs)
     v = oracle.slope_plane_meth(X, Y, (0.5 * X).astype(np.float32))[2, 2]
     assert np.allclose(v, [-0.4472136, 0.0, 0.8944272], atol=1e-6)
+
+
+def _ulp32(ref):
+    return np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
+
+
+def test_transform_matches_reference_golden():
+    """Coordinate preparation (scope row 8f-3): the oracle against the outputs of the UNMODIFIED
+    compiled reference transform.pyx / direction.pyx (tests/golden/transform_ref.npz).  The
+    reference is built with -ffast-math, the oracle without: float64 outputs agree to 2e-9 m
+    (2 ulp at Earth-radius magnitude), float32 outputs to 1 ulp."""
+    import oracle
+    g = np.load(os.path.join(GOLD, "transform_ref.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec); spec.loader.exec_module(mg)
+    lon, lat, h = mg.transform_inputs()
+
+    class T:  # TransformerEcef2enu attributes as stored by the reference
+        pass
+    for el in ("sphere", "GRS80", "WGS84"):
+        x, y, z = oracle.lonlat2ecef(lon, lat, h, el)
+        for a, k in ((x, "x"), (y, "y"), (z, "z")):
+            assert np.abs(a - g[el + "_" + k]).max() <= 2e-9, (el, k)
+        t = T()
+        t.x_ecef_or, t.y_ecef_or, t.z_ecef_or, t.lon_or, t.lat_or = g[el + "_orig"]
+        enu = oracle.ecef2enu(g[el + "_x"], g[el + "_y"], g[el + "_z"], t)
+        for a, k in zip(enu, ("xe", "ye", "ze")):
+            assert (np.abs(a.astype(np.float64) - g[el + "_" + k]) <= _ulp32(g[el + "_" + k])).all(), (el, k)
+        nrm = oracle.surf_norm(lon, lat)
+        assert (np.abs(nrm.astype(np.float64) - g[el + "_nrm"]) <= _ulp32(g[el + "_nrm"])).all()
+        nth = oracle.north_dir(g[el + "_x"], g[el + "_y"], g[el + "_z"], g[el + "_nrm"], el)
+        assert np.abs(nth.astype(np.float64) - g[el + "_nth"]).max() <= 1.2e-7, el
+        for src, k in ((g[el + "_nrm"], "nrm_e"), (g[el + "_nth"], "nth_e")):
+            v = oracle.ecef2enu_vector(src, t)
+            assert np.abs(v.astype(np.float64) - g[el + "_" + k]).max() <= 1.2e-7, (el, k)
+        rot = oracle.rotation_matrix_glob2loc(g[el + "_nth_e"], g[el + "_nrm_e"])
+        assert np.array_equal(np.isnan(rot), np.isnan(g[el + "_rot"]))
+        assert np.nanmax(np.abs(rot - g[el + "_rot"])) <= 6e-8
+    e, n, hc = oracle.wgs2swiss(lon, lat, h)
+    assert np.abs(e - g["swiss_e"]).max() <= 2e-9 and np.abs(n - g["swiss_n"]).max() <= 2e-9
+    assert (np.abs(hc.astype(np.float64) - g["swiss_h"]) <= _ulp32(g["swiss_h"])).all()
+    lo2, la2, hw = oracle.swiss2wgs(g["swiss_e"], g["swiss_n"], g["swiss_h"])
+    assert np.abs(lo2 - g["back_lon"]).max() <= 5e-14 and np.abs(la2 - g["back_lat"]).max() <= 5e-14   # degrees; -ffast-math reassociation
+    assert (np.abs(hw.astype(np.float64) - g["back_h"]) <= _ulp32(g["back_h"])).all()
+    # known answer: the ENU origin maps to (0, 0, 0), its normal to (0, 0, 1), north to (0, 1, 0)
+    t = T()
+    t.x_ecef_or, t.y_ecef_or, t.z_ecef_or, t.lon_or, t.lat_or = g["WGS84_orig"]
+    lo, la = np.array([[t.lon_or]]), np.array([[t.lat_or]])
+    x0, y0, z0 = oracle.lonlat2ecef(lo, la, np.zeros((1, 1), np.float32), "WGS84")
+    assert max(abs(float(v[0, 0])) for v in oracle.ecef2enu(x0, y0, z0, t)) <= 1e-6
+    n0 = oracle.surf_norm(lo, la)
+    assert np.allclose(oracle.ecef2enu_vector(n0, t)[0, 0], [0, 0, 1], atol=1e-7)
+    assert np.allclose(oracle.ecef2enu_vector(oracle.north_dir(x0, y0, z0, n0, "WGS84"), t)[0, 0], [0, 1, 0], atol=1e-7)
+
