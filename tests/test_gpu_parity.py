@@ -314,3 +314,42 @@ def test_transform_direction_against_oracle_and_reference_golden(mods):
     with pytest.raises(ValueError, match="TransformerEcef2enu"):
         hb.transform.ecef2enu(lon, lat, lon, object())
 
+
+def test_full_size_cfg2_two_implementations_and_oracle_rows(mods, monkeypatch):
+    """BASELINE configs[1] at FULL size (1201 x 1201 x 360 = 5.2e8 units): the production kernel
+    (two-ray packets on the compressed 4-wide BVH) and the reference-shaped per-lane kernel on the
+    binary BVH -- different traversal, different culling structure, different cast grouping --
+    must agree bit for bit on every unit and on the number of casts; twelve rows spread over the
+    domain (incl. both rims) are checked against the CPU oracle."""
+    import torch
+    hb, oracle = mods
+    c, _ = _cfg(hb, "cfg2")
+    ny, nx, K = c["ny"], c["nx"], c["azim_num"]
+    dev = torch.device("cuda:0")
+    sc = hb.resident.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+    vn = torch.from_numpy(c["vec_norm"]).to(dev); vno = torch.from_numpy(c["vec_north"]).to(dev)
+    mask = torch.ones((ny, nx), dtype=torch.uint8, device=dev)
+    out = []
+    rays = []
+    for kern in (None, "simple"):
+        if kern:
+            monkeypatch.setenv("HZB_KERNEL", kern)
+        h = torch.full((ny, nx, K), float("nan"), dtype=torch.float32, device=dev)
+        before = sc.stats()["rays"]
+        sc.horizon_gridded(vn, vno, mask, c["offset_0"], c["offset_1"], h, 0, ny, dist_search=c["dist_search"])
+        torch.cuda.synchronize()
+        rays.append(sc.stats()["rays"] - before)
+        out.append(h)
+    monkeypatch.delenv("HZB_KERNEL", raising=False)
+    assert not torch.isnan(out[0]).any()
+    assert torch.equal(out[0], out[1]), "production and per-lane kernels differ at full size"
+    assert rays[0] == rays[1], "cast counters differ"
+    rows = sorted(set(np.linspace(0, ny - 1, 12).astype(int).tolist()))
+    host = out[0].cpu().numpy()
+    for r in rows:
+        h_cpu, _ = oracle.horizon_gridded(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["vec_norm"][r:r + 1],
+                                          c["vec_north"][r:r + 1], c["offset_0"] + r, c["offset_1"], c["dist_search"],
+                                          azim_num=K)
+        _assert_same(host[r:r + 1], h_cpu, "cfg2 full size, row %d" % r)
+    sc.close()
+
