@@ -159,7 +159,7 @@ static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const floa
                                   int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
                                   int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
                                   float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
-                                  unsigned int* d_row_done, cudaStream_t st) {
+                                  unsigned int* d_row_done, cudaStream_t st, int azim_first = 0) {
     const int alg = parse_algorithm(ray_algorithm);
     if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
     if (azim_num < 1 || dim_in_0 < 0 || dim_in_1 < 0 || row_begin < 0 || row_end > dim_in_0) { set_error("invalid dimensions"); return 1; }
@@ -176,6 +176,8 @@ static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const floa
     p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1;
     p.row_begin = row_begin; p.row_end = row_end; p.hori_fill = hori_fill; p.ray_org_elev = ray_org_elev;
     p.hori = d_hori_buffer; p.row_done = d_row_done;
+    p.stride_c = azim_first ? 1 : azim_num;
+    p.stride_k = azim_first ? (long long)dim_in_0 * dim_in_1 : 1;
     return launch_horizon_gridded(sc, p, st);
 }
 
@@ -190,13 +192,26 @@ int hzb_horizon_gridded_dev(hzb_scene* h, const float* d_vec_norm, const float* 
                                   ray_org_elev, d_hori_buffer, nullptr, (cudaStream_t)stream);
 }
 
+// additive (scope row "next 4"): azimuth-first output [azim_num][dim_in_0][dim_in_1], the layout the
+// reference's examples transpose to before writing NetCDF (examples/horizon/gridded_curved_DEM.py:113-125)
+int hzb_horizon_gridded_dev_layout(hzb_scene* h, const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                   int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
+                                   int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                                   float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
+                                   int azim_first, void* stream) {
+    if (!h) { set_error("null scene"); return 1; }
+    return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, row_begin,
+                                  row_end, azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
+                                  ray_org_elev, d_hori_buffer, nullptr, (cudaStream_t)stream, azim_first);
+}
+
 // -------------------------------------------------------------- host tier
-int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
+static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
                         const float* vec_north, int offset_0, int offset_1, float* hori_buffer, int dim_in_0,
                         int dim_in_1, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
                         const char* geom_type, const float* vert_simp, int num_vert_simp,
                         const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
-                        float hori_fill, float ray_org_elev) {
+                        float hori_fill, float ray_org_elev, int azim_first) {
     memset(&g_stats, 0, sizeof(g_stats));
     const double t_start = now_s();
     const bool timing = getenv("HZB_TIMING") != nullptr;   // stderr breakdown of this call
@@ -221,7 +236,8 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
     // hide behind the traversal.
     t0 = now_s();
     const int tiles_x = (dim_in_1 + 7) / 8, tiles_y = (dim_in_0 + 3) / 4;
-    const bool overlap = getenv("HZB_NO_OVERLAP") == nullptr && !(getenv("HZB_KERNEL") && !strcmp(getenv("HZB_KERNEL"), "simple"));
+    // (rows are contiguous byte ranges only in the reference layout: azimuth-first output is copied after the kernel)
+    const bool overlap = !azim_first && getenv("HZB_NO_OVERLAP") == nullptr && !(getenv("HZB_KERNEL") && !strcmp(getenv("HZB_KERNEL"), "simple"));
     cudaStream_t s_comp = nullptr, s_copy = nullptr;
     HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
     HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
@@ -231,7 +247,7 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
     HZB_CUDA(cudaMemsetAsync(d_done.p, 0, (size_t)tiles_y * sizeof(unsigned int), s_comp));
     HZB_TRY(horizon_gridded_launch(h->s, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
                                    azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
-                                   ray_org_elev, d_hori.p, overlap ? d_done.p : nullptr, s_comp));
+                                   ray_org_elev, d_hori.p, overlap ? d_done.p : nullptr, s_comp, azim_first));
     double t_d2h = 0.0, t_trace = 0.0;
     const size_t row_elems = (size_t)dim_in_1 * (size_t)azim_num;
     const double t_pf0 = now_s();
@@ -282,6 +298,28 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, co
         fprintf(stderr, "[hzb] horizon_gridded: scene %.3f (h2d %.3f build %.3f) inputs+alloc %.3f launch..end %.3f (prefault %.3f, kernel seen done %.3f, staged d2h %.3f) total %.3f s\n",
                 t_scene, h->s.t_h2d, h->s.t_build, t_h2d_extra, now_s() - t0, t_prefault, t_trace, t_d2h, g_stats.t_total);
     return 0;
+}
+
+int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
+                        const float* vec_north, int offset_0, int offset_1, float* hori_buffer, int dim_in_0,
+                        int dim_in_1, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                        const char* geom_type, const float* vert_simp, int num_vert_simp,
+                        const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
+                        float hori_fill, float ray_org_elev) {
+    return horizon_gridded_host(vert_grid, dem_dim_0, dem_dim_1, vec_norm, vec_north, offset_0, offset_1, hori_buffer, dim_in_0,
+                                dim_in_1, azim_num, dist_search, hori_acc, ray_algorithm, geom_type, vert_simp, num_vert_simp,
+                                tri_ind_simp, num_tri_simp, elev_ang_low_lim, mask, hori_fill, ray_org_elev, 0);
+}
+// additive: same call, output [azim_num][dim_in_0][dim_in_1] when azim_first != 0
+int hzb_horizon_gridded_layout(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
+                               const float* vec_north, int offset_0, int offset_1, float* hori_buffer, int dim_in_0,
+                               int dim_in_1, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                               const char* geom_type, const float* vert_simp, int num_vert_simp,
+                               const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
+                               float hori_fill, float ray_org_elev, int azim_first) {
+    return horizon_gridded_host(vert_grid, dem_dim_0, dem_dim_1, vec_norm, vec_north, offset_0, offset_1, hori_buffer, dim_in_0,
+                                dim_in_1, azim_num, dist_search, hori_acc, ray_algorithm, geom_type, vert_simp, num_vert_simp,
+                                tri_ind_simp, num_tri_simp, elev_ang_low_lim, mask, hori_fill, ray_org_elev, azim_first);
 }
 
 int hzb_horizon_locations(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* coords,

@@ -163,10 +163,12 @@ __device__ __forceinline__ int bisect(const Search& s, const Frame& f, int k, La
 
 // output staging: four consecutive azimuths per 16-byte store when aligned
 struct OutBuf {
-    float* out; bool vec, writer; float b0, b1, b2, b3;
-    __device__ __forceinline__ void init(float* o, bool v, bool w = true) { out = o; vec = v; writer = w; b0 = b1 = b2 = b3 = 0.f; }
+    float* out; bool vec, writer; float b0, b1, b2, b3; long long sk;
+    __device__ __forceinline__ void init(float* o, bool v, bool w = true, long long stride_k = 1) {
+        out = o; vec = v && stride_k == 1; writer = w; b0 = b1 = b2 = b3 = 0.f; sk = stride_k;
+    }
     __device__ __forceinline__ void put(int k, float v) {
-        if (!vec) { if (writer) out[k] = v; return; }
+        if (!vec) { if (writer) out[k * sk] = v; return; }
         b0 = b1; b1 = b2; b2 = b3; b3 = v;
         if ((k & 3) == 3 && writer) *reinterpret_cast<float4*>(out + (k - 3)) = make_float4(b0, b1, b2, b3);
     }
@@ -255,17 +257,17 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
         unsigned int units = 0;
         if (i < p.row_end && j < p.dim_in_1) {
             const size_t c = (size_t)i * p.dim_in_1 + j;
-            float* out = p.hori + c * p.azim_num;
+            float* out = p.hori + c * p.stride_c;
             if (p.mask[c] == 1) {
                 const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
                 const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
                 const float4 v = sv.vert4[(size_t)(i + p.offset_0) * sv.W + (j + p.offset_1)];
                 const Frame f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
-                OutBuf ob; ob.init(out, vec);
+                OutBuf ob; ob.init(out, vec, true, p.stride_k);
                 cell_search<ALG>(s, f, ob, cnt);
                 units = p.azim_num;
             } else {
-                for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+                for (int k = 0; k < p.azim_num; ++k) out[k * p.stride_k] = p.hori_fill;  // horizon_comp.cpp:789-794
             }
         }
         flush_counters(cnt, units, counters);
@@ -441,18 +443,18 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
                 bool done_now = true;
                 if (ci < p.row_end && cj < p.dim_in_1) {
                     const size_t c = (size_t)ci * p.dim_in_1 + cj;
-                    float* out = p.hori + c * p.azim_num;
+                    float* out = p.hori + c * p.stride_c;
                     if (p.mask[c] == 1) {
                         const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
                         const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
                         const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
                         f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
-                        ob.init(out, vec);
+                        ob.init(out, vec, true, p.stride_k);
                         m.phase = 0; m.k = 0;
                         has_cell = true; have_result = false; my_ty = ty; units += p.azim_num;
                         done_now = false;
                     } else {
-                        for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+                        for (int k = 0; k < p.azim_num; ++k) out[k * p.stride_k] = p.hori_fill;  // horizon_comp.cpp:789-794
                     }
                 }
                 if (done_now && p.row_done) { __threadfence_system(); atomicAdd(p.row_done + ty, 1u); }
@@ -534,15 +536,15 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                 bool done_now = true;
                 if (ci < p.row_end && cj < p.dim_in_1) {
                     const size_t c = (size_t)ci * p.dim_in_1 + cj;
-                    float* out = p.hori + c * p.azim_num;
+                    float* out = p.hori + c * p.stride_c;
                     if (p.mask[c] == 1) {
                         my_cell = ((unsigned int)ci << 16) | (unsigned int)cj;    // dims <= 32767 (horizon.pyx:149-151)
-                        ob.init(out, false);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
+                        ob.init(out, false, true, p.stride_k);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
                         m.phase = 0; m.k = 0; m.spec_ie = -1;
                         has_cell = true; have_result = false; units += p.azim_num;
                         done_now = false;
                     } else {
-                        for (int k = 0; k < p.azim_num; ++k) out[k] = p.hori_fill;  // horizon_comp.cpp:789-794
+                        for (int k = 0; k < p.azim_num; ++k) out[k * p.stride_k] = p.hori_fill;  // horizon_comp.cpp:789-794
                     }
                 }
                 if (done_now && p.row_done) { __threadfence_system(); atomicAdd(p.row_done + ty, 1u); }

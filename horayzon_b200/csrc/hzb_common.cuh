@@ -126,6 +126,8 @@ struct HorizonParams {
     int offset_0, offset_1, dim_in_0, dim_in_1, row_begin, row_end;
     float hori_fill, ray_org_elev;
     float* hori;
+    long long stride_c, stride_k;   // element (cell c, azimuth k) lives at hori[c * stride_c + k * stride_k]: (K, 1) = the reference's
+                                    // [y][x][azim] layout, (1, cells) = azimuth-first [azim][y][x] (scope row "next 4")
     unsigned int* row_done;  // optional [ceil(rows/4)]: +1 per finished cell slot of that row block, 32 per 8x4 tile (host overlaps D2H)
 };
 

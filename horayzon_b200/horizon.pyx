@@ -26,6 +26,16 @@ cdef extern from "horayzon_b200.h":
         const int32_t* tri_ind_simp, int num_tri_simp,
         float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
         float ray_org_elev) nogil
+    int hzb_horizon_gridded_layout(
+        const float* vert_grid, int dem_dim_0, int dem_dim_1,
+        const float* vec_norm, const float* vec_north,
+        int offset_0, int offset_1, float* hori_buffer,
+        int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+        float hori_acc, const char* ray_algorithm, const char* geom_type,
+        const float* vert_simp, int num_vert_simp,
+        const int32_t* tri_ind_simp, int num_tri_simp,
+        float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+        float ray_org_elev, int azim_first) nogil
     int hzb_horizon_locations(
         const float* vert_grid, int dem_dim_0, int dem_dim_1,
         const float* coords, const float* vec_norm, const float* vec_north,
@@ -72,7 +82,8 @@ def horizon_gridded(
         float elev_ang_low_lim = -15.0,
         np.ndarray[np.uint8_t, ndim = 2] mask=None,
         float hori_fill=0.0,
-        float ray_org_elev=0.01):
+        float ray_org_elev=0.01,
+        bint azim_first=False):
     """Horizon of every unmasked cell of a gridded inner domain.
 
     Arguments, units and defaults are those of ``horayzon.horizon.horizon_gridded``
@@ -84,6 +95,12 @@ def horizon_gridded(
 
     Returns ``(hori_buffer, azim)``: float32 (y, x, azim_num) horizon [radian]
     and float32 (azim_num,) azimuth [radian].
+
+    Additive keyword (not in the reference): ``azim_first=True`` returns the horizon as
+    (azim_num, y, x) -- what the reference's examples produce with
+    ``np.moveaxis(hori, 2, 0)`` before writing NetCDF
+    (``examples/horizon/gridded_curved_DEM.py:113-125``) -- written in that order by
+    the kernel, with the same values.
     """
     # argument checks, in the reference's order and wording (horizon.pyx:109-156)
     if len(vert_grid) < (dem_dim_0 * dem_dim_1 * 3):
@@ -142,14 +159,15 @@ def horizon_gridded(
     cdef int ny = vn.shape[0], nx = vn.shape[1]
 
     cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] hori_buffer = \
-        np.empty((ny, nx, azim_num), dtype=np.float32)
+        np.empty((azim_num, ny, nx) if azim_first else (ny, nx, azim_num), dtype=np.float32)
+    cdef int layout = 1 if azim_first else 0
     # The reference pre-fills NaN (horizon.pyx:170-173).  The native call writes every
     # element (masked cells get hori_fill), so the 2 GB-scale fill pass is skipped and
     # the pages are first touched by the overlapped device-to-host copy instead.
     cdef int rc = 0
     if ny > 0 and nx > 0:
         with nogil:
-            rc = hzb_horizon_gridded(
+            rc = hzb_horizon_gridded_layout(
                 <const float*> vg.data, dem_dim_0, dem_dim_1,
                 <const float*> vn.data, <const float*> vno.data,
                 offset_0, offset_1, <float*> hori_buffer.data, ny, nx,
@@ -157,7 +175,7 @@ def horizon_gridded(
                 <const float*> vs.data, num_vert_simp,
                 <const int32_t*> ti.data, num_tri_simp,
                 elev_ang_low_lim, <const uint8_t*> mk.data, hori_fill,
-                ray_org_elev)
+                ray_org_elev, layout)
     if rc != 0:
         _raise_native()
     return hori_buffer, _azimuth_axis(azim_num)

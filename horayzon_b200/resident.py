@@ -52,6 +52,7 @@ def lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
             ctypes.c_char_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+        L.hzb_horizon_gridded_dev_layout.argtypes = L.hzb_horizon_gridded_dev.argtypes[:-1] + [ctypes.c_int, ctypes.c_void_p]
         for name in ("hzb_sky_view_factor_dev", "hzb_visible_sky_fraction_dev"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -127,23 +128,27 @@ class Scene:
 
     def horizon_gridded(self, vec_norm, vec_north, mask, offset_0, offset_1, hori_out, row_begin=0,
                         row_end=None, dist_search=50.0, hori_acc=0.25, ray_algorithm="guess_constant",
-                        elev_ang_low_lim=-15.0, hori_fill=0.0, ray_org_elev=0.01, stream=None):
+                        elev_ang_low_lim=-15.0, hori_fill=0.0, ray_org_elev=0.01, stream=None, azim_first=False):
         """Asynchronous horizon computation for inner-domain rows
         ``[row_begin, row_end)``.  ``vec_norm`` / ``vec_north`` (ny, nx, 3) float32,
-        ``mask`` (ny, nx) uint8 and ``hori_out`` (ny, nx, K) float32 are CUDA
-        tensors of the FULL inner domain; only the selected rows are touched."""
-        ny, nx, K = hori_out.shape
+        ``mask`` (ny, nx) uint8 and ``hori_out`` (ny, nx, K) float32 -- or (K, ny, nx)
+        with ``azim_first=True`` -- are CUDA tensors of the FULL inner domain; only the
+        selected rows are touched."""
+        if azim_first:
+            K, ny, nx = hori_out.shape
+        else:
+            ny, nx, K = hori_out.shape
         if row_end is None:
             row_end = ny
         assert vec_norm.is_cuda and vec_north.is_cuda and mask.is_cuda and hori_out.is_cuda
         assert vec_norm.is_contiguous() and vec_north.is_contiguous() and mask.is_contiguous() and hori_out.is_contiguous()
         assert tuple(vec_norm.shape) == (ny, nx, 3) and tuple(mask.shape) == (ny, nx)
-        _check(lib().hzb_horizon_gridded_dev(
+        _check(lib().hzb_horizon_gridded_dev_layout(
             self._h, ctypes.c_void_p(vec_norm.data_ptr()), ctypes.c_void_p(vec_north.data_ptr()),
             ctypes.c_void_p(mask.data_ptr()), int(offset_0), int(offset_1), int(ny), int(nx), int(row_begin),
             int(row_end), int(K), float(dist_search), float(hori_acc), ray_algorithm.encode(),
             float(elev_ang_low_lim), float(hori_fill), float(ray_org_elev),
-            ctypes.c_void_p(hori_out.data_ptr()), _stream_ptr(stream)))
+            ctypes.c_void_p(hori_out.data_ptr()), 1 if azim_first else 0, _stream_ptr(stream)))
 
 
 def sky_view_factor_dev(azim, hori, vec_tilt, out, stream=None):

@@ -72,6 +72,20 @@ int hzb_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
                         const uint8_t* mask, float hori_fill,
                         float ray_org_elev);
 
+/* Additive (scope row 8f-4): the same call with the output in azimuth-first order
+ * [azim_num][dim_in_0][dim_in_1] when azim_first != 0 -- the layout the reference's examples
+ * transpose to before writing NetCDF (examples/horizon/gridded_curved_DEM.py:113-125), so a
+ * 2 GB np.moveaxis + copy on the host disappears.  azim_first == 0 is hzb_horizon_gridded. */
+int hzb_horizon_gridded_layout(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                               const float* vec_norm, const float* vec_north,
+                               int offset_0, int offset_1, float* hori_buffer,
+                               int dim_in_0, int dim_in_1, int azim_num,
+                               float dist_search, float hori_acc, const char* ray_algorithm,
+                               const char* geom_type, const float* vert_simp, int num_vert_simp,
+                               const int32_t* tri_ind_simp, int num_tri_simp,
+                               float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+                               float ray_org_elev, int azim_first);
+
 /* Replaces horizon_locations_comp (horizon_comp.h:23-34, horizon_comp.cpp:828-1094).
  * hori_buffer / hori_dist_buffer: float32 [num_loc][azim_num]; locations whose
  * normal line misses the surface are left untouched (the wrapper pre-fills NaN). */
@@ -188,6 +202,16 @@ int hzb_horizon_gridded_dev(hzb_scene* s,
                             const char* ray_algorithm, float elev_ang_low_lim,
                             float hori_fill, float ray_org_elev,
                             float* d_hori_buffer, void* stream);
+
+/* As hzb_horizon_gridded_dev, with d_hori_buffer in azimuth-first order
+ * [azim_num][dim_in_0][dim_in_1] when azim_first != 0 (row sharding works unchanged). */
+int hzb_horizon_gridded_dev_layout(hzb_scene* s,
+                                   const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                   int offset_0, int offset_1, int dim_in_0, int dim_in_1,
+                                   int row_begin, int row_end, int azim_num,
+                                   float dist_search, float hori_acc, const char* ray_algorithm,
+                                   float elev_ang_low_lim, float hori_fill, float ray_org_elev,
+                                   float* d_hori_buffer, int azim_first, void* stream);
 
 /* Device-pointer variants of the azimuthal integrals (same layouts). */
 int hzb_sky_view_factor_dev(const float* d_azim, const float* d_hori, const float* d_vec_tilt,

@@ -353,3 +353,26 @@ def test_full_size_cfg2_two_implementations_and_oracle_rows(mods, monkeypatch):
         _assert_same(host[r:r + 1], h_cpu, "cfg2 full size, row %d" % r)
     sc.close()
 
+
+def test_azimuth_first_layout_is_the_transposed_reference_layout(mods):
+    """Scope row 8f-4 (additive): azim_first=True gives np.moveaxis(hori, 2, 0) bit for bit, through the
+    host tier and through the resident tier with row sharding."""
+    import torch
+    hb, oracle = mods
+    c, args = _cfg(hb, "cfg1")
+    mask = np.ones((c["ny"], c["nx"]), np.uint8); mask[5:9, 20:31] = 0
+    h_ref, az = hb.horizon.horizon_gridded(*args, azim_num=c["azim_num"], mask=mask, hori_fill=-1.0)
+    h_t, az_t = hb.horizon.horizon_gridded(*args, azim_num=c["azim_num"], mask=mask, hori_fill=-1.0, azim_first=True)
+    assert h_t.shape == (c["azim_num"], c["ny"], c["nx"]) and np.array_equal(az, az_t)
+    assert np.array_equal(h_t, np.moveaxis(h_ref, 2, 0))
+    dev = torch.device("cuda:0")
+    sc = hb.resident.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+    out = torch.full((c["azim_num"], c["ny"], c["nx"]), float("nan"), dtype=torch.float32, device=dev)
+    vn = torch.from_numpy(c["vec_norm"]).to(dev); vno = torch.from_numpy(c["vec_north"]).to(dev)
+    for b, e in ((0, 37), (37, c["ny"])):   # two row shards into one azimuth-first array
+        sc.horizon_gridded(vn, vno, torch.from_numpy(mask).to(dev), c["offset_0"], c["offset_1"], out, b, e,
+                           dist_search=c["dist_search"], hori_fill=-1.0, azim_first=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), h_t)
+    sc.close()
+
