@@ -135,6 +135,8 @@ int hzb_device_count(void) {
     return n;
 }
 int hzb_get_stats(hzb_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
+void* hzb_host_alloc(size_t bytes) { if (require_device()) return nullptr; return host_block_alloc(bytes); }
+void hzb_host_free(void* p) { host_block_free(p); }
 
 // ------------------------------------------------------------------ scene
 hzb_scene* hzb_scene_create(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vert_simp,
@@ -251,7 +253,8 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
     double t_d2h = 0.0, t_trace = 0.0;
     const size_t row_elems = (size_t)dim_in_1 * (size_t)azim_num;
     const double t_pf0 = now_s();
-    host_prefault(hori_buffer, nc * (size_t)azim_num * sizeof(float));   // the kernel is running meanwhile
+    const bool out_pinned = host_is_pinned(hori_buffer);   // page-locked output (hzb_host_alloc): plain DMA, no staging
+    if (!out_pinned) host_prefault(hori_buffer, nc * (size_t)azim_num * sizeof(float));   // the kernel is running meanwhile
     const double t_prefault = now_s() - t_pf0;
     if (overlap) {
         unsigned int* h_done = nullptr;
@@ -274,7 +277,13 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
             if (ready - copied_blocks >= min_blocks || (ready == tiles_y && ready > copied_blocks)) {
                 const size_t r0 = (size_t)copied_blocks * 4, r1 = std::min<size_t>((size_t)ready * 4, (size_t)dim_in_0);
                 const double tc = now_s();
-                HZB_TRY(staged_d2h(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float), s_copy));
+                if (out_pinned) {
+                    HZB_CUDA(cudaMemcpyAsync(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float),
+                                             cudaMemcpyDeviceToHost, s_copy));
+                    HZB_CUDA(cudaStreamSynchronize(s_copy));
+                } else {
+                    HZB_TRY(staged_d2h(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float), s_copy));
+                }
                 t_d2h += now_s() - tc;
                 copied_blocks = ready;
             } else {
@@ -288,7 +297,8 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
         HZB_CUDA(cudaStreamSynchronize(s_comp));
         t_trace = now_s() - t0;
         const double tc = now_s();
-        HZB_TRY(staged_d2h(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), nullptr));
+        if (out_pinned) HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
+        else HZB_TRY(staged_d2h(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), nullptr));
         t_d2h = now_s() - tc;
     }
     HZB_CUDA(cudaGetLastError());
@@ -506,11 +516,13 @@ static int integral_host(int kind, const float* azim, const float* hori, const f
     HZB_CUDA(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
     HZB_CUDA(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     struct EvGuard { cudaEvent_t* e; ~EvGuard() { cudaEventDestroy(e[0]); cudaEventDestroy(e[1]); } } eguard{done};
+    const bool in_pinned = host_is_pinned(hori);   // e.g. the array horizon_gridded returned: plain DMA
     int slot = 0;
     for (size_t c0 = 0; c0 < nc; c0 += chunk_cells, slot ^= 1) {
         const size_t cells = std::min(chunk_cells, nc - c0);
         if (c0 >= 2 * chunk_cells) HZB_CUDA(cudaEventSynchronize(done[slot]));   // the kernel two chunks back has read this buffer
-        HZB_TRY(staged_h2d(d_h[slot].p, hori + c0 * (size_t)K, cells * (size_t)K * sizeof(float), st));
+        if (in_pinned) HZB_CUDA(cudaMemcpyAsync(d_h[slot].p, hori + c0 * (size_t)K, cells * (size_t)K * sizeof(float), cudaMemcpyHostToDevice, st));
+        else HZB_TRY(staged_h2d(d_h[slot].p, hori + c0 * (size_t)K, cells * (size_t)K * sizeof(float), st));
         HZB_TRY(launch_svf(kind, d_a.p, d_h[slot].p, kind != 2 ? d_t.p + 3 * c0 : nullptr, (long long)cells, K, d_o.p + c0, st));
         HZB_CUDA(cudaEventRecord(done[slot], st));
     }

@@ -191,4 +191,58 @@ int staged_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s
     return 0;
 }
 
+// ---- pooled pinned host blocks for large OUTPUT arrays --------------------------------
+// The wrappers allocate the arrays they return; backing the big ones (the 2 GB horizon
+// array) with page-locked memory lets the finished row blocks leave by plain DMA while the
+// kernel runs and lets sky_view_factor read them back by DMA.  Page-locking 2 GB costs a
+// few 100 ms, so freed blocks are kept (at most two) and handed out again.
+namespace {
+struct PinPool {
+    std::mutex mu;
+    struct Blk { void* p; size_t cap; };
+    std::vector<Blk> free_blocks, live;
+};
+PinPool& pin_pool() { static PinPool* p = new PinPool(); return *p; }
+}  // namespace
+
+void* host_block_alloc(size_t bytes) {
+    if (bytes == 0) return nullptr;
+    PinPool& P = pin_pool();
+    std::lock_guard<std::mutex> l(P.mu);
+    int best = -1;
+    for (int i = 0; i < (int)P.free_blocks.size(); ++i)
+        if (P.free_blocks[i].cap >= bytes && P.free_blocks[i].cap <= bytes + bytes / 4 &&
+            (best < 0 || P.free_blocks[i].cap < P.free_blocks[best].cap)) best = i;
+    PinPool::Blk b{nullptr, 0};
+    if (best >= 0) { b = P.free_blocks[best]; P.free_blocks.erase(P.free_blocks.begin() + best); }
+    else {
+        if (cudaHostAlloc(&b.p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        b.cap = bytes;
+    }
+    P.live.push_back(b);
+    return b.p;
+}
+
+void host_block_free(void* p) {
+    if (!p) return;
+    PinPool& P = pin_pool();
+    std::lock_guard<std::mutex> l(P.mu);
+    for (size_t i = 0; i < P.live.size(); ++i)
+        if (P.live[i].p == p) {
+            P.free_blocks.push_back(P.live[i]);
+            P.live.erase(P.live.begin() + i);
+            while (P.free_blocks.size() > 2) {          // bound the idle page-locked memory: drop the oldest
+                if (cudaFreeHost(P.free_blocks[0].p) != cudaSuccess) cudaGetLastError();
+                P.free_blocks.erase(P.free_blocks.begin());
+            }
+            return;
+        }
+}
+
+bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
 }  // namespace hzb

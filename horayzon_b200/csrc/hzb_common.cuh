@@ -182,6 +182,10 @@ void host_prefault(void* p, size_t bytes);                                      
 int staged_d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);   // returns when dst_host is complete
 int staged_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);   // returns when src_host has been read
 
+void* host_block_alloc(size_t bytes);      // pooled page-locked block for a large output array (nullptr: not available)
+void host_block_free(void* p);
+bool host_is_pinned(const void* p);       // page-locked (ours or cudaHostRegister'ed by the caller)
+
 // number of SMs of the current device (cached)
 int sm_count();
 

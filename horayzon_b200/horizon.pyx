@@ -14,8 +14,13 @@ from libc.stdint cimport int32_t, uint8_t
 
 np.import_array()
 
+from cpython.ref cimport Py_INCREF
+import os
+
 cdef extern from "horayzon_b200.h":
     const char* hzb_last_error()
+    void* hzb_host_alloc(size_t nbytes) nogil
+    void hzb_host_free(void* p) nogil
     int hzb_horizon_gridded(
         const float* vert_grid, int dem_dim_0, int dem_dim_1,
         const float* vec_norm, const float* vec_north,
@@ -60,6 +65,55 @@ def _azimuth_axis(int azim_num):
 
 def _raise_native():
     raise RuntimeError("horayzon_b200: " + hzb_last_error().decode("utf-8", "replace"))
+
+
+cdef class _PinnedBlock:
+    """Owner of one pooled page-locked block (``hzb_host_alloc``); the ndarray built on it
+    keeps it alive through ``base`` and the block returns to the pool with the array."""
+    cdef void* p
+
+    def __dealloc__(self):
+        if self.p != NULL:
+            hzb_host_free(self.p)
+            self.p = NULL
+
+
+_big_outputs = 0   # large outputs handed out by this process so far
+
+
+cdef object _output_array(tuple shape):
+    """float32 C-contiguous output array.  Large arrays (the 2 GB horizon of a 1201 x 1201 x 360
+    run) can be backed by pooled page-locked memory so that the device writes / reads them by
+    DMA (0.1 s per call for that size); page-locking a fresh block costs more than it saves
+    (0.8 s for 2 GB), so by default it starts with the SECOND large output of a process -- a
+    single-shot script never pays for it, a loop pays once.  ``HZB_PINNED_OUTPUT=1`` / ``0``
+    force it on / off.  Anything else, or any failure, is plain ``np.empty`` as in the
+    reference wrapper (horizon.pyx:170-173)."""
+    global _big_outputs
+    cdef size_t n = 4
+    for d in shape:
+        n *= <size_t> d
+    cdef void* p = NULL
+    cdef _PinnedBlock blk
+    cdef np.npy_intp dims[3]
+    cdef np.ndarray arr
+    cdef bint big = n >= (<size_t> 64 << 20) and len(shape) == 3
+    mode = os.environ.get("HZB_PINNED_OUTPUT", "auto")
+    cdef bint use_pinned = big and (mode == "1" or (mode != "0" and _big_outputs >= 1))
+    if big:
+        _big_outputs += 1
+    if use_pinned:
+        with nogil:
+            p = hzb_host_alloc(n)
+        if p != NULL:
+            blk = _PinnedBlock.__new__(_PinnedBlock)
+            blk.p = p
+            dims[0] = shape[0]; dims[1] = shape[1]; dims[2] = shape[2]
+            arr = np.PyArray_SimpleNewFromData(3, dims, np.NPY_FLOAT32, p)
+            Py_INCREF(blk)                       # PyArray_SetBaseObject steals a reference
+            np.PyArray_SetBaseObject(arr, blk)
+            return arr
+    return np.empty(shape, dtype=np.float32)
 
 
 def horizon_gridded(
@@ -159,7 +213,7 @@ def horizon_gridded(
     cdef int ny = vn.shape[0], nx = vn.shape[1]
 
     cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] hori_buffer = \
-        np.empty((azim_num, ny, nx) if azim_first else (ny, nx, azim_num), dtype=np.float32)
+        _output_array((azim_num, ny, nx) if azim_first else (ny, nx, azim_num))
     cdef int layout = 1 if azim_first else 0
     # The reference pre-fills NaN (horizon.pyx:170-173).  The native call writes every
     # element (masked cells get hori_fill), so the 2 GB-scale fill pass is skipped and

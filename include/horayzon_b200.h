@@ -26,6 +26,7 @@
 #ifndef HORAYZON_B200_H
 #define HORAYZON_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -54,6 +55,13 @@ typedef struct hzb_stats {
     unsigned long long bvh_bytes;   /* bytes of the traversal structure in HBM */
 } hzb_stats;
 int hzb_get_stats(hzb_stats* out);
+
+/* Additive: pooled page-locked host blocks for large arrays the WRAPPER allocates and returns
+ * (the reference's wrapper allocates its outputs with np.empty, horizon.pyx:170-173).  Host-tier
+ * calls recognise page-locked buffers and move them by plain DMA instead of staging.  NULL when
+ * no device / no memory: the caller falls back to ordinary memory. */
+void* hzb_host_alloc(size_t bytes);
+void hzb_host_free(void* p);
 
 /* --------------------------------------------------------------- host tier */
 

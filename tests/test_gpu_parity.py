@@ -376,3 +376,30 @@ def test_azimuth_first_layout_is_the_transposed_reference_layout(mods):
     assert np.array_equal(out.cpu().numpy(), h_t)
     sc.close()
 
+
+def test_page_locked_output_arrays(mods, monkeypatch):
+    """Large outputs are backed by pooled page-locked memory (DMA instead of staging): same bits as the
+    pageable path, ordinary ndarray semantics, blocks return to the pool and are reused."""
+    hb, oracle = mods
+    c, args = _cfg(hb, "cfg2", n=301)          # 299 x 299 x 360 floats = 129 MB >= the 64 MB threshold
+    monkeypatch.setenv("HZB_PINNED_OUTPUT", "1")   # default: only from the second large output of a process
+    h1, az = hb.horizon.horizon_gridded(*args, azim_num=360)
+    assert type(h1.base).__name__ == "_PinnedBlock" and h1.flags.c_contiguous and h1.flags.writeable
+    monkeypatch.setenv("HZB_PINNED_OUTPUT", "0")
+    h0, _ = hb.horizon.horizon_gridded(*args, azim_num=360)
+    monkeypatch.setenv("HZB_PINNED_OUTPUT", "1")
+    assert h0.base is None and np.array_equal(h0, h1)
+    tilt = hb.synthetic.tilt_vectors(c["x"], c["y"], c["z"], c["offset_0"])
+    assert np.array_equal(hb.topo_param.sky_view_factor(az, h1, tilt), hb.topo_param.sky_view_factor(az, h0, tilt))
+    view = h1[10:20]                           # a view keeps the block alive after the array is gone
+    keep = view.copy()
+    addr = h1.ctypes.data
+    del h1
+    h2, _ = hb.horizon.horizon_gridded(*args, azim_num=360)      # the block is still referenced: a new one
+    assert h2.ctypes.data != addr and np.array_equal(view, keep) and np.array_equal(h2, h0)
+    del view, h2
+    h3, _ = hb.horizon.horizon_gridded(*args, azim_num=360)      # both blocks are back in the pool: reused
+    assert np.array_equal(h3, h0)
+    h3[0, 0, 0] = 123.0                        # writable like any ndarray
+    assert h3[0, 0, 0] == 123.0
+
