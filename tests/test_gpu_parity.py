@@ -403,3 +403,38 @@ def test_page_locked_output_arrays(mods, monkeypatch):
     h3[0, 0, 0] = 123.0                        # writable like any ndarray
     assert h3[0, 0, 0] == 123.0
 
+
+@pytest.mark.parametrize("seed", [101, 102, 103, 104, 105, 106])
+def test_randomised_configurations(mods, seed):
+    """Seeded random small cases across the parameter space the packet kernel has to honour: all three
+    algorithms, odd / tiny azimuth counts, coarse and fine accuracy, elevation tables whose ends are
+    reached (steep terrain with a high lower limit: the search runs into index 0 / the top index, where the
+    companion indices clamp), random masks, non-square inner domains, lifted origins, tilted frames."""
+    hb, oracle = mods
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(40, 72))
+    spacing = float(rng.choice([5.0, 30.0, 100.0]))
+    amp = spacing * n * float(rng.choice([0.05, 0.3, 1.5]))          # gentle ... cliffs (slopes beyond 60 deg)
+    x, y, z = hb.synthetic.sinusoid_dem(n, n + 3, spacing, amp, spacing * n * 0.7, seed, int(rng.integers(1, 5)))
+    vg = hb.synthetic.rearrange_pad_buffer(x, y, z)
+    off0, off1 = int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    ny, nx = n - off0 - int(rng.integers(1, 6)), n + 3 - off1 - int(rng.integers(1, 6))
+    nrm = np.zeros((ny, nx, 3)); nrm[..., 2] = 1.0
+    if seed % 2:
+        nrm[..., 0] = rng.normal(0, 0.03, (ny, nx)); nrm[..., 1] = rng.normal(0, 0.03, (ny, nx))
+    nrm /= np.linalg.norm(nrm, axis=2, keepdims=True)
+    nth = np.zeros((ny, nx, 3)); nth[..., 1] = 1.0
+    nth -= (nth * nrm).sum(axis=2, keepdims=True) * nrm
+    nth /= np.linalg.norm(nth, axis=2, keepdims=True)
+    mask = (rng.random((ny, nx)) < 0.85).astype(np.uint8)
+    a = (vg, n, n + 3, nrm.astype(np.float32), nth.astype(np.float32), off0, off1, float(spacing * n * 1.5 / 1000.0))
+    kw = dict(azim_num=int(rng.choice([3, 8, 25, 60])), hori_acc=float(rng.choice([0.1, 0.25, 1.0, 4.0])),
+              elev_ang_low_lim=float(rng.choice([-40.0, -15.0, -2.0])), mask=mask, hori_fill=float(rng.normal()),
+              ray_org_elev=float(rng.choice([0.006, 0.05, 2.0])),
+              ray_algorithm=str(rng.choice(["guess_constant", "guess_constant", "binary_search", "discrete_sampling"])))
+    h_gpu, _ = hb.horizon.horizon_gridded(*a, **kw)
+    st = hb.resident.last_stats()
+    h_cpu, _, rays = oracle.horizon_gridded(*a, return_rays=True, **kw)
+    _assert_same(h_gpu, h_cpu, "random case %d %s" % (seed, kw))
+    assert st["rays"] == rays, "cast counter differs from the oracle's in case %d" % seed
+
