@@ -199,21 +199,19 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
     const bool h0 = wide2_child_test<TWO>(r0, L, tfar, t0), h1 = wide2_child_test<TWO>(r1, L, tfar, t1);
     const bool h2 = wide2_child_test<TWO>(r2, L, tfar, t2), h3 = wide2_child_test<TWO>(r3, L, tfar, t3);
     cnt.nodes += trav ? 1u : 0u;
-    const unsigned int hm = trav ? ((h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u)) : 0u;
-    const unsigned int lfm = (r0.w >> 31) | ((r1.w >> 31) << 1) | ((r2.w >> 31) << 2) | ((r3.w >> 31) << 3);
-    const unsigned int lm = hm & lfm;
-    const unsigned int im = hm & ~lfm;
-    {   // first hit internal child next, the rest onto the stack.  No distance order: the upper ray of
-        // a packet usually misses and has to visit every box it meets anyway (measured on B200: the
-        // nearest-first selection cost 9 % and visited MORE nodes)
-        unsigned int first = im & (0u - im);     // lowest set bit (0 if no internal hit)
-        if (SORT) {
-            const float k0 = (im & 1u) ? t0 : INFINITY, k1 = (im & 2u) ? t1 : INFINITY;
-            const float k2 = (im & 4u) ? t2 : INFINITY, k3 = (im & 8u) ? t3 : INFINITY;
-            const float kmin = fminf(fminf(k0, k1), fminf(k2, k3));
-            const unsigned int eq = ((k0 == kmin) ? 1u : 0u) | ((k1 == kmin) ? 2u : 0u) | ((k2 == kmin) ? 4u : 0u) | ((k3 == kmin) ? 8u : 0u);
-            first = (im & eq) & (0u - (im & eq));
-        }
+    bool lf0, lf1, lf2, lf3;      // leaf children met by the packet -> pending list
+    if (SORT) {
+        const unsigned int hm = trav ? ((h0 ? 1u : 0u) | (h1 ? 2u : 0u) | (h2 ? 4u : 0u) | (h3 ? 8u : 0u)) : 0u;
+        const unsigned int lfm = (r0.w >> 31) | ((r1.w >> 31) << 1) | ((r2.w >> 31) << 2) | ((r3.w >> 31) << 3);
+        const unsigned int lm = hm & lfm;
+        const unsigned int im = hm & ~lfm;
+        lf0 = lm & 1u; lf1 = lm & 2u; lf2 = lm & 4u; lf3 = lm & 8u;
+        // nearest hit internal child next, the rest onto the stack
+        const float k0 = (im & 1u) ? t0 : INFINITY, k1 = (im & 2u) ? t1 : INFINITY;
+        const float k2 = (im & 4u) ? t2 : INFINITY, k3 = (im & 8u) ? t3 : INFINITY;
+        const float kmin = fminf(fminf(k0, k1), fminf(k2, k3));
+        const unsigned int eq = ((k0 == kmin) ? 1u : 0u) | ((k1 == kmin) ? 2u : 0u) | ((k2 == kmin) ? 4u : 0u) | ((k3 == kmin) ? 8u : 0u);
+        const unsigned int first = (im & eq) & (0u - (im & eq));     // lowest set bit (0 if no internal hit)
         const uint32_t firstc = (first & 1u) ? r0.w : ((first & 2u) ? r1.w : ((first & 4u) ? r2.w : r3.w));
         const unsigned int others = im & ~first;
         int sp = L.sp;
@@ -233,16 +231,42 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
             L.sp = sp; L.node = next;
             if (next == WQ_NONE) L.state = 2;
         }
+    } else {
+        // First hit internal child next (lowest slot), the others onto the stack.  No distance order: the
+        // upper ray of a packet usually misses and has to visit every box it meets anyway (measured on B200:
+        // the nearest-first selection cost 9 % and visited MORE nodes).  Plain predicates, no bit masks.
+        const bool l0 = (int)r0.w < 0, l1 = (int)r1.w < 0, l2 = (int)r2.w < 0, l3 = (int)r3.w < 0;   // leaf flag = bit 31
+        const bool a0 = trav && h0, a1 = trav && h1, a2 = trav && h2, a3 = trav && h3;
+        const bool i0 = a0 && !l0, i1 = a1 && !l1, i2 = a2 && !l2, i3 = a3 && !l3;
+        lf0 = a0 && l0; lf1 = a1 && l1; lf2 = a2 && l2; lf3 = a3 && l3;
+        const bool p1 = i1 && i0, p2 = i2 && (i0 || i1), p3 = i3 && (i0 || i1 || i2);   // slot 0 is never pushed
+        int sp = L.sp;
+        if (sp + 3 > WQ_STACK_N) { if (p1 || p2 || p3) atomicAdd(overflow, 1u); }
+        else {
+            if (p1) { sh.stack[sp][tid] = r1.w; ++sp; }
+            if (p2) { sh.stack[sp][tid] = r2.w; ++sp; }
+            if (p3) { sh.stack[sp][tid] = r3.w; ++sp; }
+        }
+        if (trav) {
+            uint32_t next = i0 ? r0.w : (i1 ? r1.w : (i2 ? r2.w : r3.w));
+            if (!(i0 || i1 || i2 || i3)) {
+                next = WQ_NONE;
+                if (sp > 0) { --sp; next = sh.stack[sp][tid]; }
+            }
+            L.sp = sp; L.node = next;
+            if (next == WQ_NONE) L.state = 2;
+        }
     }
-    // ---- 2. leaf hits -> the lane's own pending list (room for 4 is guaranteed by the flush rule)
+    // ---- 2. leaf hits -> the lane's own pending list (room for 4 is guaranteed by the flush rule); the
+    //         leaf flag (bit 31) stays on, the tester strips it
     {
         int pc = L.pc;
-        if (lm & 1u) { sh.pend[pc][tid] = r0.w & 0x7FFFFFFFu; ++pc; }
-        if (lm & 2u) { sh.pend[pc][tid] = r1.w & 0x7FFFFFFFu; ++pc; }
-        if (lm & 4u) { sh.pend[pc][tid] = r2.w & 0x7FFFFFFFu; ++pc; }
-        if (lm & 8u) { sh.pend[pc][tid] = r3.w & 0x7FFFFFFFu; ++pc; }
+        if (lf0) { sh.pend[pc][tid] = r0.w; ++pc; }
+        if (lf1) { sh.pend[pc][tid] = r1.w; ++pc; }
+        if (lf2) { sh.pend[pc][tid] = r2.w; ++pc; }
+        if (lf3) { sh.pend[pc][tid] = r3.w; ++pc; }
         L.pc = pc;
-        pend_est += __popc(__ballot_sync(FULL, lm != 0u));   // lower bound: one per lane with new candidates
+        pend_est += __popc(__ballot_sync(FULL, lf0 || lf1 || lf2 || lf3));   // lower bound: one per lane with new candidates
     }
     // ---- 3. leaf batches
     {
@@ -277,7 +301,7 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
                 bool q1 = false, q2 = false;
                 if ((unsigned int)lane < nb) {
                     const unsigned int k = base + (unsigned int)lane - ex_o;
-                    const uint32_t prim = sh.pend[pc_o - 1u - k][(tid & ~31) + owner];
+                    const uint32_t prim = sh.pend[pc_o - 1u - k][(tid & ~31) + owner] & 0x7FFFFFFFu;
                     const float* r = &sh.ray[warp][0][owner];
                     const F3 O = f3(r[0], r[32], r[64]);
                     const F3 D1 = f3(r[96], r[128], r[160]), D2 = f3(r[192], r[224], r[256]);
