@@ -32,7 +32,7 @@ namespace hzb {
 constexpr int WQ2_PEND_N = 12;   // per-lane pending leaf candidates (a flush is forced above PEND_N - 4)
 
 struct Wq2Shared {
-    uint32_t stack[WQ_STACK_N][WQ_BLOCK];
+    uint32_t stack[WQ_STACK_N + 3][WQ_BLOCK];     // three spare rows: a step pushes at most three entries
     uint32_t pend[WQ2_PEND_N][WQ_BLOCK];
     float ray[WQ_NWARPS][9][32];              // O.xyz, D1.xyz, D2.xyz per lane
     unsigned int hit1[WQ_NWARPS], hit2[WQ_NWARPS];
@@ -232,27 +232,31 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
             if (next == WQ_NONE) L.state = 2;
         }
     } else {
-        // First hit internal child next (lowest slot), the others onto the stack.  No distance order: the
-        // upper ray of a packet usually misses and has to visit every box it meets anyway (measured on B200:
-        // the nearest-first selection cost 9 % and visited MORE nodes).  Plain predicates, no bit masks.
-        const bool l0 = (int)r0.w < 0, l1 = (int)r1.w < 0, l2 = (int)r2.w < 0, l3 = (int)r3.w < 0;   // leaf flag = bit 31
-        const bool a0 = trav && h0, a1 = trav && h1, a2 = trav && h2, a3 = trav && h3;
-        const bool i0 = a0 && !l0, i1 = a1 && !l1, i2 = a2 && !l2, i3 = a3 && !l3;
-        lf0 = a0 && l0; lf1 = a1 && l1; lf2 = a2 && l2; lf3 = a3 && l3;
-        const bool p1 = i1 && i0, p2 = i2 && (i0 || i1), p3 = i3 && (i0 || i1 || i2);   // slot 0 is never pushed
-        int sp = L.sp;
-        if (sp + 3 > WQ_STACK_N) { if (p1 || p2 || p3) atomicAdd(overflow, 1u); }
-        else {
-            if (p1) { sh.stack[sp][tid] = r1.w; ++sp; }
-            if (p2) { sh.stack[sp][tid] = r2.w; ++sp; }
-            if (p3) { sh.stack[sp][tid] = r3.w; ++sp; }
+        // Children in slot order with three running values: the next node (first hit internal child), the
+        // stack pointer (further internal hits) and the pending-list length (leaf hits).  No distance order:
+        // the upper ray of a packet usually misses and has to visit every box it meets anyway (measured on
+        // B200: the nearest-first selection cost 9 % and visited MORE nodes).  The stack has three spare
+        // rows, so a full stack is detected once per step, not per push.
+        int sp = L.sp, pc = L.pc;
+        uint32_t next = WQ_NONE;
+#define HZB_WQ2_CHILD(RK, HK)                                                      \
+        {                                                                          \
+            const bool a_ = trav && (HK);                                          \
+            const bool lf_ = a_ && ((int)(RK).w < 0);      /* leaf flag = bit 31 */   \
+            const bool in_ = a_ && ((int)(RK).w >= 0);                             \
+            const bool push_ = in_ && (next != WQ_NONE);                           \
+            const bool first_ = in_ && (next == WQ_NONE);                          \
+            if (lf_) { sh.pend[pc][tid] = (RK).w; ++pc; }   /* the tester strips the flag */ \
+            if (push_) { sh.stack[sp][tid] = (RK).w; ++sp; }                       \
+            if (first_) next = (RK).w;                                             \
         }
+        HZB_WQ2_CHILD(r0, h0) HZB_WQ2_CHILD(r1, h1) HZB_WQ2_CHILD(r2, h2) HZB_WQ2_CHILD(r3, h3)
+#undef HZB_WQ2_CHILD
+        lf0 = pc != L.pc; lf1 = lf2 = lf3 = false;
+        L.pc = pc;
+        if (sp > WQ_STACK_N) { atomicAdd(overflow, 1u); sp = WQ_STACK_N; }     // results invalid, reported through the counter
         if (trav) {
-            uint32_t next = i0 ? r0.w : (i1 ? r1.w : (i2 ? r2.w : r3.w));
-            if (!(i0 || i1 || i2 || i3)) {
-                next = WQ_NONE;
-                if (sp > 0) { --sp; next = sh.stack[sp][tid]; }
-            }
+            if (next == WQ_NONE && sp > 0) { --sp; next = sh.stack[sp][tid]; }
             L.sp = sp; L.node = next;
             if (next == WQ_NONE) L.state = 2;
         }
@@ -260,12 +264,14 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
     // ---- 2. leaf hits -> the lane's own pending list (room for 4 is guaranteed by the flush rule); the
     //         leaf flag (bit 31) stays on, the tester strips it
     {
-        int pc = L.pc;
-        if (lf0) { sh.pend[pc][tid] = r0.w; ++pc; }
-        if (lf1) { sh.pend[pc][tid] = r1.w; ++pc; }
-        if (lf2) { sh.pend[pc][tid] = r2.w; ++pc; }
-        if (lf3) { sh.pend[pc][tid] = r3.w; ++pc; }
-        L.pc = pc;
+        if (SORT) {
+            int pc = L.pc;
+            if (lf0) { sh.pend[pc][tid] = r0.w; ++pc; }
+            if (lf1) { sh.pend[pc][tid] = r1.w; ++pc; }
+            if (lf2) { sh.pend[pc][tid] = r2.w; ++pc; }
+            if (lf3) { sh.pend[pc][tid] = r3.w; ++pc; }
+            L.pc = pc;
+        }
         pend_est += __popc(__ballot_sync(FULL, lf0 || lf1 || lf2 || lf3));   // lower bound: one per lane with new candidates
     }
     // ---- 3. leaf batches
