@@ -331,11 +331,10 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
             if (L.state != 0) {
                 if (L.hit1 && L.hit2) { L.state = 2; L.pc = 0; }          // both decided: drop the rest
                 else if (!TWO) {}
-                else if (L.hit2 && ((m2 >> lane) & 1u)) {                 // lower ray decided: walk on with the upper one only
-                    L.A2x = L.A1x; L.A2y = L.A1y; L.A2z = L.A1z; L.B2x = L.B1x; L.B2y = L.B1y; L.B2z = L.B1z;
-                } else if (L.hit1 && ((m1 >> lane) & 1u)) {
-                    L.A1x = L.A2x; L.A1y = L.A2y; L.A1z = L.A2z; L.B1x = L.B2x; L.B1y = L.B2y; L.B1z = L.B2z;
-                }
+                // one ray decided: it stops entering boxes (an infinite x offset makes its entry distance +inf),
+                // the walk goes on for the other ray only
+                else if (L.hit2) L.B2x = INFINITY;
+                else if (L.hit1) L.B1x = INFINITY;
             }
         }
     }
