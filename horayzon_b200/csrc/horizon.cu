@@ -8,8 +8,10 @@
 // explicitly rounded intrinsics in the reference's float/double mix, so the
 // outputs are decision-exact against the CPU oracle.
 //
-//   k_horizon_wq5      production: search state machine + warp-queue traversal of
-//                      the compressed 4-wide BVH (hzb_wq.cuh)
+//   k_horizon_wq6      production: search state machine + two-ray packet warp-queue
+//                      traversal of the compressed 4-wide BVH (hzb_wq2.cuh)
+//   k_horizon_wq5      first-generation single-ray step (hzb_wq.cuh; HZB_KERNEL=wq5,
+//                      kept for A/B runs and the variant parity tests)
 //   k_horizon_gridded  reference-shaped per-lane kernel on the binary BVH
 //                      (HZB_KERNEL=simple; kept for A/B runs and as a second,
 //                      structurally different implementation in the parity tests)
@@ -385,7 +387,7 @@ again:
 }
 
 // ===========================================================================
-// k_horizon_wq5: production kernel.  Per-lane search state machine (sm_advance)
+// k_horizon_wq5: first-generation kernel (HZB_KERNEL=wq5).  Per-lane search state machine (sm_advance)
 // + the shared warp-queue traversal step of hzb_wq.cuh.
 // ===========================================================================
 template <int ALG, bool TOPS>

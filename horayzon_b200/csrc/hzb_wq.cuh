@@ -1,5 +1,6 @@
-// hzb_wq.cuh -- the warp-queue traversal step shared by the horizon and the
-// shadow kernels (compressed 4-wide BVH, one ray per lane).
+// hzb_wq.cuh -- FIRST-GENERATION warp-queue traversal step (compressed 4-wide BVH, one ray per
+// lane), superseded in production by hzb_wq2.cuh; still selectable (HZB_KERNEL=wq5,
+// HZB_SHADOW_KERNEL=wq1) and parity-tested.  Shared constants (block size, stack depth) live here.
 //
 // One call = one iteration of the warp's traversal loop:
 //   1. node step, executed by ALL lanes (lanes without a traversing ray read the
