@@ -971,3 +971,156 @@ int orc_rotation_matrix_glob2loc(const float* north, const float* norm, int ny, 
     return 0;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Self-tests of two arithmetic claims the CUDA product relies on.
+// They restate the PRODUCT's formulation on the CPU (same operation order, fmaf where the
+// kernel uses __fmaf_rn) and compare it with the specification above on random and
+// adversarial inputs.  Test infrastructure only.
+// ---------------------------------------------------------------------------
+namespace {
+struct Rng {   // splitmix64
+    uint64_t s;
+    uint64_t next() { uint64_t z = (s += 0x9E3779B97F4A7C15ull); z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); }
+    double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    float range(float a, float b) { return (float)(a + (b - a) * uni()); }
+};
+static inline bool edges_accept(float U, float V, float W) {
+    const float UVW = (U + V) + W;
+    const float eps = std::numeric_limits<float>::epsilon() * fabsf(UVW);
+    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
+    return (mn >= -eps) || (mx <= eps);
+}
+static inline V3 tri_ng(V3 e0, V3 e1, V3 e2) {
+    const float ab_x = e0.z * e1.y, ab_y = e0.x * e1.z, ab_z = e0.y * e1.x;
+    const float bc_x = e1.z * e2.y, bc_y = e1.x * e2.z, bc_z = e1.y * e2.x;
+    const V3 cab = {fmaf(e0.y, e1.z, -ab_x), fmaf(e0.z, e1.x, -ab_y), fmaf(e0.x, e1.y, -ab_z)};
+    const V3 cbc = {fmaf(e1.y, e2.z, -bc_x), fmaf(e1.z, e2.x, -bc_y), fmaf(e1.x, e2.y, -bc_z)};
+    return {fabsf(ab_x) < fabsf(bc_x) ? cab.x : cbc.x, fabsf(ab_y) < fabsf(bc_y) ? cab.y : cbc.y,
+            fabsf(ab_z) < fabsf(bc_z) ? cab.z : cbc.z};
+}
+static inline bool depth_ok(V3 v0, V3 Ng, V3 D, float tfar) {
+    const float dn = dot_f(Ng, D), den = dn + dn;
+    if (den == 0.0f) return false;
+    const float tn = dot_f(v0, Ng), t = (tn + tn) / den;
+    return t >= 0.0f && t <= tfar;
+}
+// The product's quad test (hzb_wq2.cuh prim_hit2, one ray): five edge functions, the diagonal's
+// function of the second triangle is the NEGATIVE of the first triangle's.
+static bool quad_hit_shared(V3 p00, V3 p01, V3 p10, V3 p11, V3 O, V3 D, float tfar) {
+    const V3 a = sub3(p00, O), b = sub3(p01, O), c = sub3(p10, O), d = sub3(p11, O);
+    const V3 e0 = sub3(c, a), e1 = sub3(a, b), e2 = sub3(b, c);
+    const V3 f0 = sub3(b, d), f1 = sub3(d, c);
+    const V3 C0 = cross_f(e0, add3(c, a)), C1 = cross_f(e1, add3(a, b)), C2 = cross_f(e2, add3(b, c));
+    const V3 G0 = cross_f(f0, add3(b, d)), G1 = cross_f(f1, add3(d, c));
+    const float W1 = dot_f(C2, D);
+    const bool a1 = edges_accept(dot_f(C0, D), dot_f(C1, D), W1);
+    const bool a2 = edges_accept(dot_f(G0, D), dot_f(G1, D), -W1);
+    bool h = false;
+    if (a1) h = depth_ok(a, tri_ng(e0, e1, e2), D, tfar);
+    if (a2 && !h) { const V3 f2 = {-e2.x, -e2.y, -e2.z}; h = depth_ok(d, tri_ng(f0, f1, f2), D, tfar); }
+    return h;
+}
+}  // namespace
+
+extern "C" {
+// Random + adversarial (rays through vertices, edge midpoints and points on the diagonal) quads:
+// number of cases where the shared-diagonal formulation differs from tri_hit(T1) || tri_hit(T2).
+long long orc_selftest_shared_diagonal(unsigned long long seed, long long n, long long* hits_out) {
+    Rng R{seed};
+    long long bad = 0, hits = 0;
+    for (long long it = 0; it < n; ++it) {
+        const float scale = (it & 1) ? 90.0f : 2.0f, base = R.range(-5e4f, 5e4f), by = R.range(-5e4f, 5e4f);
+        const V3 p00 = {base, by, R.range(-500.f, 3000.f)};
+        const V3 p01 = {base + scale, by, p00.z + R.range(-scale, scale)};
+        const V3 p10 = {base, by + scale, p00.z + R.range(-scale, scale)};
+        const V3 p11 = {base + scale, by + scale, p00.z + R.range(-scale, scale)};
+        const V3 O = {base + R.range(-2e4f, 2e4f), by + R.range(-2e4f, 2e4f), R.range(-500.f, 4000.f)};
+        // target: a point of the quad, biased to its critical places
+        V3 T;
+        const int kind = (int)(R.next() % 6);
+        const float u = R.range(0.f, 1.f), v = R.range(0.f, 1.f);
+        if (kind == 0) T = p01;                                                   // a vertex of the diagonal
+        else if (kind == 1) T = {p01.x + (p10.x - p01.x) * u, p01.y + (p10.y - p01.y) * u, p01.z + (p10.z - p01.z) * u};   // on the diagonal
+        else if (kind == 2) T = {p00.x + (p01.x - p00.x) * u, p00.y, p00.z + (p01.z - p00.z) * u};                         // on an outer edge
+        else T = {base + scale * (u * 1.2f - 0.1f), by + scale * (v * 1.2f - 0.1f), p00.z + R.range(-scale, scale)};          // anywhere near
+        V3 D = sub3(T, O);
+        const float len = sqrtf(D.x * D.x + D.y * D.y + D.z * D.z);
+        if (!(len > 0.f)) continue;
+        D = {D.x / len, D.y / len, D.z / len};
+        const float tfar = (it % 7 == 0) ? len * R.range(0.5f, 1.5f) : 1e9f;
+        float t;
+        const Tri T1{p00, p01, p10}, T2{p11, p10, p01};
+        const bool ref = tri_hit(T1, O, D, tfar, &t) || tri_hit(T2, O, D, tfar, &t);
+        const bool got = quad_hit_shared(p00, p01, p10, p11, O, D, tfar);
+        hits += ref; bad += (ref != got);
+    }
+    if (hits_out) *hits_out = hits;
+    return bad;
+}
+
+// Conservativeness of the packet step's box test: quantised planes widened by one quantum,
+// t = fmaf(qb, A, B') with qb = 2^23 + q, B' = fmaf(-2^23, A, B), approximate reciprocal (perturbed
+// by up to 2 ulp here), no slack on tmax.  Returns the number of rays that meet the UNPADDED box
+// in exact (double) arithmetic within [0, tfar] but are rejected by the float test.
+long long orc_selftest_folded_slab(unsigned long long seed, long long n, long long* accepted_out) {
+    Rng R{seed};
+    long long bad = 0, acc = 0;
+    const float M = 8388608.0f;
+    for (long long it = 0; it < n; ++it) {
+        const double extent = (it & 1) ? 1.1e5 : 1.2e4;
+        const float qstep = (float)(extent / 65529.0), qorg[3] = {R.range(-3e6f, 3e6f), R.range(-3e6f, 3e6f), R.range(-1e3f, 1e3f)};
+        // a box on the grid (its true planes anywhere inside the outward-rounded cells)
+        double lo[3], hi[3]; uint32_t ql[3], qh[3];
+        for (int a = 0; a < 3; ++a) {
+            const double l = 3.0 + R.uni() * 65000.0, w = (R.uni() < 0.3 ? 0.0 : R.uni() * ((it & 2) ? 40.0 : 4000.0));
+            const double h = std::min(l + w, 65530.0);
+            lo[a] = (double)qorg[a] + l * (double)qstep; hi[a] = (double)qorg[a] + h * (double)qstep;
+            ql[a] = (uint32_t)floor(l) - 1u; qh[a] = (uint32_t)ceil(h) + 1u;       // bvh_wide.cu quant_pair
+        }
+        // ray: origin inside the scene, aimed near the box (so that many rays graze it)
+        double O[3], T[3], D[3];
+        for (int a = 0; a < 3; ++a) {
+            O[a] = (double)(float)((double)qorg[a] + R.uni() * 65529.0 * (double)qstep);
+            const double pad = (hi[a] - lo[a]) * 0.02 + (double)qstep * 0.5;
+            T[a] = lo[a] - pad + R.uni() * (hi[a] - lo[a] + 2 * pad);
+            D[a] = T[a] - O[a];
+        }
+        const double len = sqrt(D[0] * D[0] + D[1] * D[1] + D[2] * D[2]);
+        if (!(len > 0.0)) continue;
+        float Df[3];
+        for (int a = 0; a < 3; ++a) { Df[a] = (float)(D[a] / len); if ((R.next() & 15) == 0) Df[a] = 0.0f; }
+        const float tfar = (it % 5 == 0) ? (float)(len * (0.5 + R.uni())) : 5.0e4f;
+        // exact test of the float ray against the unpadded box
+        double t0 = 0.0, t1 = (double)tfar; bool ok = true;
+        for (int a = 0; a < 3 && ok; ++a) {
+            const double d = (double)Df[a];
+            if (d == 0.0) { if (O[a] < lo[a] || O[a] > hi[a]) ok = false; continue; }
+            double ta = (lo[a] - O[a]) / d, tb = (hi[a] - O[a]) / d;
+            if (ta > tb) std::swap(ta, tb);
+            t0 = std::max(t0, ta); t1 = std::min(t1, tb);
+        }
+        ok = ok && t0 <= t1;
+        if (!ok) continue;
+        ++acc;
+        // the product's float test
+        float tmin = 0.0f, tmax = tfar;
+        for (int a = 0; a < 3; ++a) {
+            float d = Df[a];
+            if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
+            float inv = 1.0f / d;
+            const int ulps = (int)(R.next() % 5) - 2;                             // approximate reciprocal: +-2 ulp
+            for (int k = 0; k < abs(ulps); ++k) inv = nextafterf(inv, ulps > 0 ? INFINITY : -INFINITY);
+            const float A = qstep * inv;
+            const float B = fmaf(-M, A, (qorg[a] - (float)O[a]) * inv);
+            const float qa = M + (float)ql[a], qb = M + (float)qh[a];
+            const float ta = fmaf(qa, A, B), tb = fmaf(qb, A, B);
+            tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
+        }
+        if (!(tmin <= tmax)) ++bad;
+    }
+    if (accepted_out) *accepted_out = acc;
+    return bad;
+}
+}  // extern "C"

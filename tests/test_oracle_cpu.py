@@ -278,3 +278,30 @@ def test_transform_matches_reference_golden():
     assert np.allclose(oracle.ecef2enu_vector(n0, t)[0, 0], [0, 0, 1], atol=1e-7)
     assert np.allclose(oracle.ecef2enu_vector(oracle.north_dir(x0, y0, z0, n0, "WGS84"), t)[0, 0], [0, 1, 0], atol=1e-7)
 
+
+def test_shared_diagonal_quad_test_equals_two_triangle_tests():
+    """The production quad test evaluates five Pluecker edge functions per quad: the diagonal's function of
+    the second triangle is taken as the NEGATIVE of the first triangle's (exact in round-to-nearest).  On two
+    million random and adversarial cases (rays through vertices, along the diagonal, on outer edges, short
+    tfar) it must make the decisions of tri_hit(T1) || tri_hit(T2)."""
+    import ctypes
+    L = oracle.lib()
+    L.orc_selftest_shared_diagonal.restype = ctypes.c_longlong
+    hits = ctypes.c_longlong(0)
+    bad = L.orc_selftest_shared_diagonal(ctypes.c_ulonglong(12345), ctypes.c_longlong(2_000_000), ctypes.byref(hits))
+    assert bad == 0
+    assert 200_000 < hits.value < 1_900_000      # the cases are not trivially all-hit or all-miss
+
+
+def test_folded_bias_box_test_is_conservative():
+    """The packet step's box test (2^23 decode bias folded into the ray constant, one extra quantum on every
+    plane, approximate reciprocal, no slack on tmax) must never reject a box that the ray meets in exact
+    arithmetic -- also for flat boxes, axis-parallel rays and coordinates of 3e6 m magnitude."""
+    import ctypes
+    L = oracle.lib()
+    L.orc_selftest_folded_slab.restype = ctypes.c_longlong
+    acc = ctypes.c_longlong(0)
+    bad = L.orc_selftest_folded_slab(ctypes.c_ulonglong(777), ctypes.c_longlong(3_000_000), ctypes.byref(acc))
+    assert bad == 0
+    assert acc.value > 300_000
+
