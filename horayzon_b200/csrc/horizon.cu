@@ -19,6 +19,7 @@
 #include "hzb_geom.cuh"
 #include "hzb_wq.cuh"
 #include "hzb_wq2.cuh"
+#include "hzb_search.cuh"
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
@@ -96,12 +97,8 @@ __device__ __forceinline__ Frame make_frame(F3 vert, F3 norm, F3 north, float li
     return f;
 }
 
-struct Search {  // everything a lane needs to cast one ray of the search
+struct Search : SearchTables {  // everything a lane needs to cast one ray of the search (tables: hzb_search.cuh)
     SceneView sv;
-    const float* __restrict__ azim_sin; const float* __restrict__ azim_cos;
-    const float* __restrict__ elev_ang; const float* __restrict__ elev_sin; const float* __restrict__ elev_cos;
-    int azim_num, elev_num;
-    float acc, low, up, dist; double step;
     unsigned int* overflow;
 };
 
@@ -136,12 +133,6 @@ __device__ __forceinline__ bool cast_closest(const Search& s, const Frame& f, in
     dist = tfar;
     return hit;
 }
-
-__device__ __forceinline__ int index_of(const Search& s, float elev) {  // (int)roundf((elev-low)/(acc/5.0))
-    const double q = __ddiv_rn((double)__fsub_rn(elev, s.low), s.step);
-    return (int)roundf(__double2float_rn(q));
-}
-__device__ __forceinline__ float midpoint(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
 
 // bisection for one azimuth (horizon_comp.cpp:348-376); returns the final index
 template <bool WD>
@@ -278,115 +269,6 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
 
 
 // ===========================================================================
-// Search state machine.  Every lane owns one cell and runs the reference's
-// search (horizon_comp.cpp:302-498) as explicit states, so that all lanes of a
-// warp can share ONE traversal loop (hzb_wq.cuh) instead of sitting in three
-// inlined copies of it: sm_advance consumes the result of the last cast and
-// returns the table index of the next cast, or "cell finished".  The hit/miss
-// DECISIONS are those of cell_search<ALG> above, bit for bit.
-// ===========================================================================
-struct LaneSM {
-    // search state (horizon_comp.cpp:387-498 unrolled into states)
-    int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
-    int k, cur, prev, count, prev_az;   // during a bisection (phase 1) prev / count hold the bits of lim_up / lim_low
-    int spec_ie; bool spec_hit;   // packet kernels: table index / result of the cast that travelled with the last one (-1: none)
-};
-
-template <int ALG, bool PK>
-__device__ __forceinline__ bool sm_begin_azimuth(const Search& s, LaneSM& m, int& cast_ie, int& lo_ie) {
-    // returns true if a cast is required (cast_ie set), false if the azimuth needs none
-    const int top = s.elev_num - 1;
-    if (ALG == 0) {
-        m.phase = 4; m.prev = 0; m.cur = min(10, top); cast_ie = m.cur;
-        if (PK) lo_ie = min(m.cur + 10, top);                   // the next sample, should this one hit
-        return true;
-    } else if (ALG == 1 || m.k == 0) {
-        m.phase = 1; m.prev = __float_as_int(s.up); m.count = __float_as_int(s.low);
-        m.cur = index_of(s, midpoint(s.up, s.low));
-        const float ea = __ldg(s.elev_ang + m.cur);
-        if (fmaxf(__fsub_rn(s.up, ea), __fsub_rn(ea, s.low)) > s.acc) { cast_ie = m.cur; return true; }
-        return false;
-    } else {
-        m.phase = 2; m.count = 0;
-        m.prev = max(m.prev_az - 5, 0); m.cur = min(m.prev + 10, top); cast_ie = m.cur;
-        if (PK) lo_ie = max(min(m.prev_az + 5, top) - 10, 0);   // first index of the downward search (:472-476)
-        return true;
-    }
-}
-
-// Consume the result of the last cast (if any) and move on until the next cast
-// is known or the cell is finished.  Returns true with cast_ie set when a ray
-// must be traced; false when the cell is complete.
-// PK (packet kernels): every cast of the stepping searches names a COMPANION in lo_ie --
-// the cast the reference makes next if this one goes the expected way (prev-5 beside the
-// first prev+5 of a guess_constant azimuth, otherwise the next index in the direction of
-// travel).  The kernel traces both as one packet and records the companion's index and
-// result in m.spec_ie / m.spec_hit; when the search then asks for exactly that index the
-// stored result is consumed instead of casting, and counted in extra_rays -- i.e. only
-// when the reference would have cast it.  An unused companion result is dropped.
-template <int ALG, bool PK>
-__device__ __forceinline__ bool sm_advance(const Search& s, LaneSM& m, bool have_result, bool hit, OutBuf& ob, int& cast_ie,
-                                           int& lo_ie, unsigned int& extra_rays) {
-    const int top = s.elev_num - 1;
-    lo_ie = -1;
-#define HZB_SM_CAST(COMPANION)                                                                        \
-    do {                                                                                              \
-        if (PK && m.spec_ie == m.cur) { m.spec_ie = -1; hit = m.spec_hit; ++extra_rays; goto again; } \
-        cast_ie = m.cur;                                                                              \
-        if (PK) { lo_ie = (COMPANION); if (lo_ie == cast_ie) lo_ie = -1; }                            \
-        return true;                                                                                  \
-    } while (0)
-again:
-    while (true) {
-        if (!have_result) {  // start of an azimuth
-            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie)) { if (lo_ie == cast_ie) lo_ie = -1; return true; }
-            // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
-            hit = false; have_result = true;
-            // (emulate loop exit below)
-            goto bisect_done;
-        }
-        if (m.phase == 1) {
-            {
-                const float ea = __ldg(s.elev_ang + m.cur);
-                if (hit) m.count = __float_as_int(ea); else m.prev = __float_as_int(ea);
-                const float lim_up = __int_as_float(m.prev), lim_low = __int_as_float(m.count);
-                m.cur = index_of(s, midpoint(lim_up, lim_low));
-                const float ea2 = __ldg(s.elev_ang + m.cur);
-                if (fmaxf(__fsub_rn(lim_up, ea2), __fsub_rn(ea2, lim_low)) > s.acc) { cast_ie = m.cur; return true; }
-            }
-        bisect_done:
-            ob.put(m.k, midpoint(__int_as_float(m.prev), __int_as_float(m.count)));   // un-quantised midpoint (:377, :428)
-            m.prev_az = m.cur;            // seeds the chain (:429)
-        } else if (m.phase == 2) {
-            m.count++;
-            if (m.cur == top) hit = false;            // termination rule
-            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }
-            if (m.count <= 1) {                       // first upward cast missed: search downwards (:471-488)
-                m.phase = 3;
-                m.prev = min(m.prev_az + 5, top); m.cur = max(m.prev - 10, 0);
-                HZB_SM_CAST(max(m.cur - 10, 0));
-            }
-            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
-            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
-        } else if (m.phase == 3) {
-            if (m.cur == 0) hit = true;               // termination rule
-            if (!hit) { m.prev = m.cur; m.cur = max(m.cur - 10, 0); HZB_SM_CAST(max(m.cur - 10, 0)); }
-            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
-            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
-        } else {  // phase 4: discrete sampling (:309-331)
-            if (m.cur == top) hit = false;
-            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }
-            ob.put(m.k, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
-        }
-        // azimuth finished
-        m.k++; m.spec_ie = -1;
-        if (m.k >= s.azim_num) { m.phase = 0; return false; }
-        have_result = false;
-    }
-#undef HZB_SM_CAST
-}
-
-// ===========================================================================
 // k_horizon_wq5: first-generation kernel (HZB_KERNEL=wq5).  Per-lane search state machine (sm_advance)
 // + the shared warp-queue traversal step of hzb_wq.cuh.
 // ===========================================================================
@@ -466,7 +348,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, Horiz
         bool finished_cell = false;
         if (has_cell && L.state == 0) {
             int ie, lo_ie; unsigned int extra = 0;
-            if (sm_advance<ALG, false>(s, m, have_result, L.hit, ob, ie, lo_ie, extra)) {
+            if (sm_advance<ALG, false, OutBuf>(s, m, have_result, L.hit, ob, ie, lo_ie, extra)) {
                 wq_start_ray(sv, sh, warp, lane, L, f.org, ray_dir(s, f, ie, m.k));
                 have_result = true; cnt.rays++;
             } else {
@@ -559,7 +441,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         if (has_cell && L.state == 0) {
             unsigned int extra = 0;
             m.spec_hit = L.hit2;
-            need_ray = sm_advance<ALG, true>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
+            need_ray = sm_advance<ALG, true, OutBuf>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
             cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
                 has_cell = false; finished_cell = true;

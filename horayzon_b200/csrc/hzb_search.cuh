@@ -1,0 +1,155 @@
+// hzb_search.cuh -- the reference's horizon search as a per-lane state machine.
+//
+// Host/device source: the CUDA kernels (horizon.cu) compile it for the device; the CPU test
+// infrastructure compiles THE SAME SOURCE for the host and drives it with the oracle's ray
+// casts (oracle/hzb_oracle.cpp, orc_selftest_state_machine), so that the search logic --
+// including the packet companions and the cast accounting -- is covered by the CPU suite.
+// Nothing here touches a BVH: the state machine only says which table index to cast next.
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#ifdef __CUDACC__
+#define HZB_HD __device__ __forceinline__
+#else   // host build: the explicitly rounded intrinsics are plain IEEE operations (compile with -ffp-contract=off)
+#define HZB_HD inline
+#include <algorithm>
+namespace hzb {
+using std::max; using std::min;
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline float __double2float_rn(double a) { return (float)a; }
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+}  // namespace hzb
+#endif
+
+namespace hzb {
+
+struct SearchTables {   // trig tables and limits of one call (horizon_comp.cpp:711-731)
+    const float* __restrict__ azim_sin; const float* __restrict__ azim_cos;
+    const float* __restrict__ elev_ang; const float* __restrict__ elev_sin; const float* __restrict__ elev_cos;
+    int azim_num, elev_num;
+    float acc, low, up, dist; double step;
+};
+
+HZB_HD int index_of(const SearchTables& s, float elev) {  // (int)roundf((elev-low)/(acc/5.0))
+    const double q = __ddiv_rn((double)__fsub_rn(elev, s.low), s.step);
+    return (int)roundf(__double2float_rn(q));
+}
+HZB_HD float midpoint(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f); }
+
+
+// ===========================================================================
+// Search state machine.  Every lane owns one cell and runs the reference's
+// search (horizon_comp.cpp:302-498) as explicit states, so that all lanes of a
+// warp can share ONE traversal loop (hzb_wq.cuh) instead of sitting in three
+// inlined copies of it: sm_advance consumes the result of the last cast and
+// returns the table index of the next cast, or "cell finished".  The hit/miss
+// DECISIONS are those of cell_search<ALG> above, bit for bit.
+// ===========================================================================
+struct LaneSM {
+    // search state (horizon_comp.cpp:387-498 unrolled into states)
+    int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
+    int k, cur, prev, count, prev_az;   // during a bisection (phase 1) prev / count hold the bits of lim_up / lim_low
+    int spec_ie; bool spec_hit;   // packet kernels: table index / result of the cast that travelled with the last one (-1: none)
+};
+
+template <int ALG, bool PK>
+HZB_HD bool sm_begin_azimuth(const SearchTables& s, LaneSM& m, int& cast_ie, int& lo_ie) {
+    // returns true if a cast is required (cast_ie set), false if the azimuth needs none
+    const int top = s.elev_num - 1;
+    if (ALG == 0) {
+        m.phase = 4; m.prev = 0; m.cur = min(10, top); cast_ie = m.cur;
+        if (PK) lo_ie = min(m.cur + 10, top);                   // the next sample, should this one hit
+        return true;
+    } else if (ALG == 1 || m.k == 0) {
+        m.phase = 1; m.prev = __float_as_int(s.up); m.count = __float_as_int(s.low);
+        m.cur = index_of(s, midpoint(s.up, s.low));
+        const float ea = __ldg(s.elev_ang + m.cur);
+        if (fmaxf(__fsub_rn(s.up, ea), __fsub_rn(ea, s.low)) > s.acc) { cast_ie = m.cur; return true; }
+        return false;
+    } else {
+        m.phase = 2; m.count = 0;
+        m.prev = max(m.prev_az - 5, 0); m.cur = min(m.prev + 10, top); cast_ie = m.cur;
+        if (PK) lo_ie = max(min(m.prev_az + 5, top) - 10, 0);   // first index of the downward search (:472-476)
+        return true;
+    }
+}
+
+// Consume the result of the last cast (if any) and move on until the next cast
+// is known or the cell is finished.  Returns true with cast_ie set when a ray
+// must be traced; false when the cell is complete.
+// PK (packet kernels): every cast of the stepping searches names a COMPANION in lo_ie --
+// the cast the reference makes next if this one goes the expected way (prev-5 beside the
+// first prev+5 of a guess_constant azimuth, otherwise the next index in the direction of
+// travel).  The kernel traces both as one packet and records the companion's index and
+// result in m.spec_ie / m.spec_hit; when the search then asks for exactly that index the
+// stored result is consumed instead of casting, and counted in extra_rays -- i.e. only
+// when the reference would have cast it.  An unused companion result is dropped.
+template <int ALG, bool PK, typename OB>
+HZB_HD bool sm_advance(const SearchTables& s, LaneSM& m, bool have_result, bool hit, OB& ob, int& cast_ie,
+                                           int& lo_ie, unsigned int& extra_rays) {
+    const int top = s.elev_num - 1;
+    lo_ie = -1;
+#define HZB_SM_CAST(COMPANION)                                                                        \
+    do {                                                                                              \
+        if (PK && m.spec_ie == m.cur) { m.spec_ie = -1; hit = m.spec_hit; ++extra_rays; goto again; } \
+        cast_ie = m.cur;                                                                              \
+        if (PK) { lo_ie = (COMPANION); if (lo_ie == cast_ie) lo_ie = -1; }                            \
+        return true;                                                                                  \
+    } while (0)
+again:
+    while (true) {
+        if (!have_result) {  // start of an azimuth
+            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie)) { if (lo_ie == cast_ie) lo_ie = -1; return true; }
+            // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
+            hit = false; have_result = true;
+            // (emulate loop exit below)
+            goto bisect_done;
+        }
+        if (m.phase == 1) {
+            {
+                const float ea = __ldg(s.elev_ang + m.cur);
+                if (hit) m.count = __float_as_int(ea); else m.prev = __float_as_int(ea);
+                const float lim_up = __int_as_float(m.prev), lim_low = __int_as_float(m.count);
+                m.cur = index_of(s, midpoint(lim_up, lim_low));
+                const float ea2 = __ldg(s.elev_ang + m.cur);
+                if (fmaxf(__fsub_rn(lim_up, ea2), __fsub_rn(ea2, lim_low)) > s.acc) { cast_ie = m.cur; return true; }
+            }
+        bisect_done:
+            ob.put(m.k, midpoint(__int_as_float(m.prev), __int_as_float(m.count)));   // un-quantised midpoint (:377, :428)
+            m.prev_az = m.cur;            // seeds the chain (:429)
+        } else if (m.phase == 2) {
+            m.count++;
+            if (m.cur == top) hit = false;            // termination rule
+            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }
+            if (m.count <= 1) {                       // first upward cast missed: search downwards (:471-488)
+                m.phase = 3;
+                m.prev = min(m.prev_az + 5, top); m.cur = max(m.prev - 10, 0);
+                HZB_SM_CAST(max(m.cur - 10, 0));
+            }
+            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
+            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
+        } else if (m.phase == 3) {
+            if (m.cur == 0) hit = true;               // termination rule
+            if (!hit) { m.prev = m.cur; m.cur = max(m.cur - 10, 0); HZB_SM_CAST(max(m.cur - 10, 0)); }
+            const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
+            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
+        } else {  // phase 4: discrete sampling (:309-331)
+            if (m.cur == top) hit = false;
+            if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }
+            ob.put(m.k, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
+        }
+        // azimuth finished
+        m.k++; m.spec_ie = -1;
+        if (m.k >= s.azim_num) { m.phase = 0; return false; }
+        have_result = false;
+    }
+#undef HZB_SM_CAST
+}
+
+}  // namespace hzb

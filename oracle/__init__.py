@@ -26,9 +26,11 @@ _i32p = ctypes.POINTER(ctypes.c_int32)
 
 def build(force=False):
     """Compile the oracle (gcc) if the shared object is missing or stale."""
-    src = os.path.join(_HERE, "hzb_oracle.cpp")
+    srcs = [os.path.join(_HERE, "hzb_oracle.cpp"),
+            # the product's host/device search state machine is compiled in as a unit under test
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_search.cuh")]
     if (force or not os.path.exists(_SO)
-            or os.path.getmtime(_SO) < os.path.getmtime(src)):
+            or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs if os.path.exists(f))):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhzb_oracle.so"],
                               stdout=subprocess.DEVNULL)
     return _SO
@@ -309,3 +311,22 @@ def rotation_matrix_glob2loc(vec_north_enu, vec_norm_enu):
     o = np.empty((ny + 2, nx + 2, 3, 3), np.float32)
     _check(lib().orc_rotation_matrix_glob2loc(_p(a, _f32p), _p(b, _f32p), ny, nx, _p(o, _f32p)))
     return o
+
+
+def selftest_state_machine(vert_grid, dem_dim_0, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, azim_num,
+                           dist_search, hori_acc=0.25, elev_ang_low_lim=-15.0, ray_org_elev=0.01,
+                           ray_algorithm="guess_constant", refuse_every=0):
+    """Drive the PRODUCT's search state machine (csrc/hzb_search.cuh, host build) with the oracle's casts.
+    Returns (cells that differ from the oracle's algorithm, reference casts, state-machine casts,
+    companion results consumed)."""
+    L = lib()
+    L.orc_selftest_state_machine.restype = ctypes.c_longlong
+    a, b, c = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_longlong(0)
+    vg = np.ascontiguousarray(vert_grid, dtype=np.float32)
+    bad = L.orc_selftest_state_machine(_p(vg, _f32p), int(dem_dim_0), int(dem_dim_1), int(offset_0), int(offset_1),
+                                       int(dim_in_0), int(dim_in_1), int(azim_num), ctypes.c_float(dist_search),
+                                       ctypes.c_float(hori_acc), ctypes.c_float(elev_ang_low_lim),
+                                       ctypes.c_float(ray_org_elev), ray_algorithm.encode(), int(refuse_every),
+                                       ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+    return int(bad), a.value, b.value, c.value
+

@@ -56,6 +56,9 @@
 #include <vector>
 #include <omp.h>
 
+// the PRODUCT's search state machine, compiled for the host (unit under test of orc_selftest_state_machine)
+#include "../horayzon_b200/csrc/hzb_search.cuh"
+
 namespace {
 
 // ---------------------------------------------------------------------------
@@ -1124,3 +1127,72 @@ long long orc_selftest_folded_slab(unsigned long long seed, long long n, long lo
     return bad;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// The product's search state machine (horayzon_b200/csrc/hzb_search.cuh, the source the CUDA
+// kernels compile) driven on the CPU: every cast it asks for -- and every packet companion --
+// is answered by this oracle's any-hit query.  Per cell the outputs must equal the oracle's
+// algo_* bit for bit and the cast count must be the reference's.  refuse_every > 0 refuses
+// every n-th companion (the kernel does that when the two rays cannot share plane selectors).
+// Returns the number of cells that differ.  Test infrastructure only.
+// ---------------------------------------------------------------------------
+namespace {
+struct HostOut { float* out; inline void put(int k, float v) { out[k] = v; } };
+
+template <int ALG>
+static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_grid, int W, int off0, int off1, int ny, int nx,
+                          float lift, int refuse_every, long long* casts_ref, long long* casts_sm, long long* companions_used) {
+    long long bad = 0, cr = 0, cs = 0, cu = 0;
+    hzb::SearchTables st;
+    st.azim_sin = T.as.data(); st.azim_cos = T.ac.data(); st.elev_ang = T.ea.data(); st.elev_sin = T.es.data();
+    st.elev_cos = T.ec.data(); st.azim_num = T.azim_num; st.elev_num = T.elev_num;
+    st.acc = T.acc; st.low = T.low; st.up = T.up; st.dist = T.dist; st.step = (double)T.acc / 5.0;
+#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : bad, cr, cs, cu)
+    for (int i = 0; i < ny; ++i)
+        for (int j = 0; j < nx; ++j) {
+            const float* vp = vert_grid + 3 * ((size_t)(i + off0) * W + (j + off1));
+            const Frame fr = make_frame({vp[0], vp[1], vp[2]}, {0.f, 0.f, 1.f}, {0.f, 1.f, 0.f}, lift);
+            std::vector<float> ref(T.azim_num), got(T.azim_num, -999.f);
+            Caster<false> cast{sc, T, fr, false};
+            if (ALG == 0) algo_discrete(cast, T, ref.data(), nullptr);
+            else if (ALG == 1) algo_binary(cast, T, ref.data(), nullptr);
+            else algo_guess(cast, T, ref.data());
+            // the product's state machine
+            hzb::LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0; m.spec_ie = -1; m.spec_hit = false;
+            HostOut ob{got.data()};
+            bool have_result = false, hit1 = false, hit2 = false;
+            unsigned long long rays = 0, used = 0, asked = 0;
+            while (true) {
+                int ie = 0, lo = -1; unsigned int extra = 0;
+                m.spec_hit = hit2;
+                const bool need = hzb::sm_advance<ALG, true, HostOut>(st, m, have_result, hit1, ob, ie, lo, extra);
+                rays += extra + (need ? 1u : 0u); used += extra;
+                if (!need) break;
+                hit1 = sc.occluded(fr.org, ray_dir(fr, T, ie, m.k), T.dist, false);
+                bool two = lo >= 0;
+                if (two && refuse_every > 0 && (++asked % (unsigned)refuse_every) == 0) two = false;
+                hit2 = two ? sc.occluded(fr.org, ray_dir(fr, T, lo, m.k), T.dist, false) : hit1;
+                m.spec_ie = two ? lo : -1;
+                have_result = true;
+            }
+            const bool same = memcmp(ref.data(), got.data(), sizeof(float) * T.azim_num) == 0 && rays == cast.rays;
+            bad += same ? 0 : 1; cr += (long long)cast.rays; cs += (long long)rays; cu += (long long)used;
+        }
+    *casts_ref = cr; *casts_sm = cs; *companions_used = cu;
+    return bad;
+}
+}  // namespace
+
+extern "C" long long orc_selftest_state_machine(const float* vert_grid, int dem_dim_0, int dem_dim_1, int offset_0, int offset_1,
+                                                int dim_in_0, int dim_in_1, int azim_num, float dist_search, float hori_acc,
+                                                float elev_ang_low_lim, float ray_org_elev, const char* ray_algorithm,
+                                                int refuse_every, long long* casts_ref, long long* casts_sm,
+                                                long long* companions_used) {
+    const int alg = algo_id(ray_algorithm);
+    if (alg < 0) return -1;
+    Scene sc; sc.add_grid(vert_grid, dem_dim_0, dem_dim_1); sc.build();
+    Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    if (alg == 0) return sm_cells<0>(sc, T, vert_grid, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, ray_org_elev, refuse_every, casts_ref, casts_sm, companions_used);
+    if (alg == 1) return sm_cells<1>(sc, T, vert_grid, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, ray_org_elev, refuse_every, casts_ref, casts_sm, companions_used);
+    return sm_cells<2>(sc, T, vert_grid, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, ray_org_elev, refuse_every, casts_ref, casts_sm, companions_used);
+}

@@ -305,3 +305,26 @@ def test_folded_bias_box_test_is_conservative():
     assert bad == 0
     assert acc.value > 300_000
 
+
+@pytest.mark.parametrize("alg", ["guess_constant", "binary_search", "discrete_sampling"])
+def test_product_state_machine_on_the_cpu(alg):
+    """The CUDA kernels' search state machine (csrc/hzb_search.cuh -- the very source the device code is built
+    from, compiled here for the host) asks for casts and packet companions; the oracle answers them.  Outputs
+    must equal the oracle's own algorithm bit for bit and the cast count must be the reference's: a companion
+    result counts only when the search would have cast it.  Also with every third companion refused (what the
+    kernel does when two rays cannot share plane selectors), and on cliffs with a high lower limit where the
+    stepping searches run into both ends of the elevation table."""
+    c = syn.make_config("cfg1", n=56)
+    base = (c["vert_grid"], 56, 56, c["offset_0"], c["offset_1"], c["ny"], c["nx"], 24, c["dist_search"])
+    for refuse in (0, 3):
+        bad, ref, got, used = oracle.selftest_state_machine(*base, ray_algorithm=alg, refuse_every=refuse)
+        assert bad == 0 and ref == got and ref > 0
+        if alg != "binary_search":
+            assert used > 0      # companions were really consumed
+    x, y, z = syn.sinusoid_dem(40, 40, 5.0, 300.0, 140.0, 5, 3)        # cliffs: slopes far beyond 60 degrees
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    for low, acc in ((-2.0, 1.0), (-40.0, 0.1)):
+        bad, ref, got, used = oracle.selftest_state_machine(vg, 40, 40, 2, 2, 36, 36, 15, 0.3, hori_acc=acc,
+                                                            elev_ang_low_lim=low, ray_algorithm=alg, refuse_every=2)
+        assert bad == 0 and ref == got
+
