@@ -1,8 +1,8 @@
 // hzb_search.cuh -- the reference's horizon search as a per-lane state machine.
 //
 // Host/device source: the CUDA kernels (horizon.cu) compile it for the device; the CPU test
-// infrastructure compiles THE SAME SOURCE for the host and drives it with the oracle's ray
-// casts (oracle/hzb_oracle.cpp, orc_selftest_state_machine), so that the search logic --
+// infrastructure compiles THE SAME SOURCE for the host and drives it with CPU ray casts
+// (tests/test_oracle_cpu.py::test_product_state_machine_on_the_cpu), so that the search logic --
 // including the packet companions and the cast accounting -- is covered by the CPU suite.
 // Nothing here touches a BVH: the state machine only says which table index to cast next.
 #pragma once
