@@ -10,58 +10,10 @@
 // optimiser can change a hit/miss decision.
 #pragma once
 #include "hzb_common.cuh"
+#include "hzb_tri.cuh"
 #include <float.h>
 
 namespace hzb {
-
-struct F3 { float x, y, z; };
-
-__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
-__device__ __forceinline__ F3 sub_rn(F3 a, F3 b) { return f3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
-__device__ __forceinline__ F3 add_rn(F3 a, F3 b) { return f3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
-// cross = (fma(ay,bz,-(az*by)), fma(az,bx,-(ax*bz)), fma(ax,by,-(ay*bx)))
-__device__ __forceinline__ F3 cross_f(F3 a, F3 b) {
-    return f3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
-              __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
-}
-// dot = fma(ax,bx, fma(ay,by, az*bz))
-__device__ __forceinline__ float dot_f(F3 a, F3 b) {
-    return __fmaf_rn(a.x, b.x, __fmaf_rn(a.y, b.y, __fmul_rn(a.z, b.z)));
-}
-
-// Pluecker edge function of edge (a -> b) style term: dot(cross(e, s), D)
-// with e, s prepared by the caller.
-
-// Depth part of the test, shared by both entry points below.
-__device__ __forceinline__ bool tri_depth(F3 v0, F3 e0, F3 e1, F3 e2, F3 D, float tfar, float& t_out) {
-    const float ab_x = __fmul_rn(e0.z, e1.y), ab_y = __fmul_rn(e0.x, e1.z), ab_z = __fmul_rn(e0.y, e1.x);
-    const float bc_x = __fmul_rn(e1.z, e2.y), bc_y = __fmul_rn(e1.x, e2.z), bc_z = __fmul_rn(e1.y, e2.x);
-    const float cab_x = __fmaf_rn(e0.y, e1.z, -ab_x), cab_y = __fmaf_rn(e0.z, e1.x, -ab_y), cab_z = __fmaf_rn(e0.x, e1.y, -ab_z);
-    const float cbc_x = __fmaf_rn(e1.y, e2.z, -bc_x), cbc_y = __fmaf_rn(e1.z, e2.x, -bc_y), cbc_z = __fmaf_rn(e1.x, e2.y, -bc_z);
-    const F3 Ng = f3(fabsf(ab_x) < fabsf(bc_x) ? cab_x : cbc_x, fabsf(ab_y) < fabsf(bc_y) ? cab_y : cbc_y,
-                     fabsf(ab_z) < fabsf(bc_z) ? cab_z : cbc_z);
-    const float dn = dot_f(Ng, D);
-    const float den = __fadd_rn(dn, dn);
-    if (den == 0.0f) return false;
-    const float tn = dot_f(v0, Ng);
-    const float t = __fdiv_rn(__fadd_rn(tn, tn), den);
-    if (!(t >= 0.0f && t <= tfar)) return false;
-    t_out = t;
-    return true;
-}
-
-__device__ __forceinline__ bool tri_hit(F3 p0, F3 p1, F3 p2, F3 O, F3 D, float tfar, float& t_out) {
-    const F3 v0 = sub_rn(p0, O), v1 = sub_rn(p1, O), v2 = sub_rn(p2, O);
-    const F3 e0 = sub_rn(v2, v0), e1 = sub_rn(v0, v1), e2 = sub_rn(v1, v2);
-    const float U = dot_f(cross_f(e0, add_rn(v2, v0)), D);
-    const float V = dot_f(cross_f(e1, add_rn(v0, v1)), D);
-    const float W = dot_f(cross_f(e2, add_rn(v1, v2)), D);
-    const float UVW = __fadd_rn(__fadd_rn(U, V), W);
-    const float eps = __fmul_rn(FLT_EPSILON, fabsf(UVW));
-    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
-    if (!((mn >= -eps) || (mx <= eps))) return false;
-    return tri_depth(v0, e0, e1, e2, D, tfar, t_out);
-}
 
 __device__ __forceinline__ F3 ld_vert(const float4* p) {
     const float4 v = __ldg(p);

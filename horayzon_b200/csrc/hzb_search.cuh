@@ -6,26 +6,7 @@
 // including the packet companions and the cast accounting -- is covered by the CPU suite.
 // Nothing here touches a BVH: the state machine only says which table index to cast next.
 #pragma once
-#include <math.h>
-#include <string.h>
-
-#ifdef __CUDACC__
-#define HZB_HD __device__ __forceinline__
-#else   // host build: the explicitly rounded intrinsics are plain IEEE operations (compile with -ffp-contract=off)
-#define HZB_HD inline
-#include <algorithm>
-namespace hzb {
-using std::max; using std::min;
-template <typename T> static inline T __ldg(const T* p) { return *p; }
-static inline float __fsub_rn(float a, float b) { return a - b; }
-static inline float __fadd_rn(float a, float b) { return a + b; }
-static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline double __ddiv_rn(double a, double b) { return a / b; }
-static inline float __double2float_rn(double a) { return (float)a; }
-static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
-static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
-}  // namespace hzb
-#endif
+#include "hzb_hd.cuh"
 
 namespace hzb {
 

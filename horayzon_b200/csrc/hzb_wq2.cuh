@@ -109,32 +109,6 @@ __device__ __forceinline__ bool wide2_child_test(const uint4 r, const Wq2Lane& L
     return hit && (r.w != WIDE_EMPTY);
 }
 
-// ---- two rays against one primitive -------------------------------------------------
-// Edge test of tri_hit() from the three edge functions of one ray.
-__device__ __forceinline__ bool edges_accept(float U, float V, float W) {
-    const float UVW = __fadd_rn(__fadd_rn(U, V), W);
-    const float eps = __fmul_rn(FLT_EPSILON, fabsf(UVW));
-    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
-    return (mn >= -eps) || (mx <= eps);
-}
-// The stable geometric normal of tri_depth() (ray independent).
-__device__ __forceinline__ F3 tri_ng(F3 e0, F3 e1, F3 e2) {
-    const float ab_x = __fmul_rn(e0.z, e1.y), ab_y = __fmul_rn(e0.x, e1.z), ab_z = __fmul_rn(e0.y, e1.x);
-    const float bc_x = __fmul_rn(e1.z, e2.y), bc_y = __fmul_rn(e1.x, e2.z), bc_z = __fmul_rn(e1.y, e2.x);
-    const float cab_x = __fmaf_rn(e0.y, e1.z, -ab_x), cab_y = __fmaf_rn(e0.z, e1.x, -ab_y), cab_z = __fmaf_rn(e0.x, e1.y, -ab_z);
-    const float cbc_x = __fmaf_rn(e1.y, e2.z, -bc_x), cbc_y = __fmaf_rn(e1.z, e2.x, -bc_y), cbc_z = __fmaf_rn(e1.x, e2.y, -bc_z);
-    return f3(fabsf(ab_x) < fabsf(bc_x) ? cab_x : cbc_x, fabsf(ab_y) < fabsf(bc_y) ? cab_y : cbc_y,
-              fabsf(ab_z) < fabsf(bc_z) ? cab_z : cbc_z);
-}
-__device__ __forceinline__ bool depth_ok(F3 v0, F3 Ng, F3 D, float tfar) {
-    const float dn = dot_f(Ng, D);
-    const float den = __fadd_rn(dn, dn);
-    if (den == 0.0f) return false;
-    const float tn = dot_f(v0, Ng);
-    const float t = __fdiv_rn(__fadd_rn(tn, tn), den);
-    return t >= 0.0f && t <= tfar;
-}
-
 // Same decisions as prim_hit<false>(.., D1, ..) and (TWO) prim_hit<false>(.., D2, ..).
 template <bool TWO>
 __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 O, F3 D1, F3 D2, float tfar, bool& h1, bool& h2) {
@@ -144,33 +118,32 @@ __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 
         const uint32_t i = prim / wq, j = prim - i * wq;
         const float4* r0 = s.vert4 + (size_t)i * s.W + j;
         const float4* r1 = r0 + s.W;
-        // triangle 1 = (p00, p01, p10) = (a, b, c); triangle 2 = (p11, p10, p01) = (d, c, b)
-        const F3 a = sub_rn(ld_vert(r0), O), b = sub_rn(ld_vert(r0 + 1), O), c = sub_rn(ld_vert(r1), O), d = sub_rn(ld_vert(r1 + 1), O);
-        const F3 e0 = sub_rn(c, a), e1 = sub_rn(a, b), e2 = sub_rn(b, c);          // triangle 1
-        const F3 f0 = sub_rn(b, d), f1 = sub_rn(d, c);                             // triangle 2 (its e2 = c - b = -e2)
-        const F3 C0 = cross_f(e0, add_rn(c, a)), C1 = cross_f(e1, add_rn(a, b)), C2 = cross_f(e2, add_rn(b, c));
-        const F3 G0 = cross_f(f0, add_rn(b, d)), G1 = cross_f(f1, add_rn(d, c));
-        const float W1 = dot_f(C2, D1);
-        const bool a11 = edges_accept(dot_f(C0, D1), dot_f(C1, D1), W1);
-        const bool a21 = edges_accept(dot_f(G0, D1), dot_f(G1, D1), -W1);   // reversed diagonal: exact negative
-        bool a12 = false, a22 = false;
         if (TWO) {
-            const float W2 = dot_f(C2, D2);
-            a12 = edges_accept(dot_f(C0, D2), dot_f(C1, D2), W2);
-            a22 = edges_accept(dot_f(G0, D2), dot_f(G1, D2), -W2);
-        }
-        // depth tests (rare): one (triangle, ray) combination per round, shared code
-        unsigned int acc = (a11 ? 1u : 0u) | (a12 ? 2u : 0u) | (a21 ? 4u : 0u) | (a22 ? 8u : 0u);
-        while (acc) {
-            const bool second = (acc & 3u) == 0u;                     // triangle 2 once triangle 1 is done
-            const unsigned int pair = second ? (acc >> 2) : (acc & 3u);
-            const F3 g0 = second ? f0 : e0, g1 = second ? f1 : e1;
-            const F3 g2 = second ? f3(-e2.x, -e2.y, -e2.z) : e2;
-            const F3 v0 = second ? d : a;
-            const F3 Ng = tri_ng(g0, g1, g2);
-            if ((pair & 1u) && !h1) h1 = depth_ok(v0, Ng, D1, tfar);
-            if ((pair & 2u) && !h2) h2 = depth_ok(v0, Ng, D2, tfar);
-            acc &= second ? 0u : 0xCu;
+            quad_hit2<true>(ld_vert(r0), ld_vert(r0 + 1), ld_vert(r1), ld_vert(r1 + 1), O, D1, D2, tfar, h1, h2);   // hzb_tri.cuh
+        } else {
+            // single-ray form (shadow kernels), kept textually as validated on the GPU; to be folded into
+            // quad_hit2<false> once a GPU run can confirm the regenerated code
+            const F3 a = sub_rn(ld_vert(r0), O), b = sub_rn(ld_vert(r0 + 1), O), c = sub_rn(ld_vert(r1), O), d = sub_rn(ld_vert(r1 + 1), O);
+            const F3 e0 = sub_rn(c, a), e1 = sub_rn(a, b), e2 = sub_rn(b, c);
+            const F3 f0 = sub_rn(b, d), f1 = sub_rn(d, c);
+            const F3 C0 = cross_f(e0, add_rn(c, a)), C1 = cross_f(e1, add_rn(a, b)), C2 = cross_f(e2, add_rn(b, c));
+            const F3 G0 = cross_f(f0, add_rn(b, d)), G1 = cross_f(f1, add_rn(d, c));
+            const float W1 = dot_f(C2, D1);
+            const bool a11 = edges_accept(dot_f(C0, D1), dot_f(C1, D1), W1);
+            const bool a21 = edges_accept(dot_f(G0, D1), dot_f(G1, D1), -W1);
+            bool a12 = false, a22 = false;
+            unsigned int acc = (a11 ? 1u : 0u) | (a12 ? 2u : 0u) | (a21 ? 4u : 0u) | (a22 ? 8u : 0u);
+            while (acc) {
+                const bool second = (acc & 3u) == 0u;
+                const unsigned int pair = second ? (acc >> 2) : (acc & 3u);
+                const F3 g0 = second ? f0 : e0, g1 = second ? f1 : e1;
+                const F3 g2 = second ? f3(-e2.x, -e2.y, -e2.z) : e2;
+                const F3 v0 = second ? d : a;
+                const F3 Ng = tri_ng(g0, g1, g2);
+                if ((pair & 1u) && !h1) h1 = depth_ok(v0, Ng, D1, tfar);
+                if ((pair & 2u) && !h2) h2 = depth_ok(v0, Ng, D2, tfar);
+                acc &= second ? 0u : 0xCu;
+            }
         }
     } else {
         const float4* q = s.tin4 + 3 * (size_t)(prim - s.num_quads);

@@ -27,8 +27,10 @@ _i32p = ctypes.POINTER(ctypes.c_int32)
 def build(force=False):
     """Compile the oracle (gcc) if the shared object is missing or stale."""
     srcs = [os.path.join(_HERE, "hzb_oracle.cpp"),
-            # the product's host/device search state machine is compiled in as a unit under test
-            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_search.cuh")]
+            # the product's host/device sources (search state machine, triangle tests) are compiled in as units under test
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_search.cuh"),
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_tri.cuh"),
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_hd.cuh")]
     if (force or not os.path.exists(_SO)
             or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs if os.path.exists(f))):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhzb_oracle.so"],

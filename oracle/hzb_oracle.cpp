@@ -58,6 +58,7 @@
 
 // the PRODUCT's search state machine, compiled for the host (unit under test of orc_selftest_state_machine)
 #include "../horayzon_b200/csrc/hzb_search.cuh"
+#include "../horayzon_b200/csrc/hzb_tri.cuh"
 
 namespace {
 
@@ -976,10 +977,10 @@ int orc_rotation_matrix_glob2loc(const float* north, const float* norm, int ny, 
 }  // extern "C"
 
 // ---------------------------------------------------------------------------
-// Self-tests of two arithmetic claims the CUDA product relies on.
-// They restate the PRODUCT's formulation on the CPU (same operation order, fmaf where the
-// kernel uses __fmaf_rn) and compare it with the specification above on random and
-// adversarial inputs.  Test infrastructure only.
+// Self-tests of arithmetic the CUDA product relies on.  The quad / triangle
+// tests are the PRODUCT's own source (horayzon_b200/csrc/hzb_tri.cuh, host build of the file the
+// kernels compile), compared with the specification above on random and adversarial inputs; the box
+// test is restated (it lives inside the traversal step).  Test infrastructure only.
 // ---------------------------------------------------------------------------
 namespace {
 struct Rng {   // splitmix64
@@ -989,47 +990,13 @@ struct Rng {   // splitmix64
     double uni() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
     float range(float a, float b) { return (float)(a + (b - a) * uni()); }
 };
-static inline bool edges_accept(float U, float V, float W) {
-    const float UVW = (U + V) + W;
-    const float eps = std::numeric_limits<float>::epsilon() * fabsf(UVW);
-    const float mn = fminf(fminf(U, V), W), mx = fmaxf(fmaxf(U, V), W);
-    return (mn >= -eps) || (mx <= eps);
-}
-static inline V3 tri_ng(V3 e0, V3 e1, V3 e2) {
-    const float ab_x = e0.z * e1.y, ab_y = e0.x * e1.z, ab_z = e0.y * e1.x;
-    const float bc_x = e1.z * e2.y, bc_y = e1.x * e2.z, bc_z = e1.y * e2.x;
-    const V3 cab = {fmaf(e0.y, e1.z, -ab_x), fmaf(e0.z, e1.x, -ab_y), fmaf(e0.x, e1.y, -ab_z)};
-    const V3 cbc = {fmaf(e1.y, e2.z, -bc_x), fmaf(e1.z, e2.x, -bc_y), fmaf(e1.x, e2.y, -bc_z)};
-    return {fabsf(ab_x) < fabsf(bc_x) ? cab.x : cbc.x, fabsf(ab_y) < fabsf(bc_y) ? cab.y : cbc.y,
-            fabsf(ab_z) < fabsf(bc_z) ? cab.z : cbc.z};
-}
-static inline bool depth_ok(V3 v0, V3 Ng, V3 D, float tfar) {
-    const float dn = dot_f(Ng, D), den = dn + dn;
-    if (den == 0.0f) return false;
-    const float tn = dot_f(v0, Ng), t = (tn + tn) / den;
-    return t >= 0.0f && t <= tfar;
-}
-// The product's quad test (hzb_wq2.cuh prim_hit2, one ray): five edge functions, the diagonal's
-// function of the second triangle is the NEGATIVE of the first triangle's.
-static bool quad_hit_shared(V3 p00, V3 p01, V3 p10, V3 p11, V3 O, V3 D, float tfar) {
-    const V3 a = sub3(p00, O), b = sub3(p01, O), c = sub3(p10, O), d = sub3(p11, O);
-    const V3 e0 = sub3(c, a), e1 = sub3(a, b), e2 = sub3(b, c);
-    const V3 f0 = sub3(b, d), f1 = sub3(d, c);
-    const V3 C0 = cross_f(e0, add3(c, a)), C1 = cross_f(e1, add3(a, b)), C2 = cross_f(e2, add3(b, c));
-    const V3 G0 = cross_f(f0, add3(b, d)), G1 = cross_f(f1, add3(d, c));
-    const float W1 = dot_f(C2, D);
-    const bool a1 = edges_accept(dot_f(C0, D), dot_f(C1, D), W1);
-    const bool a2 = edges_accept(dot_f(G0, D), dot_f(G1, D), -W1);
-    bool h = false;
-    if (a1) h = depth_ok(a, tri_ng(e0, e1, e2), D, tfar);
-    if (a2 && !h) { const V3 f2 = {-e2.x, -e2.y, -e2.z}; h = depth_ok(d, tri_ng(f0, f1, f2), D, tfar); }
-    return h;
-}
+static inline hzb::F3 to_f3(V3 v) { return hzb::f3(v.x, v.y, v.z); }
 }  // namespace
 
 extern "C" {
 // Random + adversarial (rays through vertices, edge midpoints and points on the diagonal) quads:
-// number of cases where the shared-diagonal formulation differs from tri_hit(T1) || tri_hit(T2).
+// number of cases where the product's quad_hit2<true> (five edge functions, two rays) or the product's
+// tri_hit differ from this file's tri_hit(T1) || tri_hit(T2) for either ray.
 long long orc_selftest_shared_diagonal(unsigned long long seed, long long n, long long* hits_out) {
     Rng R{seed};
     long long bad = 0, hits = 0;
@@ -1053,11 +1020,22 @@ long long orc_selftest_shared_diagonal(unsigned long long seed, long long n, lon
         if (!(len > 0.f)) continue;
         D = {D.x / len, D.y / len, D.z / len};
         const float tfar = (it % 7 == 0) ? len * R.range(0.5f, 1.5f) : 1e9f;
-        float t;
+        float t, tp;
         const Tri T1{p00, p01, p10}, T2{p11, p10, p01};
-        const bool ref = tri_hit(T1, O, D, tfar, &t) || tri_hit(T2, O, D, tfar, &t);
-        const bool got = quad_hit_shared(p00, p01, p10, p11, O, D, tfar);
-        hits += ref; bad += (ref != got);
+        // second ray of the packet: the same ray tilted by up to +-0.5 degree (like the search's companions)
+        const float tilt = R.range(-0.0087f, 0.0087f);
+        V3 D2 = {D.x, D.y, D.z + tilt};
+        const float l2 = sqrtf(D2.x * D2.x + D2.y * D2.y + D2.z * D2.z);
+        D2 = {D2.x / l2, D2.y / l2, D2.z / l2};
+        const bool r1a = tri_hit(T1, O, D, tfar, &t), r1b = tri_hit(T2, O, D, tfar, &t);
+        const bool ref1 = r1a || r1b;
+        const bool ref2 = tri_hit(T1, O, D2, tfar, &t) || tri_hit(T2, O, D2, tfar, &t);
+        bool g1 = false, g2 = false;
+        hzb::quad_hit2<true>(to_f3(p00), to_f3(p01), to_f3(p10), to_f3(p11), to_f3(O), to_f3(D), to_f3(D2), tfar, g1, g2);
+        // the product's single-triangle test must agree as well (decision and distance)
+        const bool p1a = hzb::tri_hit(to_f3(p00), to_f3(p01), to_f3(p10), to_f3(O), to_f3(D), tfar, tp);
+        float tref; const bool chk = tri_hit(T1, O, D, tfar, &tref);
+        hits += ref1; bad += (ref1 != g1) + (ref2 != g2) + (p1a != r1a) + (chk && p1a && tp != tref);
     }
     if (hits_out) *hits_out = hits;
     return bad;

@@ -280,10 +280,12 @@ def test_transform_matches_reference_golden():
 
 
 def test_shared_diagonal_quad_test_equals_two_triangle_tests():
-    """The production quad test evaluates five Pluecker edge functions per quad: the diagonal's function of
-    the second triangle is taken as the NEGATIVE of the first triangle's (exact in round-to-nearest).  On two
-    million random and adversarial cases (rays through vertices, along the diagonal, on outer edges, short
-    tfar) it must make the decisions of tri_hit(T1) || tri_hit(T2)."""
+    """The production quad test (csrc/hzb_tri.cuh -- the source the kernels compile, built here for the host)
+    evaluates five Pluecker edge functions per quad for two rays: the diagonal's function of the second
+    triangle is taken as the NEGATIVE of the first triangle's (exact in round-to-nearest).  On two million
+    random and adversarial cases (rays through vertices, along the diagonal, on outer edges, short tfar, a
+    companion ray tilted by up to half a degree) it must make the oracle's decisions tri_hit(T1) || tri_hit(T2)
+    for both rays, and the product's tri_hit must equal the oracle's in decision and distance."""
     import ctypes
     L = oracle.lib()
     L.orc_selftest_shared_diagonal.restype = ctypes.c_longlong
