@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 #include "../../include/horayzon_b200.h"
+#include "hzb_hd.cuh"
 
 namespace hzb {
 
@@ -46,8 +47,7 @@ static_assert(sizeof(Bvh2Node) == 64, "Bvh2Node must be 64 bytes");
 struct __align__(16) WideChild { uint32_t qx, qy, qz, ref; };
 struct __align__(64) Bvh4Node { WideChild c[4]; };
 static_assert(sizeof(Bvh4Node) == 64, "Bvh4Node must be 64 bytes");
-constexpr uint32_t WIDE_EMPTY = 0xFFFFFFFFu;
-constexpr uint32_t WIDE_LEAF = 0x80000000u;
+// WIDE_EMPTY / WIDE_LEAF: hzb_hd.cuh
 
 // Device view of a scene: DEM vertices, optional TIN, BVH.
 // Primitive p < num_quads is grid quad (i = p / (W-1), j = p % (W-1)), split

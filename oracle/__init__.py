@@ -30,6 +30,7 @@ def build(force=False):
             # the product's host/device sources (search state machine, triangle tests) are compiled in as units under test
             os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_search.cuh"),
             os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_tri.cuh"),
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_box.cuh"),
             os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_hd.cuh")]
     if (force or not os.path.exists(_SO)
             or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs if os.path.exists(f))):

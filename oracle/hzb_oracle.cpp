@@ -59,6 +59,7 @@
 // the PRODUCT's search state machine, compiled for the host (unit under test of orc_selftest_state_machine)
 #include "../horayzon_b200/csrc/hzb_search.cuh"
 #include "../horayzon_b200/csrc/hzb_tri.cuh"
+#include "../horayzon_b200/csrc/hzb_box.cuh"
 
 namespace {
 
@@ -1041,65 +1042,64 @@ long long orc_selftest_shared_diagonal(unsigned long long seed, long long n, lon
     return bad;
 }
 
-// Conservativeness of the packet step's box test: quantised planes widened by one quantum,
-// t = fmaf(qb, A, B') with qb = 2^23 + q, B' = fmaf(-2^23, A, B), approximate reciprocal (perturbed
-// by up to 2 ulp here), no slack on tmax.  Returns the number of rays that meet the UNPADDED box
-// in exact (double) arithmetic within [0, tfar] but are rejected by the float test.
-long long orc_selftest_folded_slab(unsigned long long seed, long long n, long long* accepted_out) {
+// Conservativeness of the packet step's box test -- the PRODUCT's own source (hzb_box.cuh, host build:
+// wq2_set_rays + wide2_child_test<true>, i.e. PRMT decode of the 16-bit planes, bias folded into the ray
+// constant, clamped reciprocal, shared x/y selectors, no slack on tmax) on child words quantised like
+// bvh_wide.cu's quant_pair (outward rounding plus one quantum; pad_quanta = 0 shows what happens without it).
+// Returns the number of packets of which a ray meets the UNPADDED box in exact (double) arithmetic within
+// [0, tfar] while the product's test rejects the box.
+long long orc_selftest_folded_slab(unsigned long long seed, long long n, int pad_quanta, long long* accepted_out) {
     Rng R{seed};
     long long bad = 0, acc = 0;
-    const float M = 8388608.0f;
     for (long long it = 0; it < n; ++it) {
         const double extent = (it & 1) ? 1.1e5 : 1.2e4;
-        const float qstep = (float)(extent / 65529.0), qorg[3] = {R.range(-3e6f, 3e6f), R.range(-3e6f, 3e6f), R.range(-1e3f, 1e3f)};
-        // a box on the grid (its true planes anywhere inside the outward-rounded cells)
+        const float qstep[3] = {(float)(extent / 65529.0), (float)(extent / 65529.0), (float)(extent / 65529.0 / ((it & 4) ? 40.0 : 1.0))};
+        const float qorg[3] = {R.range(-3e6f, 3e6f), R.range(-3e6f, 3e6f), R.range(-1e3f, 1e3f)};
         double lo[3], hi[3]; uint32_t ql[3], qh[3];
         for (int a = 0; a < 3; ++a) {
             const double l = 3.0 + R.uni() * 65000.0, w = (R.uni() < 0.3 ? 0.0 : R.uni() * ((it & 2) ? 40.0 : 4000.0));
             const double h = std::min(l + w, 65530.0);
-            lo[a] = (double)qorg[a] + l * (double)qstep; hi[a] = (double)qorg[a] + h * (double)qstep;
-            ql[a] = (uint32_t)floor(l) - 1u; qh[a] = (uint32_t)ceil(h) + 1u;       // bvh_wide.cu quant_pair
+            lo[a] = (double)qorg[a] + l * (double)qstep[a]; hi[a] = (double)qorg[a] + h * (double)qstep[a];
+            ql[a] = (uint32_t)floor(l) - (uint32_t)pad_quanta; qh[a] = (uint32_t)ceil(h) + (uint32_t)pad_quanta;   // quant_pair
         }
-        // ray: origin inside the scene, aimed near the box (so that many rays graze it)
+        hzb::uint4 child;
+        child.x = ql[0] | (qh[0] << 16); child.y = ql[1] | (qh[1] << 16); child.z = ql[2] | (qh[2] << 16); child.w = 7u;
+        // packet: origin inside the scene, ray 1 aimed near the box, ray 2 = ray 1 tilted by up to half a degree
         double O[3], T[3], D[3];
         for (int a = 0; a < 3; ++a) {
-            O[a] = (double)(float)((double)qorg[a] + R.uni() * 65529.0 * (double)qstep);
-            const double pad = (hi[a] - lo[a]) * 0.02 + (double)qstep * 0.5;
+            O[a] = (double)(float)((double)qorg[a] + R.uni() * 65529.0 * (double)qstep[a]);
+            const double pad = (hi[a] - lo[a]) * 0.02 + (double)qstep[a] * 0.5;
             T[a] = lo[a] - pad + R.uni() * (hi[a] - lo[a] + 2 * pad);
             D[a] = T[a] - O[a];
         }
         const double len = sqrt(D[0] * D[0] + D[1] * D[1] + D[2] * D[2]);
         if (!(len > 0.0)) continue;
-        float Df[3];
-        for (int a = 0; a < 3; ++a) { Df[a] = (float)(D[a] / len); if ((R.next() & 15) == 0) Df[a] = 0.0f; }
+        float D1[3], D2[3];
+        for (int a = 0; a < 3; ++a) { D1[a] = (float)(D[a] / len); if ((R.next() & 15) == 0) D1[a] = 0.0f; }
+        D2[0] = D1[0]; D2[1] = D1[1]; D2[2] = D1[2] + R.range(-0.0087f, 0.0087f);
+        { const float l2 = sqrtf(D2[0] * D2[0] + D2[1] * D2[1] + D2[2] * D2[2]); if (l2 > 0.f) { D2[0] /= l2; D2[1] /= l2; D2[2] /= l2; } }
         const float tfar = (it % 5 == 0) ? (float)(len * (0.5 + R.uni())) : 5.0e4f;
-        // exact test of the float ray against the unpadded box
-        double t0 = 0.0, t1 = (double)tfar; bool ok = true;
-        for (int a = 0; a < 3 && ok; ++a) {
-            const double d = (double)Df[a];
-            if (d == 0.0) { if (O[a] < lo[a] || O[a] > hi[a]) ok = false; continue; }
-            double ta = (lo[a] - O[a]) / d, tb = (hi[a] - O[a]) / d;
-            if (ta > tb) std::swap(ta, tb);
-            t0 = std::max(t0, ta); t1 = std::min(t1, tb);
-        }
-        ok = ok && t0 <= t1;
-        if (!ok) continue;
+        auto exact = [&](const float* Df) {
+            double t0 = 0.0, t1 = (double)tfar;
+            for (int a = 0; a < 3; ++a) {
+                const double d = (double)Df[a];
+                if (d == 0.0) { if (O[a] < lo[a] || O[a] > hi[a]) return false; continue; }
+                double ta = (lo[a] - O[a]) / d, tb = (hi[a] - O[a]) / d;
+                if (ta > tb) std::swap(ta, tb);
+                t0 = std::max(t0, ta); t1 = std::min(t1, tb);
+            }
+            return t0 <= t1;
+        };
+        const hzb::F3 Of = hzb::f3((float)O[0], (float)O[1], (float)O[2]), d1 = hzb::f3(D1[0], D1[1], D1[2]);
+        hzb::F3 d2 = hzb::f3(D2[0], D2[1], D2[2]);
+        hzb::Wq2Lane L;
+        const bool two = hzb::wq2_set_rays(L, qorg, qstep, Of, d1, d2);     // ray 2 becomes ray 1 when selectors cannot be shared
+        const float D2eff[3] = {d2.x, d2.y, d2.z};
+        const bool ex = exact(D1) || exact(two ? D2 : D2eff);
+        if (!ex) continue;
         ++acc;
-        // the product's float test
-        float tmin = 0.0f, tmax = tfar;
-        for (int a = 0; a < 3; ++a) {
-            float d = Df[a];
-            if (fabsf(d) < 1e-18f) d = copysignf(1e-18f, d);
-            float inv = 1.0f / d;
-            const int ulps = (int)(R.next() % 5) - 2;                             // approximate reciprocal: +-2 ulp
-            for (int k = 0; k < abs(ulps); ++k) inv = nextafterf(inv, ulps > 0 ? INFINITY : -INFINITY);
-            const float A = qstep * inv;
-            const float B = fmaf(-M, A, (qorg[a] - (float)O[a]) * inv);
-            const float qa = M + (float)ql[a], qb = M + (float)qh[a];
-            const float ta = fmaf(qa, A, B), tb = fmaf(qb, A, B);
-            tmin = fmaxf(tmin, fminf(ta, tb)); tmax = fminf(tmax, fmaxf(ta, tb));
-        }
-        if (!(tmin <= tmax)) ++bad;
+        float key;
+        if (!hzb::wide2_child_test<true>(child, L, tfar, key)) ++bad;
     }
     if (accepted_out) *accepted_out = acc;
     return bad;

@@ -296,16 +296,20 @@ def test_shared_diagonal_quad_test_equals_two_triangle_tests():
 
 
 def test_folded_bias_box_test_is_conservative():
-    """The packet step's box test (2^23 decode bias folded into the ray constant, one extra quantum on every
-    plane, approximate reciprocal, no slack on tmax) must never reject a box that the ray meets in exact
-    arithmetic -- also for flat boxes, axis-parallel rays and coordinates of 3e6 m magnitude."""
+    """The packet step's box test (csrc/hzb_box.cuh -- the source the kernels compile, built here for the host:
+    PRMT decode of the 16-bit planes, 2^23 bias folded into the ray constant, clamped reciprocal, shared x/y
+    selectors, no slack on tmax) must never reject a box that a ray of the packet meets in exact arithmetic --
+    also for flat boxes, axis-parallel rays, anisotropic grids and coordinates of 3e6 m magnitude.  It relies on
+    the extra quantum bvh_wide.cu adds to every plane: without it the same test does reject such boxes."""
     import ctypes
     L = oracle.lib()
     L.orc_selftest_folded_slab.restype = ctypes.c_longlong
     acc = ctypes.c_longlong(0)
-    bad = L.orc_selftest_folded_slab(ctypes.c_ulonglong(777), ctypes.c_longlong(3_000_000), ctypes.byref(acc))
+    bad = L.orc_selftest_folded_slab(ctypes.c_ulonglong(777), ctypes.c_longlong(3_000_000), 1, ctypes.byref(acc))
     assert bad == 0
     assert acc.value > 300_000
+    bad0 = L.orc_selftest_folded_slab(ctypes.c_ulonglong(777), ctypes.c_longlong(3_000_000), 0, ctypes.byref(acc))
+    assert bad0 > 0          # the test is sharp: the quantum is what makes the folded form conservative
 
 
 @pytest.mark.parametrize("alg", ["guess_constant", "binary_search", "discrete_sampling"])
