@@ -135,6 +135,22 @@ int hzb_device_count(void) {
     return n;
 }
 int hzb_get_stats(hzb_stats* out) { if (!out) return 1; *out = g_stats; return 0; }
+// Pure host code (no device needed): the tables the kernels use, for inspection and for the CPU tests.
+int hzb_horizon_tables(int azim_num, float dist_search, float hori_acc, float elev_ang_low_lim, int cap, float* elev_ang,
+                       float* elev_sin, float* elev_cos, float* azim_sin, float* azim_cos) {
+    if (azim_num < 1 || !(hori_acc > 0.f)) { set_error("invalid table parameters"); return -1; }
+    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    if (elev_ang && elev_sin && elev_cos && cap >= T.elev_num) {
+        memcpy(elev_ang, T.elev_ang.data(), sizeof(float) * (size_t)T.elev_num);
+        memcpy(elev_sin, T.elev_sin.data(), sizeof(float) * (size_t)T.elev_num);
+        memcpy(elev_cos, T.elev_cos.data(), sizeof(float) * (size_t)T.elev_num);
+    }
+    if (azim_sin && azim_cos) {
+        memcpy(azim_sin, T.azim_sin.data(), sizeof(float) * (size_t)azim_num);
+        memcpy(azim_cos, T.azim_cos.data(), sizeof(float) * (size_t)azim_num);
+    }
+    return T.elev_num;
+}
 void* hzb_host_alloc(size_t bytes) { if (require_device()) return nullptr; return host_block_alloc(bytes); }
 void hzb_host_free(void* p) { host_block_free(p); }
 

@@ -56,6 +56,13 @@ typedef struct hzb_stats {
 } hzb_stats;
 int hzb_get_stats(hzb_stats* out);
 
+/* Additive, pure host code (works without a device): the trig tables of one call, built exactly like
+ * horizon_comp.cpp:711-731 (azimuth sin/cos; elevation angle/sin/cos anchored at 89.98 degree, step
+ * hori_acc/5).  Returns elev_num (or -1); the elevation arrays are filled when cap >= elev_num, the
+ * azimuth arrays when non-NULL.  The table entries are the alphabet of the horizon output. */
+int hzb_horizon_tables(int azim_num, float dist_search, float hori_acc, float elev_ang_low_lim, int cap,
+                       float* elev_ang, float* elev_sin, float* elev_cos, float* azim_sin, float* azim_cos);
+
 /* Additive: pooled page-locked host blocks for large arrays the WRAPPER allocates and returns
  * (the reference's wrapper allocates its outputs with np.empty, horizon.pyx:170-173).  Host-tier
  * calls recognise page-locked buffers and move them by plain DMA instead of staging.  NULL when

@@ -211,3 +211,24 @@ def test_signature_parameter_order():
     c = syn.make_config("cfg1", n=48)
     with pytest.raises(ValueError, match="limit of hori_acc"):
         hb.horizon.horizon_gridded(c["vert_grid"], 48, 48, c["vec_norm"], c["vec_north"], 16, 16, 5.0, 8, 11.0)
+
+
+def test_product_tables_equal_the_oracle_tables():
+    """The elevation / azimuth tables are the alphabet of the horizon output (horizon_comp.cpp:711-731): the
+    product's host-side builder (hzb_horizon_tables, no device needed) must give the oracle's bits, for the
+    defaults and for odd parameters."""
+    import ctypes
+    import oracle
+    L = resident.lib()
+    f32p = ctypes.POINTER(ctypes.c_float)
+    L.hzb_horizon_tables.argtypes = [ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+                                     f32p, f32p, f32p, f32p, f32p]
+    for azim_num, dist, acc, low in ((360, 50.0, 0.25, -15.0), (37, 8.0, 0.1, -40.0), (1, 1.0, 4.0, -2.0), (720, 12.0, 0.15, -25.0)):
+        want = oracle.tables(azim_num, dist, acc, low)
+        n = L.hzb_horizon_tables(azim_num, dist, acc, low, 0, None, None, None, None, None)
+        assert n == len(want["elev_ang"])
+        bufs = [np.empty(n, np.float32) for _ in range(3)] + [np.empty(azim_num, np.float32) for _ in range(2)]
+        assert L.hzb_horizon_tables(azim_num, dist, acc, low, n, *[b.ctypes.data_as(f32p) for b in bufs]) == n
+        for got, key in zip(bufs, ("elev_ang", "elev_sin", "elev_cos", "azim_sin", "azim_cos")):
+            assert np.array_equal(got, want[key]), (key, azim_num, acc)
+
