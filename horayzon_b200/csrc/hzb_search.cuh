@@ -7,6 +7,7 @@
 // Nothing here touches a BVH: the state machine only says which table index to cast next.
 #pragma once
 #include "hzb_hd.cuh"
+#include "hzb_tri.cuh"
 
 namespace hzb {
 
@@ -16,6 +17,33 @@ struct SearchTables {   // trig tables and limits of one call (horizon_comp.cpp:
     int azim_num, elev_num;
     float acc, low, up, dist; double step;
 };
+
+struct Frame {  // per-cell local frame: columns east, north, norm (horizon_comp.cpp:773-779)
+    F3 org;
+    float m00, m01, m02, m10, m11, m12, m20, m21, m22;
+};
+
+HZB_HD Frame make_frame(F3 vert, F3 norm, F3 north, float lift) {
+    Frame f;
+    f.org = f3(__fadd_rn(vert.x, __fmul_rn(norm.x, lift)), __fadd_rn(vert.y, __fmul_rn(norm.y, lift)),
+               __fadd_rn(vert.z, __fmul_rn(norm.z, lift)));
+    const float ex = __fsub_rn(__fmul_rn(north.y, norm.z), __fmul_rn(north.z, norm.y));
+    const float ey = __fsub_rn(__fmul_rn(north.z, norm.x), __fmul_rn(north.x, norm.z));
+    const float ez = __fsub_rn(__fmul_rn(north.x, norm.y), __fmul_rn(north.y, norm.x));
+    f.m00 = ex; f.m01 = north.x; f.m02 = norm.x;
+    f.m10 = ey; f.m11 = north.y; f.m12 = norm.y;
+    f.m20 = ez; f.m21 = north.z; f.m22 = norm.z;
+    return f;
+}
+
+HZB_HD F3 ray_dir(const SearchTables& s, const Frame& f, int ie, int k) {
+    const float ec = __ldg(s.elev_cos + ie), es = __ldg(s.elev_sin + ie);
+    const float r0 = __fmul_rn(ec, __ldg(s.azim_sin + k)), r1 = __fmul_rn(ec, __ldg(s.azim_cos + k)), r2 = es;
+    return f3(__fadd_rn(__fadd_rn(__fmul_rn(f.m00, r0), __fmul_rn(f.m01, r1)), __fmul_rn(f.m02, r2)),
+              __fadd_rn(__fadd_rn(__fmul_rn(f.m10, r0), __fmul_rn(f.m11, r1)), __fmul_rn(f.m12, r2)),
+              __fadd_rn(__fadd_rn(__fmul_rn(f.m20, r0), __fmul_rn(f.m21, r1)), __fmul_rn(f.m22, r2)));
+}
+
 
 HZB_HD int index_of(const SearchTables& s, float elev) {  // (int)roundf((elev-low)/(acc/5.0))
     const double q = __ddiv_rn((double)__fsub_rn(elev, s.low), s.step);

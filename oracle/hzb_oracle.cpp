@@ -1129,7 +1129,16 @@ static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_gr
     for (int i = 0; i < ny; ++i)
         for (int j = 0; j < nx; ++j) {
             const float* vp = vert_grid + 3 * ((size_t)(i + off0) * W + (j + off1));
-            const Frame fr = make_frame({vp[0], vp[1], vp[2]}, {0.f, 0.f, 1.f}, {0.f, 1.f, 0.f}, lift);
+            // a slightly tilted, rotated frame per cell so that all nine matrix entries matter
+            const float tx = 0.02f * (float)((i * 7 + j * 3) % 11 - 5) / 5.f, ty = 0.015f * (float)((i * 5 + j) % 7 - 3) / 3.f;
+            const float nl = sqrtf(tx * tx + ty * ty + 1.f);
+            const V3 nrm = {tx / nl, ty / nl, 1.f / nl};
+            V3 nth = {0.05f, 1.f, 0.f};
+            { const float dp = nth.x * nrm.x + nth.y * nrm.y + nth.z * nrm.z; nth = {nth.x - dp * nrm.x, nth.y - dp * nrm.y, nth.z - dp * nrm.z};
+              const float l = sqrtf(nth.x * nth.x + nth.y * nth.y + nth.z * nth.z); nth = {nth.x / l, nth.y / l, nth.z / l}; }
+            const Frame fr = make_frame({vp[0], vp[1], vp[2]}, nrm, nth, lift);
+            const hzb::Frame pf = hzb::make_frame(hzb::f3(vp[0], vp[1], vp[2]), hzb::f3(nrm.x, nrm.y, nrm.z), hzb::f3(nth.x, nth.y, nth.z), lift);
+            long long dir_bad = 0;
             std::vector<float> ref(T.azim_num), got(T.azim_num, -999.f);
             Caster<false> cast{sc, T, fr, false};
             if (ALG == 0) algo_discrete(cast, T, ref.data(), nullptr);
@@ -1146,14 +1155,20 @@ static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_gr
                 const bool need = hzb::sm_advance<ALG, true, HostOut>(st, m, have_result, hit1, ob, ie, lo, extra);
                 rays += extra + (need ? 1u : 0u); used += extra;
                 if (!need) break;
-                hit1 = sc.occluded(fr.org, ray_dir(fr, T, ie, m.k), T.dist, false);
+                // the ray comes from the PRODUCT's frame / direction arithmetic and must carry the oracle's bits
+                const hzb::F3 pd = hzb::ray_dir(st, pf, ie, m.k);
+                const V3 od = ray_dir(fr, T, ie, m.k);
+                if (memcmp(&pd.x, &od.x, 4) || memcmp(&pd.y, &od.y, 4) || memcmp(&pd.z, &od.z, 4) ||
+                    memcmp(&pf.org.x, &fr.org.x, 4) || memcmp(&pf.org.y, &fr.org.y, 4) || memcmp(&pf.org.z, &fr.org.z, 4)) ++dir_bad;
+                hit1 = sc.occluded({pf.org.x, pf.org.y, pf.org.z}, {pd.x, pd.y, pd.z}, T.dist, false);
                 bool two = lo >= 0;
                 if (two && refuse_every > 0 && (++asked % (unsigned)refuse_every) == 0) two = false;
-                hit2 = two ? sc.occluded(fr.org, ray_dir(fr, T, lo, m.k), T.dist, false) : hit1;
+                if (two) { const hzb::F3 pl = hzb::ray_dir(st, pf, lo, m.k); hit2 = sc.occluded({pf.org.x, pf.org.y, pf.org.z}, {pl.x, pl.y, pl.z}, T.dist, false); }
+                else hit2 = hit1;
                 m.spec_ie = two ? lo : -1;
                 have_result = true;
             }
-            const bool same = memcmp(ref.data(), got.data(), sizeof(float) * T.azim_num) == 0 && rays == cast.rays;
+            const bool same = memcmp(ref.data(), got.data(), sizeof(float) * T.azim_num) == 0 && rays == cast.rays && dir_bad == 0;
             bad += same ? 0 : 1; cr += (long long)cast.rays; cs += (long long)rays; cu += (long long)used;
         }
     *casts_ref = cr; *casts_sm = cs; *companions_used = cu;

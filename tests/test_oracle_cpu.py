@@ -316,7 +316,9 @@ def test_folded_bias_box_test_is_conservative():
 def test_product_state_machine_on_the_cpu(alg):
     """The CUDA kernels' search state machine (csrc/hzb_search.cuh -- the very source the device code is built
     from, compiled here for the host) asks for casts and packet companions; the oracle answers them.  Outputs
-    must equal the oracle's own algorithm bit for bit and the cast count must be the reference's: a companion
+    must equal the oracle's own algorithm bit for bit and the cast count must be the reference's (per-cell
+    tilted frames; origins and ray directions come from the product's make_frame / ray_dir and must carry the
+    oracle's bits): a companion
     result counts only when the search would have cast it.  Also with every third companion refused (what the
     kernel does when two rays cannot share plane selectors), and on cliffs with a high lower limit where the
     stepping searches run into both ends of the elevation table."""
