@@ -97,7 +97,9 @@ cdef object _output_array(tuple shape):
     cdef _PinnedBlock blk
     cdef np.npy_intp dims[3]
     cdef np.ndarray arr
-    cdef bint big = n >= (<size_t> 64 << 20) and len(shape) == 3
+    # between 64 MB and 8 GB: smaller arrays do not matter, larger ones (the 52 GB horizon of a 6000 x 6000 x 360 run)
+    # would keep too much memory page-locked in the pool and take tens of seconds to lock
+    cdef bint big = n >= (<size_t> 64 << 20) and n <= (<size_t> 8 << 30) and len(shape) == 3
     mode = os.environ.get("HZB_PINNED_OUTPUT", "auto")
     cdef bint use_pinned = big and (mode == "1" or (mode != "0" and _big_outputs >= 1))
     if big:
