@@ -10,24 +10,34 @@ beside it, like the reference prints at horizon_comp.cpp:807-810).
 One step = one pass of the hot path over the whole workload: horizon search
 for every inner-domain cell + the SVF integral ("horizon+SVF", BASELINE.json
 configs[1]).  Default workload: cfg2 = 1201 x 1201 synthetic DEM x 360 azimuths
-(SURVEY.md 8d); `--workload cfg4p` is the north-star 6000 x 6000 x 360 line.
+(SURVEY.md 8d).
 
   value : DEM + BVH + per-cell inputs resident in HBM before the timed region
           (the reference's "Ray tracing time", horizon_comp.cpp:737-805).
-  e2e   : the same metric through the reference-shaped public API
-          (horayzon_b200.horizon.horizon_gridded + topo_param.sky_view_factor)
-          with HOST buffers: H2D, on-device BVH build, kernels and D2H inside the
-          timed region ("Total run time", :816-818).
-  N > 1 : strong scaling -- the rows of the same workload are split into N
-          contiguous blocks (the reference's own partitioning axis, :739-744),
-          one process per GPU, replicated DEM/BVH, one NCCL all-gather of the
-          horizon blocks per step inside the timed region.
+  e2e   : the same metric through the reference-shaped public API with HOST
+          buffers: H2D, on-device BVH build, kernels and D2H inside the timed
+          region ("Total run time", :816-818).  Headline: the fused call
+          horizon_gridded(..., svf_vec_tilt=) -> (hori, azim, svf); the
+          reference's two-call sequence (horizon_gridded, then
+          topo_param.sky_view_factor on the returned host array) is timed beside
+          it.  Every sample and the phase breakdown are printed.
+  N > 1 : strong scaling -- the 4-row blocks of the same workload are dealt out
+          to the N GPUs in turn (block b to rank b % N: the reference's row
+          partition, horizon_comp.cpp:739-744, cost-balanced), one process per
+          GPU, replicated DEM/BVH, one NCCL all-gather of the packed shards per
+          step inside the timed region.  The gathered array is checked bit for
+          bit against a single-GPU pass outside the timed region.
+  northstar : at every N, one warm + one timed pass of the north-star workload
+          (cfg4p = 6000 x 6000 x 360 azimuths) through the same sharded path,
+          with rows checked bit for bit against the CPU oracle.
+  shadow : (N = 1) cfg3 = 3601 x 3601 shadow map, ms per sun position.
   --impl reference : the reference's CPU path.  Embree/TBB cannot be installed
           here, so this arm times the CPU oracle (reference-algorithm restatement,
-          NOT Embree; OpenMP over rows where the reference uses TBB) on a bounded
-          row sample of the same workload, on all host cores.
+          NOT Embree; OpenMP over rows where the reference uses TBB) on a
+          stratified row sample of the same workload, on all host cores.
 """
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -46,6 +56,15 @@ METRIC = "horizon rays/sec (cells x azimuths)"
 UNIT = "rays/s"
 HORI_ACC = 0.25
 ALGORITHM = "guess_constant"
+KERNEL = "k_horizon_wq6"
+
+
+def load_synthetic():
+    """horayzon_b200/synthetic.py by path: the reference arm must not load the product package (or its .so)."""
+    spec = importlib.util.spec_from_file_location("hzb_synthetic", os.path.join(ROOT, "horayzon_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def workload_label(c, K):
@@ -53,6 +72,15 @@ def workload_label(c, K):
             "dist_search %g km, inner domain %dx%d, horizon+SVF"
             % (c["name"], c["dem_dim_0"], c["dem_dim_1"], c["spacing"], K, ALGORITHM, HORI_ACC,
                c["dist_search"], c["ny"], c["nx"]))
+
+
+def config_dict(c, K, world):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": workload_label(c, K),
+            "parallelism": ("4-row blocks dealt to %d GPUs, replicated DEM+BVH, 1 NCCL all-gather/step" % world)
+            if world > 1 else "single GPU",
+            "l2": "256 MB flush write before every step; per-step output %.2f GB >> 126 MB L2"
+                  % (c["ny"] * c["nx"] * K * 4 / 1e9)}
 
 
 # --------------------------------------------------------------------- clocks
@@ -118,64 +146,258 @@ def recorded_traffic(workload):
 
 
 # ---------------------------------------------------------------- CPU oracle
-def oracle_sample(c, K, target_s=15.0, rows=None):
-    """Time the CPU oracle on a centred block of inner rows (T_rt: BVH build
-    excluded, like the reference's 'Ray tracing time')."""
-    import oracle
-    ny, nx = c["ny"], c["nx"]
+def stratified_rows(ny, n):
+    """n inner rows spread evenly over the whole domain (both rims included)."""
+    n = int(max(1, min(n, ny)))
+    return sorted(set(int(r) for r in np.round(np.linspace(0, ny - 1, n))))
 
-    def run(nrows):
-        b = (ny - nrows) // 2
-        sl = slice(b, b + nrows)
-        oracle.horizon_gridded(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["vec_norm"][sl], c["vec_north"][sl],
-                               c["offset_0"] + b, c["offset_1"], c["dist_search"], azim_num=K, hori_acc=HORI_ACC,
-                               ray_algorithm=ALGORITHM)
-        build_s, trace_s = oracle.last_timing()
-        return b, nrows * nx * K, trace_s, build_s
 
-    if rows is None:
-        _, u, t, _ = run(min(2, ny))
-        rows = int(max(2, min(ny, round(2 * target_s / max(t, 1e-3)))))
-    b, units, trace_s, build_s = run(rows)
-    return {"value": units / trace_s, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port", "rows": rows,
-            "sample": "inner rows %d..%d of %d (%d units), ray tracing %.2f s, BVH build %.2f s excluded; CPU oracle "
-                      "= reference-algorithm restatement with OpenMP over rows, NOT Embree+TBB (not installable)"
-                      % (b, b + rows, ny, units, trace_s, build_s)}
+class OracleSampler:
+    """The CPU oracle on a stratified row sample of one workload; the BVH is built once (outside the
+    timed part, like the reference's 'Ray tracing time')."""
+
+    def __init__(self, c, K):
+        import oracle
+        self.oracle, self.c, self.K = oracle, c, K
+        self.cores = os.cpu_count() or 1
+        oracle.set_num_threads(self.cores)          # torchrun exports OMP_NUM_THREADS=1
+        self.cores = oracle.num_threads()
+        t0 = time.perf_counter()
+        self.scene = oracle.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+        self.build_s = time.perf_counter() - t0
+
+    def run(self, rows):
+        c = self.c
+        h = self.scene.horizon_rows(rows, c["vec_norm"], c["vec_north"], c["offset_0"], c["offset_1"], c["dist_search"],
+                                    azim_num=self.K, hori_acc=HORI_ACC, ray_algorithm=ALGORITHM)
+        return h, self.oracle.last_timing()[1]
+
+    def size_sample(self, target_s):
+        probe = stratified_rows(self.c["ny"], 4)
+        _, t = self.run(probe)
+        n = int(max(4, round(target_s / max(t / len(probe), 1e-4))))
+        return stratified_rows(self.c["ny"], n)
+
+    def sample(self, rows):
+        _, t = self.run(rows)
+        units = len(rows) * self.c["nx"] * self.K
+        return {"value": units / t, "unit": UNIT, "cores": self.cores, "kind": "port", "rows": len(rows),
+                "sample": "%d inner rows spread evenly over all %d (%d units), ray tracing %.2f s, BVH build %.2f s excluded; "
+                          "CPU oracle = reference-algorithm restatement with OpenMP over rows, NOT Embree+TBB (not installable)"
+                          % (len(rows), self.c["ny"], units, t, self.build_s)}
+
+    def close(self):
+        self.scene.close()
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import horayzon_b200.synthetic as syn
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    syn = load_synthetic()
     c = syn.make_config(args.workload)
     K = c["azim_num"]
-    first = oracle_sample(c, K, target_s=args.ref_seconds)       # sizes the sample
-    rows = first["rows"]
-    vals = []
+    smp = OracleSampler(c, K)
+    rows = smp.size_sample(args.ref_seconds)
     for _ in range(args.warmup):
-        oracle_sample(c, K, rows=rows)
-    for _ in range(args.steps):
-        vals.append(oracle_sample(c, K, rows=rows))
-    units = rows * c["nx"] * K
+        smp.sample(rows)
+    vals = [smp.sample(rows) for _ in range(args.steps)]
+    units = len(rows) * c["nx"] * K
     v = statistics.mean(x["value"] for x in vals)
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": units / v * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_label(c, K), "sample_rows": rows},
+            "config": config_dict(c, K, world),
             "cpu_baseline": dict(vals[-1], value=v),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    smp.close()
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------ GPU arm
+class ShardedRun:
+    """One workload resident on this rank's GPU, sharded in interleaved 4-row blocks over the ranks."""
+
+    def __init__(self, hb, torch, dist, c, dev, rank, world, with_svf=True):
+        from horayzon_b200 import resident, sharding
+        self.hb, self.torch, self.dist, self.c, self.dev, self.rank, self.world = hb, torch, dist, c, dev, rank, world
+        self.resident, self.sharding = resident, sharding
+        self.K = c["azim_num"]
+        ny, nx, K = c["ny"], c["nx"], self.K
+        self.scene = resident.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], device=dev.index)
+        self.vn = torch.from_numpy(c["vec_norm"]).to(dev); self.vno = torch.from_numpy(c["vec_north"]).to(dev)
+        self.mask = torch.ones((ny, nx), dtype=torch.uint8, device=dev)
+        self.per = sharding.padded_block_rows(ny, world)
+        self.my_rows = sharding.shard_block_rows(ny, rank, world)
+        # all-gather buffer [world][per][nx][K]: this rank's packed shard is slice `rank`
+        self.gathered = torch.empty((world * self.per, nx, K), dtype=torch.float32, device=dev)
+        self.with_svf = with_svf
+        if with_svf:
+            tilt_np = hb.synthetic.tilt_vectors(c["x"], c["y"], c["z"], c["offset_0"])
+            idx = sharding.shard_row_indices(ny, rank, world)
+            tl = np.zeros((self.per, nx, 3), np.float32); tl[..., 2] = 1.0
+            ok = idx >= 0
+            tl[:len(idx)][ok] = tilt_np[idx[ok]]
+            self.tilt_np = tilt_np
+            self.tilt_packed = torch.from_numpy(tl).to(dev)
+            self.azim = torch.from_numpy(np.array([(2 * np.pi) / K * i for i in range(K)], np.float32)).to(dev)
+            self.svf_gathered = torch.empty((world * self.per, nx), dtype=torch.float32, device=dev)
+
+    def shard_view(self):
+        return self.gathered[self.rank * self.per:(self.rank + 1) * self.per]
+
+    def step(self, stream, ev=None):
+        c = self.c
+        mine = self.shard_view()
+        if ev is not None:
+            ev[0].record(stream)
+        self.scene.horizon_gridded_sharded(self.vn, self.vno, self.mask, c["offset_0"], c["offset_1"], mine, self.rank, self.world,
+                                           self.K, packed=True, dist_search=c["dist_search"], hori_acc=HORI_ACC,
+                                           ray_algorithm=ALGORITHM, stream=stream)
+        if ev is not None:
+            ev[1].record(stream)
+        if self.with_svf and self.my_rows > 0:
+            sv = self.svf_gathered[self.rank * self.per:(self.rank + 1) * self.per]
+            self.resident.sky_view_factor_dev(self.azim, mine[:self.my_rows], self.tilt_packed[:self.my_rows], sv[:self.my_rows],
+                                              stream=stream)
+        if self.world > 1:   # the single exchange step: all-gather of the packed shards (in place)
+            self.dist.all_gather_into_tensor(self.gathered, mine)
+            if self.with_svf:
+                self.dist.all_gather_into_tensor(self.svf_gathered, self.svf_gathered[self.rank * self.per:(self.rank + 1) * self.per])
+
+    def result(self):
+        """Gathered horizon in domain order (view/permute copy, outside the timed region)."""
+        if self.world == 1:
+            return self.gathered[:self.c["ny"]]
+        return self.sharding.unpack_blocks(self.gathered, self.c["ny"], self.world)
+
+    def row(self, r):
+        """Inner-domain row r of the gathered result, without materialising the whole array."""
+        blk = r // 4
+        return self.gathered[(blk % self.world) * self.per + (blk // self.world) * 4 + r % 4]
+
+    def close(self):
+        self.scene.close()
+
+
+def rank_stats(torch, dist, world, dev, values):
+    """min / mean / max over ranks of each value."""
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world > 1:
+        allv = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        m = torch.stack(allv)
+    else:
+        m = t[None]
+    return m.min(0).values.tolist(), m.mean(0).tolist(), m.max(0).tolist(), m.sum(0).tolist()
+
+
+def northstar_record(hb, torch, dist, dev, rank, world, args):
+    """One warm + one timed pass of the north-star workload (cfg4p), sharded like the main run; sampled rows are
+    checked bit for bit against the CPU oracle outside the timed region."""
+    c = hb.synthetic.make_config("cfg4p")
+    K = c["azim_num"]
+    run = ShardedRun(hb, torch, dist, c, dev, rank, world, with_svf=False)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run.step(stream)            # warm
+    barrier()
+    before = run.scene.stats()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    barrier()
+    t0.record(stream)
+    run.step(stream, kev)
+    t1.record(stream)
+    barrier()
+    after = run.scene.stats()
+    mn, mean, mx, sm = rank_stats(torch, dist, world, dev, [t0.elapsed_time(t1), kev[0].elapsed_time(kev[1]),
+                                                           float(after["rays"] - before["rays"]),
+                                                           float(after["node_visits"] - before["node_visits"]),
+                                                           float(after["prim_tests"] - before["prim_tests"])])
+    units = c["ny"] * c["nx"] * K
+    rec = None
+    if rank == 0:
+        rec = {"workload": workload_label(c, K), "value": units / (mx[0] * 1e-3), "unit": UNIT, "ms": mx[0],
+               "kernel_ms": {"min": mn[1], "mean": mean[1], "max": mx[1]}, "passes": "1 warm + 1 timed",
+               "counters": {"casts_per_unit": sm[2] / units, "nodes_per_cast": sm[3] / max(sm[2], 1.0),
+                            "prims_per_cast": sm[4] / max(sm[2], 1.0)},
+               "fallback_packets": int(after["fallback_packets"])}
+        if args.northstar_rows > 0:
+            import oracle
+            oracle.set_num_threads(os.cpu_count() or 1)
+            rows = sorted(set([0, c["ny"] // 4, c["ny"] // 2][:args.northstar_rows] +
+                              stratified_rows(c["ny"], max(0, args.northstar_rows - 3))))
+            sc = oracle.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+            h_cpu = sc.horizon_rows(rows, c["vec_norm"], c["vec_north"], c["offset_0"], c["offset_1"], c["dist_search"],
+                                    azim_num=K, hori_acc=HORI_ACC, ray_algorithm=ALGORITHM)
+            sc.close()
+            bad = 0
+            for i, r in enumerate(rows):
+                if not np.array_equal(run.row(r).cpu().numpy(), h_cpu[i]):
+                    bad += 1
+            rec["rows_checked_vs_oracle"] = len(rows)
+            rec["rows_checked"] = rows
+            rec["rows_bit_identical"] = len(rows) - bad
+            rec["check"] = "ok" if bad == 0 else "MISMATCH"
+    run.close()
+    del run
+    torch.cuda.empty_cache()
+    return rec
+
+
+def shadow_record(hb, torch, dev, args):
+    """cfg3 (3601 x 3601 shadow map): ms per sun position through Terrain.shadow (one call per position, host uint8
+    result, as the reference's loop) and through the batched entry point."""
+    syn = hb.synthetic
+    c = syn.make_config("cfg3")
+    ny, nx = c["ny"], c["nx"]
+    tilt = syn.tilt_vectors(c["x"], c["y"], c["z"], c["offset_0"])
+    enl = (1.0 / np.maximum(tilt[..., 2], 1e-3)).astype(np.float32)
+    elev = np.ascontiguousarray(c["z"][c["offset_0"]:c["offset_0"] + ny, c["offset_1"]:c["offset_1"] + nx])
+    mask = np.ones((ny, nx), np.uint8)
+    t = hb.shadow.Terrain()
+    t0 = time.perf_counter()
+    t.initialise(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["offset_0"], c["offset_1"], tilt, c["vec_norm"], enl, elev, mask)
+    init_s = time.perf_counter() - t0
+    n_sun = 16
+    suns = syn.sun_positions_diurnal(288)[::288 // n_sun][:n_sun].copy()
+    buf = np.empty((ny, nx), np.uint8)
+    for s in suns[:2]:
+        t.shadow(s, buf)                       # warm
+    w0 = time.perf_counter()
+    for s in suns:
+        t.shadow(s, buf)
+    single_ms = (time.perf_counter() - w0) / n_sun * 1e3
+    t.shadow_batch(suns[:2])                    # warm
+    w0 = time.perf_counter()
+    out = t.shadow_batch(suns)
+    batch_ms = (time.perf_counter() - w0) / n_sun * 1e3
+    del out
+    peak, _ = measured_peak()
+    bytes_per_unit = 38.0                       # SURVEY.md 8(d): 1 B out + vertex, tilt, norm, mask re-read per sun position
+    cells = ny * nx
+    ach = bytes_per_unit * cells / (batch_ms * 1e-3) / 1e9
+    return {"workload": "cfg3: 3601x3601 synthetic DEM (spacing 30 m), shadow codes (uint8), %d sun positions of a diurnal arc" % n_sun,
+            "ms_per_sun_single_call": single_ms, "ms_per_sun_batched": batch_ms, "cells_per_s": cells / (batch_ms * 1e-3),
+            "timing": "host wall clock incl. the D2H of every 13 MB result", "initialise_s": init_s,
+            "roofline": {"bound": "hbm", "algorithmic_bytes_per_unit": bytes_per_unit, "achieved": ach, "peak": peak,
+                         "unit": "GB/s", "frac": ach / peak, "kernel": "k_terrain_wq2"}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import horayzon_b200 as hb
-    from horayzon_b200 import resident, sharding
+    from horayzon_b200 import resident
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -192,37 +414,15 @@ def run_ours(args):
     c = hb.synthetic.make_config(args.workload)
     K = c["azim_num"]
     ny, nx = c["ny"], c["nx"]
-    tilt_np = hb.synthetic.tilt_vectors(c["x"], c["y"], c["z"], c["offset_0"])
-    azim_np = np.array([(2 * np.pi) / K * i for i in range(K)], np.float32)
-
-    # ---- resident state (outside the timed region): DEM + BVH + per-cell inputs
-    scene = resident.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], device=local_rank)
-    vn = torch.from_numpy(c["vec_norm"]).to(dev); vno = torch.from_numpy(c["vec_north"]).to(dev)
-    mask = torch.ones((ny, nx), dtype=torch.uint8, device=dev)
-    tilt = torch.from_numpy(tilt_np).to(dev); azim = torch.from_numpy(azim_np).to(dev)
-    shards = sharding.row_shards(ny, world)
-    b, e = shards[rank]
-    per = sharding.padded_rows(ny, world)
-    # full-size output: this rank fills rows [b, e); the all-gather fills the rest
-    hori = torch.empty((world * per, nx, K), dtype=torch.float32, device=dev)
-    svf = torch.empty((world * per, nx), dtype=torch.float32, device=dev)
+    run = ShardedRun(hb, torch, dist, c, dev, rank, world)
+    tilt_np = run.tilt_np
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > L2 (126 MB)
     stream = torch.cuda.current_stream()
     k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
 
     def step(i_timed=None):
         flush.zero_()  # L2 flush between iterations (inside the bracket; ~0.05 ms)
-        if i_timed is not None:
-            k_ev[i_timed][0].record(stream)
-        scene.horizon_gridded(vn, vno, mask, c["offset_0"], c["offset_1"], hori[:ny], b, e,
-                              dist_search=c["dist_search"], hori_acc=HORI_ACC, ray_algorithm=ALGORITHM, stream=stream)
-        if i_timed is not None:
-            k_ev[i_timed][1].record(stream)
-        if e > b:
-            resident.sky_view_factor_dev(azim, hori[b:e], tilt[b:e], svf[b:e], stream=stream)
-        if world > 1:  # single exchange step: all-gather of the row blocks (in place)
-            dist.all_gather_into_tensor(hori, hori[rank * per:(rank + 1) * per])
-            dist.all_gather_into_tensor(svf, svf[rank * per:(rank + 1) * per])
+        run.step(stream, k_ev[i_timed] if i_timed is not None else None)
 
     def barrier():
         if world > 1:
@@ -232,7 +432,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
-    before = scene.stats()
+    before = run.scene.stats()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -246,85 +446,131 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     total_ms = t0.elapsed_time(t1)
     kern_ms = sum(a.elapsed_time(z) for a, z in k_ev) / args.steps
-    after = scene.stats()
-    stat = torch.tensor([total_ms, kern_ms, float(after["rays"] - before["rays"]),
-                         float(after["node_visits"] - before["node_visits"]),
-                         float(after["prim_tests"] - before["prim_tests"]),
-                         float(after["warp_node_visits"] - before["warp_node_visits"])], dtype=torch.float64, device=dev)
-    smax = stat.clone()
-    if world > 1:
-        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
-        ssum = stat.clone(); dist.all_reduce(ssum, op=dist.ReduceOp.SUM)
-    else:
-        ssum = stat
-    total_ms, kern_ms_max = float(smax[0]), float(smax[1])
+    after = run.scene.stats()
+    mn, mean, mx, sm = rank_stats(torch, dist, world, dev, [
+        total_ms, kern_ms, float(after["rays"] - before["rays"]), float(after["node_visits"] - before["node_visits"]),
+        float(after["prim_tests"] - before["prim_tests"])])
+    total_ms, kern_ms_max = mx[0], mx[1]
     units_step = ny * nx * K
     value = units_step * args.steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the public (reference-shaped) API with host buffers
+    # ---- N > 1: the gathered array must equal a single-GPU pass over the whole domain (outside the timed region)
+    gather_check = None
+    if world > 1:
+        full = torch.empty((ny, nx, K), dtype=torch.float32, device=dev)
+        if rank == 0:
+            run.scene.horizon_gridded(run.vn, run.vno, run.mask, c["offset_0"], c["offset_1"], full, 0, ny,
+                                      dist_search=c["dist_search"], hori_acc=HORI_ACC, ray_algorithm=ALGORITHM, stream=stream)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(run.result(), full))
+            gather_check = "all-gathered horizon of %d ranks bit-identical to the 1-GPU pass" % world if same else "MISMATCH"
+        del full
+        barrier()
+
+    # ---- end-to-end through the public (reference-shaped) API with host buffers, on this rank's share of the rows
+    # (contiguous block: the host API takes an inner domain, offset_0 selects its first row)
+    per = -(-ny // world)
+    b, e = min(rank * per, ny), min(rank * per + per, ny)
     sl = slice(b, e)
-    e2e_times = []
-    h2d = d2h = 0
-    h_host = svf_host = None
-    for it in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
-        h_host = svf_host = None   # a loop that consumes each result before asking for the next one
-        if world > 1:
-            dist.barrier()
+
+    def e2e_pass(fused):
+        h2d = d2h = 0
         torch.cuda.synchronize()
         w0 = time.perf_counter()
+        phases = None
         if e > b:
-            h_host, a_host = hb.horizon.horizon_gridded(
-                c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["vec_norm"][sl], c["vec_north"][sl],
-                c["offset_0"] + b, c["offset_1"], c["dist_search"], azim_num=K, hori_acc=HORI_ACC,
-                ray_algorithm=ALGORITHM)
-            svf_host = hb.topo_param.sky_view_factor(a_host, h_host, tilt_np[sl])
-            h2d = (c["dem_dim_0"] * c["dem_dim_1"] * 12 + (e - b) * nx * 25) + (h_host.nbytes + tilt_np[sl].nbytes + a_host.nbytes)
+            a = (c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["vec_norm"][sl], c["vec_north"][sl],
+                 c["offset_0"] + b, c["offset_1"], c["dist_search"])
+            if fused:
+                h_host, a_host, svf_host = hb.horizon.horizon_gridded(*a, azim_num=K, hori_acc=HORI_ACC, ray_algorithm=ALGORITHM,
+                                                                      svf_vec_tilt=tilt_np[sl])
+                st = resident.last_stats()
+                h2d = c["dem_dim_0"] * c["dem_dim_1"] * 12 + (e - b) * nx * 25 + tilt_np[sl].nbytes
+            else:
+                h_host, a_host = hb.horizon.horizon_gridded(*a, azim_num=K, hori_acc=HORI_ACC, ray_algorithm=ALGORITHM)
+                st = resident.last_stats()
+                svf_host = hb.topo_param.sky_view_factor(a_host, h_host, tilt_np[sl])
+                h2d = c["dem_dim_0"] * c["dem_dim_1"] * 12 + (e - b) * nx * 25 + h_host.nbytes + tilt_np[sl].nbytes + a_host.nbytes
             d2h = h_host.nbytes + svf_host.nbytes
+            phases = {k: round(st[k] * 1e3, 1) for k in ("t_h2d", "t_build", "t_trace", "t_d2h", "t_total")}
+            del h_host, svf_host            # a loop that consumes each result before asking for the next one
         torch.cuda.synchronize()
         dt = torch.tensor([time.perf_counter() - w0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if it > 0:  # first call is warm-up (context, allocator)
-            e2e_times.append(float(dt[0]))
-    e2e_s = statistics.median(e2e_times) if e2e_times else float('nan')
+        return float(dt[0]), h2d, d2h, phases
+
+    e2e = {}
+    for name, fused in (("fused", True), ("two_call", False)):
+        samples, ph = [], None
+        h2d = d2h = 0
+        for it in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
+            if world > 1:
+                dist.barrier()
+            s, h2d, d2h, ph = e2e_pass(fused)
+            if it > 0:  # first call is warm-up (context, allocator, pools)
+                samples.append(s)
+        e2e[name] = {"samples_ms": [round(x * 1e3, 1) for x in samples], "h2d": h2d, "d2h": d2h, "phases_ms_last_call_rank0": ph,
+                     "median_s": statistics.median(samples) if samples else float("nan")}
+    hb.resident.trim()
+
+    # ---- the north-star workload and the shadow map (outside the main timed region; own timings)
+    run.close()
+    del run, flush
+    torch.cuda.empty_cache()
+    northstar = northstar_record(hb, torch, dist, dev, rank, world, args) if not args.no_northstar else None
+    shadow = None
+    if rank == 0 and world == 1 and not args.no_shadow:
+        shadow = shadow_record(hb, torch, dev, args)
 
     if rank == 0:
         peak, peak_src = measured_peak()
         algo_bytes_per_unit = 4.0 + 37.0 / K          # compulsory traffic
-        # dominant kernel = k_horizon_wq6 (launched by hzb_horizon_gridded_dev); at N > 1 each rank launches it on units/N
+        # dominant kernel = k_horizon_wq6; at N > 1 each rank launches it on units/N
         achieved = algo_bytes_per_unit * (units_step / world) / (kern_ms_max * 1e-3) / 1e9
-        rays = float(ssum[2])
+        rays = sm[2] / args.steps
+        fz = e2e["fused"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_label(c, K),
-                       "parallelism": "rows x%d, replicated DEM+BVH, 1 NCCL all-gather/step" % world if world > 1 else "single GPU",
-                       "l2": "256 MB flush write before every step; per-step output %.2f GB >> 126 MB L2" % (units_step * 4 / 1e9)},
+            "config": config_dict(c, K, world),
             "clocks": clocks,
-            "e2e": {"value": units_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3,
-                    "api": "horayzon_b200.horizon.horizon_gridded + topo_param.sky_view_factor (host ndarray in/out, "
-                           "inputs pageable like the reference's; the returned horizon array is page-locked from the second large call "
-                           "of a process on; H2D + BVH build + kernels + D2H timed; median of %d calls after one warm-up call, "
-                           "each result released before the next call)" % len(e2e_times)},
+            "e2e": {"value": units_step / fz["median_s"], "unit": UNIT, "h2d_bytes_per_step": int(fz["h2d"]),
+                    "d2h_bytes_per_step": int(fz["d2h"]), "ms_per_step": fz["median_s"] * 1e3,
+                    "samples_ms": fz["samples_ms"], "phases_ms_last_call_rank0": fz["phases_ms_last_call_rank0"],
+                    "api": "horayzon_b200.horizon.horizon_gridded(..., svf_vec_tilt=) -> (hori, azim, svf): host ndarrays in/out "
+                           "(pageable inputs like the reference's), H2D + BVH build + horizon kernel + SVF integral on the "
+                           "device-resident horizon + D2H timed; median after one warm-up call, each result released before the next call",
+                    "two_call": {"value": units_step / e2e["two_call"]["median_s"], "ms_per_step": e2e["two_call"]["median_s"] * 1e3,
+                                 "samples_ms": e2e["two_call"]["samples_ms"], "h2d_bytes_per_step": int(e2e["two_call"]["h2d"]),
+                                 "phases_ms_last_call_rank0": e2e["two_call"]["phases_ms_last_call_rank0"],
+                                 "api": "the reference's sequence: horizon_gridded(...) then topo_param.sky_view_factor(azim, hori, "
+                                        "vec_tilt) on the returned host array (uploads the horizon array again)"}},
             "gpu_launches": int(2 * args.steps),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": recorded_traffic(args.workload), "peak_source": peak_src,
-                         "kernel": "k_horizon_wq6", "kernel_ms": kern_ms_max,
+                         "kernel": KERNEL, "kernel_ms": kern_ms_max,
+                         "kernel_ms_ranks": {"min": mn[1], "mean": mean[1], "max": mx[1]},
                          "algorithmic_bytes_per_unit": algo_bytes_per_unit,
-                         "note": "compulsory bytes only (output store + per-cell inputs); BVH traversal is "
-                                 "latency/L2-bound, see DESIGN.md"},
-            "counters": {"casts_per_unit": rays / (units_step * args.steps),
-                         "nodes_per_cast": float(ssum[3]) / max(rays, 1.0), "prims_per_cast": float(ssum[4]) / max(rays, 1.0),
-                         "warp_nodes_per_cast": float(ssum[5]) / max(rays, 1.0)},
+                         "note": "compulsory bytes only (output store + per-cell inputs); the traversal is bound by "
+                                 "instruction issue with the BVH served from L1/L2, see DESIGN.md"},
+            "counters": {"casts_per_unit": rays / units_step,
+                         "nodes_per_cast": sm[3] / max(sm[2], 1.0), "prims_per_cast": sm[4] / max(sm[2], 1.0)},
             "bvh": {"prims": int(after["num_prims"]), "bytes": int(after["bvh_bytes"]), "build_s": after["t_build"],
                     "h2d_s": after["t_h2d"]},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = oracle_sample(c, K, target_s=args.ref_seconds)
+        if gather_check:
+            line["gather_check"] = gather_check
+        if northstar:
+            line["northstar"] = northstar
+        if shadow:
+            line["shadow"] = shadow
+        if not args.no_cpu_baseline:
+            smp = OracleSampler(c, K)
+            line["cpu_baseline"] = smp.sample(smp.size_sample(args.ref_seconds))
+            smp.close()
         print(json.dumps(line), flush=True)
-    scene.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -340,6 +586,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-northstar", action="store_true")
+    ap.add_argument("--northstar-rows", type=int, default=3, help="rows of the north-star pass checked against the CPU oracle")
+    ap.add_argument("--no-shadow", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3

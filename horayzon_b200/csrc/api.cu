@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <time.h>
 #include <stdlib.h>
+#include <mutex>
+#include <thread>
 
 namespace hzb {
 
@@ -57,6 +59,87 @@ int parse_ellps(const char* s) {
     return -1;
 }
 
+DebugOptions& debug_options() { static DebugOptions o; return o; }
+
+// ---- device buffer pool: the big per-call buffers of the host tier (the 2 GB horizon array of a
+// 1201 x 1201 x 360 call) are kept between calls instead of cudaMalloc / cudaFree every time.
+// Idle memory is bounded (HZB_POOL_IDLE_MAX) and released by hzb_trim().
+namespace {
+struct DevPool {
+    std::mutex mu;
+    struct Blk { void* p; size_t cap; int dev; };
+    std::vector<Blk> idle, live;
+    size_t idle_bytes = 0;
+};
+DevPool& dev_pool() { static DevPool* p = new DevPool(); return *p; }
+constexpr size_t HZB_POOL_IDLE_MAX = (size_t)6 << 30;
+}  // namespace
+
+void* pool_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    int dev = 0; cudaGetDevice(&dev);
+    DevPool& P = dev_pool();
+    std::lock_guard<std::mutex> l(P.mu);
+    int best = -1;
+    for (int i = 0; i < (int)P.idle.size(); ++i)
+        if (P.idle[i].dev == dev && P.idle[i].cap >= bytes && P.idle[i].cap <= bytes + bytes / 4 + 4096 &&
+            (best < 0 || P.idle[i].cap < P.idle[best].cap)) best = i;
+    DevPool::Blk b{nullptr, 0, dev};
+    if (best >= 0) { b = P.idle[best]; P.idle.erase(P.idle.begin() + best); P.idle_bytes -= b.cap; }
+    else {
+        if (cudaMalloc(&b.p, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            for (DevPool::Blk& x : P.idle) if (x.dev == dev) cudaFree(x.p);      // make room and retry once
+            P.idle.erase(std::remove_if(P.idle.begin(), P.idle.end(), [&](const DevPool::Blk& x) { return x.dev == dev; }), P.idle.end());
+            P.idle_bytes = 0; for (DevPool::Blk& x : P.idle) P.idle_bytes += x.cap;
+            if (cudaMalloc(&b.p, bytes) != cudaSuccess) { set_error(std::string("cudaMalloc of ") + std::to_string(bytes) + " bytes failed: " + cudaGetErrorString(cudaGetLastError())); return nullptr; }
+        }
+        b.cap = bytes;
+    }
+    P.live.push_back(b);
+    return b.p;
+}
+void pool_free(void* p) {
+    if (!p) return;
+    DevPool& P = dev_pool();
+    std::lock_guard<std::mutex> l(P.mu);
+    for (size_t i = 0; i < P.live.size(); ++i)
+        if (P.live[i].p == p) {
+            DevPool::Blk b = P.live[i];
+            P.live.erase(P.live.begin() + i);
+            if (b.cap < ((size_t)1 << 20) || b.cap > HZB_POOL_IDLE_MAX) { cudaFree(b.p); return; }
+            P.idle.push_back(b); P.idle_bytes += b.cap;
+            while (P.idle_bytes > HZB_POOL_IDLE_MAX || P.idle.size() > 8) {        // oldest first
+                cudaFree(P.idle[0].p); P.idle_bytes -= P.idle[0].cap; P.idle.erase(P.idle.begin());
+            }
+            return;
+        }
+    cudaFree(p);
+}
+void pool_trim() {
+    DevPool& P = dev_pool();
+    std::lock_guard<std::mutex> l(P.mu);
+    int cur = 0; cudaGetDevice(&cur);
+    for (DevPool::Blk& b : P.idle) { cudaSetDevice(b.dev); cudaFree(b.p); }
+    cudaSetDevice(cur);
+    P.idle.clear(); P.idle_bytes = 0;
+}
+
+// ---- per-thread, per-device host-tier context: two streams (compute / copy) created once
+struct HostCtx { int dev = -1; cudaStream_t comp = nullptr, copy = nullptr; };
+static int host_ctx(HostCtx** out) {
+    static thread_local std::vector<HostCtx> ctxs;
+    int dev = 0;
+    HZB_CUDA(cudaGetDevice(&dev));
+    for (HostCtx& c : ctxs) if (c.dev == dev) { *out = &c; return 0; }
+    HostCtx c; c.dev = dev;
+    HZB_CUDA(cudaStreamCreateWithFlags(&c.comp, cudaStreamNonBlocking));
+    HZB_CUDA(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    ctxs.push_back(c);
+    *out = &ctxs.back();
+    return 0;
+}
+
 static int require_device() {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -73,18 +156,18 @@ static int read_counters(const Scene& s, hzb_stats& st) {
     Counters c;
     HZB_CUDA(cudaMemcpy(&c, s.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     st.rays = c.rays; st.node_visits = c.node_visits; st.prim_tests = c.prim_tests; st.units = c.units;
-    st.warp_node_visits = c.warp_node_visits;
+    st.warp_node_visits = c.warp_node_visits; st.fallback_packets = c.fallback_packets;
     st.num_prims = s.num_prims; st.num_nodes = s.num_nodes4; st.bvh_bytes = s.bvh_bytes;
     st.t_h2d = s.t_h2d; st.t_build = s.t_build;
-    if (c.stack_overflow) { set_error("BVH traversal stack overflow (results invalid)"); return 1; }
+    if (c.stack_overflow) { set_error("binary-BVH walker stack overflow (results invalid)"); return 1; }
     return 0;
 }
 
 template <typename T>
-struct DevBuf {  // RAII device buffer
+struct DevBuf {  // RAII device buffer (pooled: large blocks survive the call, see pool_alloc)
     T* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t n) { HZB_CUDA(cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T))); return 0; }
+    ~DevBuf() { if (p) pool_free(p); }
+    int alloc(size_t n) { p = (T*)pool_alloc((n ? n : 1) * sizeof(T)); return p ? 0 : 1; }
     int upload(const T* h, size_t n) {
         HZB_TRY(alloc(n));
         HZB_CUDA(cudaMemcpy(p, h, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -118,9 +201,26 @@ struct hzb_terrain {
     Scene s; bool ready = false; TerrainParams tp{};
     float *d_tilt = nullptr, *d_norm = nullptr, *d_enl = nullptr, *d_elev = nullptr; uint8_t* d_mask = nullptr;
     void* d_out = nullptr; size_t out_cap = 0;
+    // created once per terrain (not per sun position): compute / copy streams and the double-buffer events
+    cudaStream_t s_comp = nullptr, s_copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    int streams() {
+        if (s_comp) return 0;
+        HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+        HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            HZB_CUDA(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming));
+            HZB_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
+        }
+        return 0;
+    }
     void release() {
         cudaFree(d_tilt); cudaFree(d_norm); cudaFree(d_enl); cudaFree(d_elev); cudaFree(d_mask); cudaFree(d_out);
         d_tilt = d_norm = d_enl = d_elev = nullptr; d_mask = nullptr; d_out = nullptr; out_cap = 0;
+        if (s_comp) cudaStreamDestroy(s_comp);
+        if (s_copy) cudaStreamDestroy(s_copy);
+        for (int b = 0; b < 2; ++b) { if (done[b]) cudaEventDestroy(done[b]); if (freed[b]) cudaEventDestroy(freed[b]); done[b] = freed[b] = nullptr; }
+        s_comp = s_copy = nullptr;
         scene_free(s); ready = false;
     }
 };
@@ -151,6 +251,23 @@ int hzb_horizon_tables(int azim_num, float dist_search, float hori_acc, float el
     }
     return T.elev_num;
 }
+// Test-only switches (see DebugOptions).  Returns 0, or 1 for an unknown name.
+int hzb_debug_option(const char* name, int value) {
+    DebugOptions& o = debug_options();
+    if (!name) { set_error("null option name"); return 1; }
+    if (!strcmp(name, "reset")) { o = DebugOptions(); return 0; }
+    if (!strcmp(name, "horizon_kernel")) { o.horizon_kernel = value; return 0; }
+    if (!strcmp(name, "shadow_kernel")) { o.shadow_kernel = value; return 0; }
+    if (!strcmp(name, "wrefill")) { o.wrefill = value; return 0; }
+    if (!strcmp(name, "wwait")) { o.wwait = value; return 0; }
+    if (!strcmp(name, "no_overlap")) { o.no_overlap = value; return 0; }
+    if (!strcmp(name, "stack_limit")) { o.stack_limit = value; return 0; }
+    if (!strcmp(name, "horizon_variant")) { o.horizon_variant = value; return 0; }
+    set_error(std::string("unknown debug option ") + name);
+    return 1;
+}
+// Release the idle pooled memory of this process (device blocks of the host tier, page-locked output blocks).
+void hzb_trim(void) { pool_trim(); host_block_trim(); }
 void* hzb_host_alloc(size_t bytes) { if (require_device()) return nullptr; return host_block_alloc(bytes); }
 void hzb_host_free(void* p) { host_block_free(p); }
 
@@ -158,6 +275,16 @@ void hzb_host_free(void* p) { host_block_free(p); }
 hzb_scene* hzb_scene_create(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vert_simp,
                             int num_vert_simp, const int32_t* tri_ind_simp, int num_tri_simp, int device) {
     if (require_device()) return nullptr;
+    if (!vert_grid) { set_error("null pointer argument"); return nullptr; }
+    // the kernels pack a cell as (row << 16) | column and the reference's wrapper has the same limit (horizon.pyx:149-151)
+    if (dem_dim_0 > 32767 || dem_dim_1 > 32767) { set_error("maximal allowed input length for dem_dim_0 and dem_dim_1 is 32'767"); return nullptr; }
+    if (num_vert_simp >= 3 && num_tri_simp > 0) {
+        if (!vert_simp || !tri_ind_simp) { set_error("null pointer argument"); return nullptr; }
+        const size_t m = (size_t)num_tri_simp * 3;
+        int32_t lo = 0, hi = 0;
+        for (size_t i = 0; i < m; ++i) { lo = std::min(lo, tri_ind_simp[i]); hi = std::max(hi, tri_ind_simp[i]); }
+        if (lo < 0 || hi >= num_vert_simp) { set_error("triangle indices of simplified outer domain exceed number of vertices"); return nullptr; }
+    }
     if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice failed"); cudaGetLastError(); return nullptr; }
     hzb_scene* h = new hzb_scene();
     h->s.device = device;
@@ -177,7 +304,8 @@ static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const floa
                                   int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
                                   int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
                                   float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
-                                  unsigned int* d_row_done, cudaStream_t st, int azim_first = 0) {
+                                  unsigned int* d_row_done, volatile unsigned int* row_flags, cudaStream_t st, int azim_first = 0,
+                                  int shard_rank = 0, int shard_count = 1, int packed = 0) {
     const int alg = parse_algorithm(ray_algorithm);
     if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
     if (azim_num < 1 || dim_in_0 < 0 || dim_in_1 < 0 || row_begin < 0 || row_end > dim_in_0) { set_error("invalid dimensions"); return 1; }
@@ -185,15 +313,17 @@ static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const floa
         set_error("inner domain exceeds DEM dimensions"); return 1;
     }
     if (!(hori_acc > 0.f)) { set_error("hori_acc must be positive"); return 1; }
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) { set_error("invalid shard"); return 1; }
+    if ((shard_count > 1 || packed) && (d_row_done || azim_first)) { set_error("block sharding needs the reference layout and no progress counters"); return 1; }
     HZB_CUDA(cudaSetDevice(sc.device));
-    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
-    if (T.elev_num < 2) { set_error("elevation table too small"); return 1; }
     HorizonParams p{};
-    HZB_TRY(upload_tables(sc, T, p, st));
+    HZB_TRY(scene_tables(sc, azim_num, dist_search, hori_acc, elev_ang_low_lim, p, st));
     p.algorithm = alg; p.vec_norm = d_vec_norm; p.vec_north = d_vec_north; p.mask = d_mask;
     p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1;
     p.row_begin = row_begin; p.row_end = row_end; p.hori_fill = hori_fill; p.ray_org_elev = ray_org_elev;
-    p.hori = d_hori_buffer; p.row_done = d_row_done;
+    p.hori = d_hori_buffer; p.row_done = d_row_done; p.row_flags = row_flags;
+    p.row_full = (unsigned int)((dim_in_1 + 7) / 8) * 32u;
+    p.blk_stride = shard_count; p.blk_offset = shard_rank; p.packed = packed;
     p.stride_c = azim_first ? 1 : azim_num;
     p.stride_k = azim_first ? (long long)dim_in_0 * dim_in_1 : 1;
     return launch_horizon_gridded(sc, p, st);
@@ -207,7 +337,7 @@ int hzb_horizon_gridded_dev(hzb_scene* h, const float* d_vec_norm, const float* 
     if (!h) { set_error("null scene"); return 1; }
     return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, row_begin,
                                   row_end, azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
-                                  ray_org_elev, d_hori_buffer, nullptr, (cudaStream_t)stream);
+                                  ray_org_elev, d_hori_buffer, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 // additive (scope row "next 4"): azimuth-first output [azim_num][dim_in_0][dim_in_1], the layout the
@@ -220,22 +350,51 @@ int hzb_horizon_gridded_dev_layout(hzb_scene* h, const float* d_vec_norm, const 
     if (!h) { set_error("null scene"); return 1; }
     return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, row_begin,
                                   row_end, azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
-                                  ray_org_elev, d_hori_buffer, nullptr, (cudaStream_t)stream, azim_first);
+                                  ray_org_elev, d_hori_buffer, nullptr, nullptr, (cudaStream_t)stream, azim_first);
+}
+
+// additive (multi-GPU): shard `shard_rank` of `shard_count` computes the 4-row blocks b of the inner domain with
+// b % shard_count == shard_rank (interleaved, so every shard sees the same mix of cheap rim rows and expensive
+// centre rows).  packed == 0: results go to their places in the full [dim_in_0][dim_in_1][azim_num] array;
+// packed != 0: the shard's blocks are stored back to back from d_hori_buffer on -- a contiguous all-gather send
+// buffer of hzb_shard_rows(dim_in_0, rank, count) rows.
+int hzb_horizon_gridded_dev_sharded(hzb_scene* h, const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                    int offset_0, int offset_1, int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+                                    float hori_acc, const char* ray_algorithm, float elev_ang_low_lim, float hori_fill,
+                                    float ray_org_elev, float* d_hori_buffer, int shard_rank, int shard_count, int packed,
+                                    void* stream) {
+    if (!h) { set_error("null scene"); return 1; }
+    return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
+                                  azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill, ray_org_elev,
+                                  d_hori_buffer, nullptr, nullptr, (cudaStream_t)stream, 0, shard_rank, shard_count, packed);
+}
+// rows (padded to whole 4-row blocks) a shard's packed buffer holds
+int hzb_shard_rows(int dim_in_0, int shard_rank, int shard_count) {
+    if (shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count || dim_in_0 < 0) return -1;
+    const int all = (dim_in_0 + 3) / 4;
+    return all > shard_rank ? 4 * ((all - shard_rank + shard_count - 1) / shard_count) : 0;
 }
 
 // -------------------------------------------------------------- host tier
+// One call = H2D of the inputs, on-device BVH build, horizon kernel, (optionally) the SVF integral on
+// the device-resident horizon, D2H.  The kernel runs on one stream; finished 4-row blocks -- the last
+// cell of a block raises a flag in mapped host memory, so the host polls plain memory, no CUDA call --
+// leave for the caller's array on a second stream while the kernel is still running.
 static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
                         const float* vec_north, int offset_0, int offset_1, float* hori_buffer, int dim_in_0,
                         int dim_in_1, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
                         const char* geom_type, const float* vert_simp, int num_vert_simp,
                         const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
-                        float hori_fill, float ray_org_elev, int azim_first) {
+                        float hori_fill, float ray_org_elev, int azim_first,
+                        const float* svf_vec_tilt = nullptr, float* svf_out = nullptr) {
     memset(&g_stats, 0, sizeof(g_stats));
     const double t_start = now_s();
     const bool timing = getenv("HZB_TIMING") != nullptr;   // stderr breakdown of this call
     if (require_device()) return 1;
     if (parse_geom_type(geom_type) < 0) { set_error("invalid input argument for geom_type"); return 1; }
     if (!vert_grid || !vec_norm || !vec_north || !hori_buffer || !mask) { set_error("null pointer argument"); return 1; }
+    if ((svf_vec_tilt == nullptr) != (svf_out == nullptr)) { set_error("svf_vec_tilt and svf_out go together"); return 1; }
+    if (svf_out && azim_num < 2) { set_error("the sky view factor needs at least two azimuth sectors"); return 1; }
     int dev = 0; cudaGetDevice(&dev);
     const double t_scene0 = now_s();
     hzb_scene* h = hzb_scene_create(vert_grid, dem_dim_0, dem_dim_1, vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp, dev);
@@ -244,28 +403,45 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
     const size_t nc = (size_t)dim_in_0 * dim_in_1;
     const double t_scene = now_s() - t_scene0;
     double t0 = now_s();
-    DevBuf<float> d_norm, d_north, d_hori; DevBuf<uint8_t> d_mask;
+    HostCtx* ctx = nullptr;
+    HZB_TRY(host_ctx(&ctx));
+    cudaStream_t s_comp = ctx->comp, s_copy = ctx->copy;
+    DevBuf<float> d_norm, d_north, d_hori, d_tilt, d_azim, d_svf; DevBuf<uint8_t> d_mask;
     HZB_TRY(d_norm.upload(vec_norm, nc * 3)); HZB_TRY(d_north.upload(vec_north, nc * 3)); HZB_TRY(d_mask.upload(mask, nc));
     HZB_TRY(d_hori.alloc(nc * (size_t)azim_num));
+    if (svf_out) {
+        std::vector<float> az((size_t)azim_num);
+        for (int i = 0; i < azim_num; ++i) az[i] = (float)((2 * M_PI) / azim_num * i);    // horizon.pyx:190-195
+        HZB_TRY(d_tilt.upload(svf_vec_tilt, nc * 3)); HZB_TRY(d_azim.upload(az.data(), (size_t)azim_num));
+        HZB_TRY(d_svf.alloc(nc));
+    }
     const double t_h2d_extra = now_s() - t0;
-    // Kernel on one stream; finished row blocks (published by the kernel through
-    // row_done counters) are copied to the caller's array on a second stream while
-    // the kernel is still running, so D2H and the page faults of the fresh ndarray
-    // hide behind the traversal.
     t0 = now_s();
-    const int tiles_x = (dim_in_1 + 7) / 8, tiles_y = (dim_in_0 + 3) / 4;
+    const int tiles_y = (dim_in_0 + 3) / 4;
     // (rows are contiguous byte ranges only in the reference layout: azimuth-first output is copied after the kernel)
-    const bool overlap = !azim_first && getenv("HZB_NO_OVERLAP") == nullptr && !(getenv("HZB_KERNEL") && !strcmp(getenv("HZB_KERNEL"), "simple"));
-    cudaStream_t s_comp = nullptr, s_copy = nullptr;
-    HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    struct StreamGuard { cudaStream_t a, b; ~StreamGuard() { cudaStreamDestroy(a); cudaStreamDestroy(b); } } sguard{s_comp, s_copy};
+    const DebugOptions& dbg = debug_options();
+    const bool overlap = !azim_first && !dbg.no_overlap && dbg.horizon_kernel == 0;
     DevBuf<unsigned int> d_done;
-    HZB_TRY(d_done.alloc((size_t)tiles_y));
-    HZB_CUDA(cudaMemsetAsync(d_done.p, 0, (size_t)tiles_y * sizeof(unsigned int), s_comp));
+    unsigned int* h_flags = nullptr; unsigned int* d_flags = nullptr;
+    struct PinGuard { unsigned int*& p; ~PinGuard() { if (p) cudaFreeHost(p); } } pguard{h_flags};
+    if (overlap) {
+        HZB_TRY(d_done.alloc((size_t)tiles_y));
+        HZB_CUDA(cudaMemsetAsync(d_done.p, 0, (size_t)tiles_y * sizeof(unsigned int), s_comp));
+        HZB_CUDA(cudaHostAlloc((void**)&h_flags, (size_t)tiles_y * sizeof(unsigned int), cudaHostAllocMapped));
+        memset(h_flags, 0, (size_t)tiles_y * sizeof(unsigned int));
+        HZB_CUDA(cudaHostGetDevicePointer((void**)&d_flags, h_flags, 0));
+    }
     HZB_TRY(horizon_gridded_launch(h->s, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
                                    azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
-                                   ray_org_elev, d_hori.p, overlap ? d_done.p : nullptr, s_comp, azim_first));
+                                   ray_org_elev, d_hori.p, overlap ? d_done.p : nullptr, overlap ? d_flags : nullptr, s_comp, azim_first));
+    if (svf_out && nc > 0) {   // fused epilogue: the integral reads the horizon where the kernel left it (HBM), azimuth-first aware
+        if (azim_first) { set_error("the fused sky view factor needs the reference layout (azim_first = 0)"); cudaStreamSynchronize(s_comp); return 1; }
+        HZB_TRY(launch_svf(0, d_azim.p, d_hori.p, d_tilt.p, (long long)nc, azim_num, d_svf.p, s_comp));
+    }
+    cudaEvent_t ev_done = nullptr;
+    HZB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } evguard{ev_done};
+    HZB_CUDA(cudaEventRecord(ev_done, s_comp));
     double t_d2h = 0.0, t_trace = 0.0;
     const size_t row_elems = (size_t)dim_in_1 * (size_t)azim_num;
     const double t_pf0 = now_s();
@@ -273,18 +449,14 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
     if (!out_pinned) host_prefault(hori_buffer, nc * (size_t)azim_num * sizeof(float));   // the kernel is running meanwhile
     const double t_prefault = now_s() - t_pf0;
     if (overlap) {
-        unsigned int* h_done = nullptr;
-        HZB_CUDA(cudaMallocHost((void**)&h_done, (size_t)tiles_y * sizeof(unsigned int)));
-        struct PinGuard { unsigned int* p; ~PinGuard() { cudaFreeHost(p); } } pguard{h_done};
+        const volatile unsigned int* flags = h_flags;
         const int min_blocks = std::max(1, (int)((64u << 20) / (row_elems * 4 * sizeof(float)) ));  // >= 64 MB per copy
         int copied_blocks = 0;
         while (copied_blocks < tiles_y) {
-            const bool finished = cudaStreamQuery(s_comp) == cudaSuccess;
+            const bool finished = cudaEventQuery(ev_done) == cudaSuccess;
             if (finished && t_trace == 0.0) t_trace = now_s() - t0;
-            HZB_CUDA(cudaMemcpyAsync(h_done, d_done.p, (size_t)tiles_y * sizeof(unsigned int), cudaMemcpyDeviceToHost, s_copy));
-            HZB_CUDA(cudaStreamSynchronize(s_copy));
             int ready = copied_blocks;
-            while (ready < tiles_y && h_done[ready] == (unsigned int)tiles_x * 32u) ++ready;   // counts cells (32 per tile)
+            while (ready < tiles_y && flags[ready] != 0u) ++ready;
             if (finished && ready < tiles_y) {
                 cudaError_t e = cudaGetLastError();
                 set_error(std::string("horizon kernel ended with unfinished rows") + (e != cudaSuccess ? std::string(": ") + cudaGetErrorString(e) : ""));
@@ -296,18 +468,18 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
                 if (out_pinned) {
                     HZB_CUDA(cudaMemcpyAsync(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float),
                                              cudaMemcpyDeviceToHost, s_copy));
-                    HZB_CUDA(cudaStreamSynchronize(s_copy));
+                    if (ready == tiles_y) HZB_CUDA(cudaStreamSynchronize(s_copy));   // earlier blocks keep flowing while we poll
                 } else {
                     HZB_TRY(staged_d2h(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float), s_copy));
                 }
                 t_d2h += now_s() - tc;
                 copied_blocks = ready;
             } else {
-                struct timespec ts = {0, 2000000};  // 2 ms
-                nanosleep(&ts, nullptr);
+                std::this_thread::sleep_for(std::chrono::microseconds(100));
             }
         }
         HZB_CUDA(cudaStreamSynchronize(s_comp));
+        HZB_CUDA(cudaStreamSynchronize(s_copy));
         if (t_trace == 0.0) t_trace = now_s() - t0;
     } else {
         HZB_CUDA(cudaStreamSynchronize(s_comp));
@@ -317,11 +489,12 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
         else HZB_TRY(staged_d2h(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), nullptr));
         t_d2h = now_s() - tc;
     }
+    if (svf_out && nc > 0) HZB_CUDA(cudaMemcpy(svf_out, d_svf.p, nc * sizeof(float), cudaMemcpyDeviceToHost));
     HZB_CUDA(cudaGetLastError());
     HZB_TRY(read_counters(h->s, g_stats));
     g_stats.t_h2d += t_h2d_extra; g_stats.t_trace = t_trace; g_stats.t_d2h = t_d2h; g_stats.t_total = now_s() - t_start;
     if (timing)
-        fprintf(stderr, "[hzb] horizon_gridded: scene %.3f (h2d %.3f build %.3f) inputs+alloc %.3f launch..end %.3f (prefault %.3f, kernel seen done %.3f, staged d2h %.3f) total %.3f s\n",
+        fprintf(stderr, "[hzb] horizon_gridded: scene %.3f (h2d %.3f build %.3f) inputs+alloc %.3f launch..end %.3f (prefault %.3f, kernel seen done %.3f, d2h calls %.3f) total %.3f s\n",
                 t_scene, h->s.t_h2d, h->s.t_build, t_h2d_extra, now_s() - t0, t_prefault, t_trace, t_d2h, g_stats.t_total);
     return 0;
 }
@@ -348,6 +521,21 @@ int hzb_horizon_gridded_layout(const float* vert_grid, int dem_dim_0, int dem_di
                                 tri_ind_simp, num_tri_simp, elev_ang_low_lim, mask, hori_fill, ray_org_elev, azim_first);
 }
 
+// additive: horizon + sky view factor in one call.  The integral (topo_param.pyx:412-460) runs on the
+// device-resident horizon right behind the search, so the 2 GB-scale array is never uploaded again
+// (examples/horizon/gridded_curved_DEM.py:104-144 calls the two back to back).
+int hzb_horizon_gridded_svf(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
+                            const float* vec_north, int offset_0, int offset_1, float* hori_buffer, int dim_in_0,
+                            int dim_in_1, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
+                            const char* geom_type, const float* vert_simp, int num_vert_simp,
+                            const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
+                            float hori_fill, float ray_org_elev, const float* vec_tilt, float* svf_buffer) {
+    if (!vec_tilt || !svf_buffer) { set_error("null pointer argument"); return 1; }
+    return horizon_gridded_host(vert_grid, dem_dim_0, dem_dim_1, vec_norm, vec_north, offset_0, offset_1, hori_buffer, dim_in_0,
+                                dim_in_1, azim_num, dist_search, hori_acc, ray_algorithm, geom_type, vert_simp, num_vert_simp,
+                                tri_ind_simp, num_tri_simp, elev_ang_low_lim, mask, hori_fill, ray_org_elev, 0, vec_tilt, svf_buffer);
+}
+
 int hzb_horizon_locations(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* coords,
                           const float* vec_norm, const float* vec_north, float* hori_buffer, float* hori_dist_buffer,
                           int num_loc, int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
@@ -371,9 +559,8 @@ int hzb_horizon_locations(const float* vert_grid, int dem_dim_0, int dem_dim_1, 
     HZB_TRY(d_elev.upload(ray_org_elev, n));
     HZB_TRY(d_hori.upload(hori_buffer, no));  // keeps the caller's pre-fill for skipped locations
     if (hori_dist_out) HZB_TRY(d_dist.upload(hori_dist_buffer, no));
-    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
     HorizonParams p{};
-    HZB_TRY(upload_tables(h->s, T, p, nullptr));
+    HZB_TRY(scene_tables(h->s, azim_num, dist_search, hori_acc, elev_ang_low_lim, p, nullptr));
     p.algorithm = alg;
     LocationParams lp{d_coords.p, d_norm.p, d_north.p, d_elev.p, d_hori.p, d_dist.p, num_loc, hori_dist_out};
     double t0 = now_s();
@@ -456,12 +643,9 @@ static int terrain_batch(hzb_terrain* t, const float* suns, int n_sun, T* out, L
     HZB_CUDA(cudaSetDevice(t->s.device));
     const int nbuf = n_sun > 1 ? 2 : 1;
     HZB_TRY(terrain_out(t, nc * sizeof(T) * nbuf));
-    cudaStream_t s_comp = nullptr, s_copy = nullptr;
-    HZB_CUDA(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    HZB_CUDA(cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking));
-    cudaEvent_t done[2], freed[2];
-    for (int b = 0; b < 2; ++b) { cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming); cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming); }
-    struct Guard { cudaStream_t a, b; cudaEvent_t* d; cudaEvent_t* f; ~Guard() { cudaStreamDestroy(a); cudaStreamDestroy(b); for (int i = 0; i < 2; ++i) { cudaEventDestroy(d[i]); cudaEventDestroy(f[i]); } } } guard{s_comp, s_copy, done, freed};
+    HZB_TRY(t->streams());
+    cudaStream_t s_comp = t->s_comp, s_copy = t->s_copy;
+    cudaEvent_t* done = t->done; cudaEvent_t* freed = t->freed;
     int rc = 0;
     for (int k = 0; k <= n_sun && rc == 0; ++k) {
         if (k < n_sun) {

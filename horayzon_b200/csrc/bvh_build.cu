@@ -369,9 +369,11 @@ int exclusive_scan_u32(uint32_t* d_in, uint32_t* d_out, size_t m, uint32_t* d_su
 
 void scene_free(Scene& s) {
     cudaFree(s.d_vert4); cudaFree(s.d_tin4); cudaFree(s.d_nodes2); cudaFree(s.d_nodes4);
-    cudaFree(s.d_prim_ids); cudaFree(s.d_counters); cudaFree(s.d_tile_counter); cudaFree(s.d_tables);
+    cudaFree(s.d_prim_ids); cudaFree(s.d_counters); cudaFree(s.d_tile_counter);
+    for (Scene::TableEntry& e : s.tables) cudaFree(e.d);
+    s.tables.clear();
     s.d_vert4 = nullptr; s.d_tin4 = nullptr; s.d_nodes2 = nullptr; s.d_nodes4 = nullptr; s.d_prim_ids = nullptr;
-    s.d_counters = nullptr; s.d_tile_counter = nullptr; s.d_tables = nullptr; s.tables_cap = 0;
+    s.d_counters = nullptr; s.d_tile_counter = nullptr;
 }
 
 int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const float* vert_simp,
@@ -385,14 +387,23 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
     const size_t nv = (size_t)H * W;
     const uint32_t n = s.num_prims;
 
+    // build temporaries: released on every exit path
+    struct Tmp {
+        std::vector<void**> slots;
+        void own(void** p) { slots.push_back(p); }
+        ~Tmp() { for (void** p : slots) if (*p) { cudaFree(*p); *p = nullptr; } }
+    } tmp;
+#define HZB_TMP(ptr) tmp.own((void**)&(ptr))
+
     // ---- H2D
     double t0 = now_s();
     float* d_v3 = nullptr; float* d_vs = nullptr; int32_t* d_ti = nullptr; unsigned int* d_bounds = nullptr;
+    HZB_TMP(d_v3); HZB_TMP(d_vs); HZB_TMP(d_ti); HZB_TMP(d_bounds);
     HZB_TRY(dalloc(&d_v3, nv * 3));
     HZB_TRY(dalloc(&s.d_vert4, nv));
     HZB_TRY(dalloc(&d_bounds, 6));
     HZB_TRY(dalloc(&s.d_counters, 1));
-    HZB_TRY(dalloc(&s.d_tile_counter, 4));
+    HZB_TRY(dalloc(&s.d_tile_counter, HZB_TILE_SLOTS));
     HZB_CUDA(cudaMemsetAsync(s.d_counters, 0, sizeof(Counters), st));
     HZB_CUDA(cudaMemcpyAsync(d_v3, vert_grid, nv * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     if (s.num_tin) {
@@ -426,6 +437,7 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
 
     PrimGeom g{s.d_vert4, s.d_tin4, W, s.num_quads};
     unsigned long long *d_k0 = nullptr, *d_k1 = nullptr; uint32_t *d_v0 = nullptr, *d_v1 = nullptr;
+    HZB_TMP(d_k0); HZB_TMP(d_k1); HZB_TMP(d_v0); HZB_TMP(d_v1);
     HZB_TRY(dalloc(&d_k0, n)); HZB_TRY(dalloc(&d_k1, n)); HZB_TRY(dalloc(&d_v0, n)); HZB_TRY(dalloc(&d_v1, n));
     int morton_mode = getenv("HZB_MORTON") ? atoi(getenv("HZB_MORTON")) : 2;
     if (morton_mode == 2 && s.num_tin > 0) morton_mode = 1;
@@ -436,6 +448,7 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
     const uint32_t ntiles = (n + RS_TILE - 1) / RS_TILE;
     const size_t m = (size_t)256 * ntiles;
     uint32_t *d_hist = nullptr, *d_offs = nullptr, *d_sums = nullptr;
+    HZB_TMP(d_hist); HZB_TMP(d_offs); HZB_TMP(d_sums);
     HZB_TRY(dalloc(&d_hist, m)); HZB_TRY(dalloc(&d_offs, m)); HZB_TRY(dalloc(&d_sums, (m + SC_TILE - 1) / SC_TILE + 1));
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = 8 * pass;
@@ -450,6 +463,7 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
 
     const uint32_t n_int = n > 1 ? n - 1 : 1;
     uint32_t *d_np = nullptr, *d_lp = nullptr; unsigned int* d_visit = nullptr; float* d_root = nullptr;
+    HZB_TMP(d_np); HZB_TMP(d_lp); HZB_TMP(d_visit); HZB_TMP(d_root);
     HZB_TRY(dalloc(&s.d_nodes2, n_int)); HZB_TRY(dalloc(&d_np, n_int)); HZB_TRY(dalloc(&d_lp, n));
     HZB_TRY(dalloc(&d_visit, n_int)); HZB_TRY(dalloc(&d_root, 6));
     HZB_CUDA(cudaMemsetAsync(d_visit, 0, (size_t)n_int * sizeof(unsigned int), st));
@@ -461,13 +475,10 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
     HZB_TRY(build_wide_bvh(s, st));
     s.bvh_bytes = (size_t)s.num_nodes4 * sizeof(Bvh4Node);
 
-    cudaFree(d_v3); cudaFree(d_vs); cudaFree(d_ti); cudaFree(d_bounds);
-    cudaFree(d_k0); cudaFree(d_k1); cudaFree(d_v0); cudaFree(d_v1);
-    cudaFree(d_hist); cudaFree(d_offs); cudaFree(d_sums);
-    cudaFree(d_np); cudaFree(d_lp); cudaFree(d_visit); cudaFree(d_root);
+#undef HZB_TMP
     HZB_CUDA(cudaStreamSynchronize(st));
     s.t_build = now_s() - t0;
-    return 0;
+    return 0;   // ~Tmp frees the build temporaries
 }
 
 }  // namespace hzb

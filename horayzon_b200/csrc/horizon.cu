@@ -10,11 +10,9 @@
 //
 //   k_horizon_wq6      production: search state machine + two-ray packet warp-queue
 //                      traversal of the compressed 4-wide BVH (hzb_wq2.cuh)
-//   k_horizon_wq5      first-generation single-ray step (hzb_wq.cuh; HZB_KERNEL=wq5,
-//                      kept for A/B runs and the variant parity tests)
-//   k_horizon_gridded  reference-shaped per-lane kernel on the binary BVH
-//                      (HZB_KERNEL=simple; kept for A/B runs and as a second,
-//                      structurally different implementation in the parity tests)
+//   k_horizon_gridded  reference-shaped per-lane kernel on the binary BVH: the second,
+//                      structurally different implementation the full-size parity test
+//                      compares the production kernel with (hzb_debug_option, test only)
 //   k_loc_*            arbitrary locations (closest-hit queries, binary BVH)
 #include "hzb_geom.cuh"
 #include "hzb_wq.cuh"
@@ -22,26 +20,27 @@
 #include "hzb_search.cuh"
 #include <math.h>
 #include <string.h>
-#include <stdlib.h>
+#include <algorithm>
 
 namespace hzb {
 
 // ------------------------------------------------------------ host tables
 static inline float deg2rad_f(float a) { return (float)(((double)a / 180.0) * M_PI); }  // horizon_comp.cpp:37-39
 
-void HorizonTables::make(int azim_n, float dist_km, float acc_deg, float low_deg) {
+void HorizonTables::make(int azim_n, float dist_km, float acc_deg, float low_deg, bool fill) {
     azim_num = azim_n;
     acc = deg2rad_f(acc_deg);
     low = deg2rad_f(low_deg);
     up = deg2rad_f(89.98f);                      // horizon_comp.cpp:648
     dist = (float)((double)dist_km * 1000.0);    // :670
     step = (double)acc / 5.0;
+    elev_num = (int)ceil((double)(up - low) / step) + 1;  // :721-722
+    if (!fill) return;                           // scalars only (the arrays are cached on the device)
     azim_sin.resize(azim_n); azim_cos.resize(azim_n);
     for (int i = 0; i < azim_n; ++i) {           // :714-718: float angle, float sin/cos overloads
         const float ang = (float)((2 * M_PI) / azim_n * i);
         azim_sin[i] = sinf(ang); azim_cos[i] = cosf(ang);
     }
-    elev_num = (int)ceil((double)(up - low) / step) + 1;  // :721-722
     elev_ang.resize(elev_num); elev_sin.resize(elev_num); elev_cos.resize(elev_num);
     for (int i = 0; i < elev_num; ++i) {         // :726-731: anchored at the upper limit
         const float ang = (float)((double)up - step * i);
@@ -51,29 +50,47 @@ void HorizonTables::make(int azim_n, float dist_km, float acc_deg, float low_deg
     }
 }
 
-int upload_tables(Scene& s, const HorizonTables& T, HorizonParams& p, cudaStream_t st) {
-    const size_t need = (size_t)2 * T.azim_num + (size_t)3 * T.elev_num;
-    if (need > s.tables_cap) {
-        if (s.d_tables) cudaFree(s.d_tables);
-        s.d_tables = nullptr; s.tables_cap = 0;
-        HZB_CUDA(cudaMalloc((void**)&s.d_tables, need * sizeof(float)));
-        s.tables_cap = need;
+// Device tables of one parameter set: looked up in the scene's cache, uploaded once.
+int scene_tables(Scene& s, int azim_num, float dist_km, float acc_deg, float low_deg, HorizonParams& p, cudaStream_t st) {
+    HorizonTables T;
+    const Scene::TableEntry* hit = nullptr;
+    for (const Scene::TableEntry& e : s.tables)
+        if (e.azim_num == azim_num && e.acc_deg == acc_deg && e.low_deg == low_deg && e.dist_km == dist_km) { hit = &e; break; }
+    T.make(azim_num, dist_km, acc_deg, low_deg, hit == nullptr);
+    if (T.elev_num < 2) { set_error("elevation table too small"); return 1; }
+    if (!hit) {
+        if (s.tables.size() >= 32) {   // bounded cache: drop everything once nothing can be in flight any more
+            HZB_CUDA(cudaDeviceSynchronize());
+            for (Scene::TableEntry& e : s.tables) cudaFree(e.d);
+            s.tables.clear();
+        }
+        const size_t need = (size_t)2 * T.azim_num + (size_t)3 * T.elev_num;
+        std::vector<float> h(need);
+        float* q = h.data();
+        memcpy(q, T.azim_sin.data(), 4 * (size_t)T.azim_num); q += T.azim_num;
+        memcpy(q, T.azim_cos.data(), 4 * (size_t)T.azim_num); q += T.azim_num;
+        memcpy(q, T.elev_ang.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
+        memcpy(q, T.elev_sin.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
+        memcpy(q, T.elev_cos.data(), 4 * (size_t)T.elev_num);
+        Scene::TableEntry e{azim_num, acc_deg, low_deg, dist_km, nullptr, T.elev_num};
+        HZB_CUDA(cudaMalloc((void**)&e.d, need * sizeof(float)));
+        // pageable source: the call returns once the data has left `h` (first use of a parameter set only)
+        if (cudaMemcpyAsync(e.d, h.data(), need * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(e.d); set_error("table upload failed"); cudaGetLastError(); return 1; }
+        s.tables.push_back(e);
+        hit = &s.tables.back();
     }
-    std::vector<float> h(need);
-    float* q = h.data();
-    memcpy(q, T.azim_sin.data(), 4 * (size_t)T.azim_num); q += T.azim_num;
-    memcpy(q, T.azim_cos.data(), 4 * (size_t)T.azim_num); q += T.azim_num;
-    memcpy(q, T.elev_ang.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
-    memcpy(q, T.elev_sin.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
-    memcpy(q, T.elev_cos.data(), 4 * (size_t)T.elev_num);
-    // synchronous copy from pageable memory: the host vector may die afterwards
-    HZB_CUDA(cudaMemcpyAsync(s.d_tables, h.data(), need * sizeof(float), cudaMemcpyHostToDevice, st));
-    HZB_CUDA(cudaStreamSynchronize(st));
-    p.azim_sin = s.d_tables; p.azim_cos = p.azim_sin + T.azim_num;
-    p.elev_ang = p.azim_cos + T.azim_num; p.elev_sin = p.elev_ang + T.elev_num; p.elev_cos = p.elev_sin + T.elev_num;
-    p.azim_num = T.azim_num; p.elev_num = T.elev_num;
+    p.azim_sin = hit->d; p.azim_cos = p.azim_sin + azim_num;
+    p.elev_ang = p.azim_cos + azim_num; p.elev_sin = p.elev_ang + T.elev_num; p.elev_cos = p.elev_sin + T.elev_num;
+    p.azim_num = azim_num; p.elev_num = T.elev_num;
     p.acc = T.acc; p.low = T.low; p.up = T.up; p.dist = T.dist; p.step = T.step;
     return 0;
+}
+
+unsigned int* scene_tile_counter(Scene& s, cudaStream_t st) {
+    unsigned int* c = s.d_tile_counter + (s.tile_slot++ % HZB_TILE_SLOTS);
+    if (cudaMemsetAsync(c, 0, sizeof(unsigned int), st) != cudaSuccess) { set_error("work-queue reset failed"); cudaGetLastError(); return nullptr; }
+    return c;
 }
 
 // ------------------------------------------------------------ device side
@@ -202,6 +219,23 @@ __device__ __forceinline__ void flush_counters(LaneCounters& cnt, unsigned int u
     cnt.rays = cnt.nodes = cnt.prims = 0;
 }
 
+// A finished cell (or empty cell slot) of row block `blk`: its outputs are made visible system-wide, the
+// block's counter goes up, and the lane that completes the block raises the block's flag in mapped host
+// memory -- the host tier polls those flags and copies finished blocks while the kernel is still running.
+__device__ __forceinline__ void publish_cell(const HorizonParams& p, int blk) {
+    __threadfence_system();
+    if (atomicAdd(p.row_done + blk, 1u) == p.row_full - 1u && p.row_flags) {
+        __threadfence_system();
+        p.row_flags[blk] = 1u;
+    }
+}
+
+// 4-row blocks of this launch: those blocks b of the row range with b % blk_stride == blk_offset
+__device__ __forceinline__ int local_blocks(const HorizonParams& p, int rows) {
+    const int all = (rows + 3) >> 2;
+    return all > p.blk_offset ? (all - p.blk_offset + p.blk_stride - 1) / p.blk_stride : 0;
+}
+
 constexpr int HG_THREADS = 128;
 
 template <int ALG>
@@ -210,7 +244,7 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
     const Search s = make_search(sv, p, counters);
     const int lane = threadIdx.x & 31;
     const int rows = p.row_end - p.row_begin;
-    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = local_blocks(p, rows);
     const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
@@ -220,11 +254,11 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= num_tiles) break;
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-        const int i = p.row_begin + ty * 4 + (lane >> 3), j = tx * 8 + (lane & 7);
+        const int i = p.row_begin + (ty * p.blk_stride + p.blk_offset) * 4 + (lane >> 3), j = tx * 8 + (lane & 7);
         unsigned int units = 0;
         if (i < p.row_end && j < p.dim_in_1) {
             const size_t c = (size_t)i * p.dim_in_1 + j;
-            float* out = p.hori + c * p.stride_c;
+            float* out = p.hori + (p.packed ? (size_t)(ty * 4 + (lane >> 3)) * p.dim_in_1 + j : c) * p.stride_c;
             if (p.mask[c] == 1) {
                 const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
                 const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
@@ -243,118 +277,21 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
 
 
 // ===========================================================================
-// k_horizon_wq5: first-generation kernel (HZB_KERNEL=wq5).  Per-lane search state machine (sm_advance)
-// + the shared warp-queue traversal step of hzb_wq.cuh.
-// ===========================================================================
-template <int ALG, bool TOPS>
-__global__ void __launch_bounds__(WQ_BLOCK, 6) k_horizon_wq5(SceneView sv, HorizonParams p, Counters* counters,
-                                                             unsigned int* tile_counter, int refill_thr, int wait_thr) {
-    __shared__ WqShared sh;
-    __shared__ __align__(128) uint4 top_nodes[TOPS ? WQ_TOP_NODES * 4 : 4];
-    __shared__ __align__(8) unsigned long long top_mbar;
-    const unsigned int n_top = TOPS ? min((unsigned int)WQ_TOP_NODES, sv.num_nodes4) : 0u;
-    if (TOPS) wq_tma_stage_top(top_nodes, sv.nodes4, n_top, &top_mbar);
-    const Search s = make_search(sv, p, counters);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
-    const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
-    const int rows = p.row_end - p.row_begin;
-    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
-    const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
-    const bool vec = (p.azim_num & 3) == 0 && ((reinterpret_cast<size_t>(p.hori) & 15) == 0);
-    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
-    unsigned int units = 0;
-    if (lane == 0) sh.hitmask[warp] = 0u;
-    WqWarp W; W.pushed = 0; W.tested = 0;
-    __syncwarp();
-
-    // warp-uniform work source: cells of the current 8x4 tile are handed to lanes one by
-    // one; when the tile is used up the warp pulls the next tile from the global queue
-    unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
-    // per-lane cell and search state
-    LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
-    m.spec_ie = -1; m.spec_hit = false;
-    Frame f; OutBuf ob; ob.init(nullptr, false);
-    bool has_cell = false, have_result = false;
-    int my_ty = 0;
-    WqLane L; L.state = 0; L.hit = false; L.queued = false; L.node = WQ_NONE; L.sp = 0; L.my_last = 0;
-    L.Ax = L.Ay = L.Az = L.Bx = L.By = L.Bz = 0.f; L.selnx = L.selny = L.selnz = 0x7410u;
-
-    while (true) {
-        // (A) hand out cells to lanes that have none
-        while (true) {
-            const bool want = !has_cell;
-            const unsigned int wmask = __ballot_sync(FULL, want);
-            if (wmask == 0u) break;
-            if (next_cell >= 32) {
-                if (!more_tiles) break;
-                unsigned int t = 0;
-                if (lane == 0) t = atomicAdd(tile_counter, 1u);
-                t = __shfl_sync(FULL, t, 0);
-                if (t >= num_tiles) { more_tiles = false; break; }
-                cur_tile = t; next_cell = 0;
-            }
-            const int mine = next_cell + __popc(wmask & lt_mask);
-            next_cell += __popc(wmask);
-            if (want && mine < 32) {
-                const int ty = cur_tile / tiles_x, tx = cur_tile - ty * tiles_x;
-                const int ci = p.row_begin + ty * 4 + (mine >> 3), cj = tx * 8 + (mine & 7);
-                bool done_now = true;
-                if (ci < p.row_end && cj < p.dim_in_1) {
-                    const size_t c = (size_t)ci * p.dim_in_1 + cj;
-                    float* out = p.hori + c * p.stride_c;
-                    if (p.mask[c] == 1) {
-                        const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
-                        const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
-                        const float4 v = sv.vert4[(size_t)(ci + p.offset_0) * sv.W + (cj + p.offset_1)];
-                        f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
-                        ob.init(out, vec, true, p.stride_k);
-                        m.phase = 0; m.k = 0;
-                        has_cell = true; have_result = false; my_ty = ty; units += p.azim_num;
-                        done_now = false;
-                    } else {
-                        for (int k = 0; k < p.azim_num; ++k) out[k * p.stride_k] = p.hori_fill;  // horizon_comp.cpp:789-794
-                    }
-                }
-                if (done_now && p.row_done) { __threadfence_system(); atomicAdd(p.row_done + ty, 1u); }
-            }
-        }
-        // (B) lanes with a cell but no ray in flight advance their search
-        bool finished_cell = false;
-        if (has_cell && L.state == 0) {
-            int ie, lo_ie; unsigned int extra = 0;
-            if (sm_advance<ALG, false, OutBuf>(s, m, have_result, L.hit, ob, ie, lo_ie, extra)) {
-                wq_start_ray(sv, sh, warp, lane, L, f.org, ray_dir(s, f, ie, m.k));
-                have_result = true; cnt.rays++;
-            } else {
-                has_cell = false; finished_cell = true;
-                if (p.row_done) { __threadfence_system(); atomicAdd(p.row_done + my_ty, 1u); }  // this cell's outputs are visible
-            }
-        }
-        if (__any_sync(FULL, finished_cell) && (more_tiles || next_cell < 32)) continue;   // give them a new cell first
-        const unsigned int cell_mask = __ballot_sync(FULL, has_cell);
-        if (cell_mask == 0u) break;
-        const int thr = min(refill_thr, __popc(cell_mask));
-        __syncwarp();
-        // (C) shared traversal loop
-        while (__popc(wq_step<TOPS>(sv, sh, top_nodes, n_top, warp, lane, tid, L, W, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
-    }
-    flush_counters(cnt, units, counters);
-}
-
-// ===========================================================================
-// k_horizon_wq6: production kernel.  Same work distribution and search state
-// machine as k_horizon_wq5, on the two-ray packet traversal of hzb_wq2.cuh: the
-// casts at prev+5 and prev-5 of a guess_constant azimuth share one traversal.
+// k_horizon_wq6: production kernel.  Persistent warps pull 8x4-cell tiles from an atomic
+// queue; every lane runs the search state machine of hzb_search.cuh for its cell on the
+// two-ray packet traversal of hzb_wq2.cuh: the casts at prev+5 and prev-5 of a
+// guess_constant azimuth share one traversal.
 // ===========================================================================
 template <int ALG, int MINB>
 __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, HorizonParams p, Counters* counters,
-                                                                unsigned int* tile_counter, int refill_thr, int wait_thr) {
+                                                                unsigned int* tile_counter, int refill_thr, int wait_thr,
+                                                                int stack_lim) {
     __shared__ Wq2Shared sh;
     const Search s = make_search(sv, p, counters);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     const int rows = p.row_end - p.row_begin;
-    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = (rows + 3) >> 2;
+    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = local_blocks(p, rows);
     const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
     unsigned int units = 0;
@@ -390,11 +327,11 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
             next_cell += __popc(wmask);
             if (want && mine < 32) {
                 const int ty = cur_tile / tiles_x, tx = cur_tile - ty * tiles_x;
-                const int ci = p.row_begin + ty * 4 + (mine >> 3), cj = tx * 8 + (mine & 7);
+                const int ci = p.row_begin + (ty * p.blk_stride + p.blk_offset) * 4 + (mine >> 3), cj = tx * 8 + (mine & 7);
                 bool done_now = true;
                 if (ci < p.row_end && cj < p.dim_in_1) {
                     const size_t c = (size_t)ci * p.dim_in_1 + cj;
-                    float* out = p.hori + c * p.stride_c;
+                    float* out = p.hori + (p.packed ? (size_t)(ty * 4 + (mine >> 3)) * p.dim_in_1 + cj : c) * p.stride_c;
                     if (p.mask[c] == 1) {
                         my_cell = ((unsigned int)ci << 16) | (unsigned int)cj;    // dims <= 32767 (horizon.pyx:149-151)
                         ob.init(out, false, true, p.stride_k);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
@@ -405,7 +342,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                         for (int k = 0; k < p.azim_num; ++k) out[k * p.stride_k] = p.hori_fill;  // horizon_comp.cpp:789-794
                     }
                 }
-                if (done_now && p.row_done) { __threadfence_system(); atomicAdd(p.row_done + ty, 1u); }
+                if (done_now && p.row_done) publish_cell(p, ty);
             }
         }
         // (B) lanes with a cell but no packet in flight advance their search; the ray set-up
@@ -413,13 +350,17 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         bool finished_cell = false, need_ray = false;
         int ie = 0, lo_ie = -1;
         if (has_cell && L.state == 0) {
+            if (L.node == WQ_OVF) {   // the packet's stack was full: decided by the binary-BVH walker instead (same decisions)
+                const unsigned int hb = HZB_WQ2_RECAST(sv, &sh.ray[warp][0][lane], s.dist, m.spec_ie >= 0 ? 1 : 0, counters);
+                L.hit1 = hb & 1u; L.hit2 = hb & 2u; L.node = WQ_NONE;
+            }
             unsigned int extra = 0;
             m.spec_hit = L.hit2;
             need_ray = sm_advance<ALG, true, OutBuf>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
             cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
                 has_cell = false; finished_cell = true;
-                if (p.row_done) { __threadfence_system(); atomicAdd(p.row_done + (((int)(my_cell >> 16) - p.row_begin) >> 2), 1u); }  // this cell's outputs are visible
+                if (p.row_done) publish_cell(p, ((int)(my_cell >> 16) - p.row_begin) >> 2);   // (row_done is only used unsharded: block == local block)
             }
         }
         __syncwarp();
@@ -443,7 +384,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         const int thr = min(refill_thr, __popc(cell_mask));
         __syncwarp();
         // (C) shared traversal loop
-        while (__popc(wq2_step<true, false>(sv, sh, warp, lane, tid, L, pend_est, s.dist, wait_thr, cnt, s.overflow)) >= thr) {}
+        while (__popc(wq2_step<true, false>(sv, sh, warp, lane, tid, L, pend_est, s.dist, wait_thr, cnt, stack_lim)) >= thr) {}
     }
     flush_counters(cnt, units, counters);
 }
@@ -542,46 +483,26 @@ __global__ void k_loc_dist_fix(LocationParams lp, int azim_num, const float4* or
 
 int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
     if (p.row_end <= p.row_begin || p.dim_in_1 <= 0) return 0;
-    HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
+    unsigned int* tile_counter = scene_tile_counter(s, st);
+    if (!tile_counter) return 1;
     const SceneView sv = s.view();
-    const char* kern_env = getenv("HZB_KERNEL");   // "simple": reference-shaped per-lane kernel on the binary BVH (A/B, tests)
-    if (kern_env && !strcmp(kern_env, "simple")) {
+    const DebugOptions& o = debug_options();
+    if (o.horizon_kernel == 1) {   // reference-shaped per-lane kernel on the binary BVH (second implementation for the parity tests)
         const int grid = sm_count() * 8;
         switch (p.algorithm) {
-            case 0: k_horizon_gridded<0><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
-            case 1: k_horizon_gridded<1><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
-            default: k_horizon_gridded<2><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter); break;
+            case 0: k_horizon_gridded<0><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, tile_counter); break;
+            case 1: k_horizon_gridded<1><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, tile_counter); break;
+            default: k_horizon_gridded<2><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, tile_counter); break;
         }
-    } else if (!(kern_env && !strcmp(kern_env, "wq5"))) {
-        const int w_refill = getenv("HZB_WREFILL") ? atoi(getenv("HZB_WREFILL")) : 24;   // refill when fewer lanes hold a packet
-        const int w_wait = getenv("HZB_WWAIT") ? atoi(getenv("HZB_WWAIT")) : 2;          // flush the lists when this many lanes wait
-        const int minb = getenv("HZB_MINB") ? atoi(getenv("HZB_MINB")) : 5;
-#define HZB_LAUNCH6(ALG_, MB_) k_horizon_wq6<ALG_, MB_><<<sm_count() * MB_, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait)
-        if (minb >= 6) {
-            switch (p.algorithm) { case 0: HZB_LAUNCH6(0, 6); break; case 1: HZB_LAUNCH6(1, 6); break; default: HZB_LAUNCH6(2, 6); break; }
-        } else if (minb == 5) {
-            switch (p.algorithm) { case 0: HZB_LAUNCH6(0, 5); break; case 1: HZB_LAUNCH6(1, 5); break; default: HZB_LAUNCH6(2, 5); break; }
-        } else {
-            switch (p.algorithm) { case 0: HZB_LAUNCH6(0, 4); break; case 1: HZB_LAUNCH6(1, 4); break; default: HZB_LAUNCH6(2, 4); break; }
-        }
-#undef HZB_LAUNCH6
     } else {
-        const int w_refill = getenv("HZB_WREFILL") ? atoi(getenv("HZB_WREFILL")) : 24;   // refill when fewer lanes hold a ray
-        const int w_wait = getenv("HZB_WWAIT") ? atoi(getenv("HZB_WWAIT")) : 6;          // flush the ring when this many lanes wait
-        const bool tops = getenv("HZB_TOPSMEM") && atoi(getenv("HZB_TOPSMEM")) != 0;     // TMA-staged top levels (3 % slower)
-        const int grid = sm_count() * 6;
-        if (tops) {
-            switch (p.algorithm) {
-                case 0: k_horizon_wq5<0, true><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
-                case 1: k_horizon_wq5<1, true><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
-                default: k_horizon_wq5<2, true><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
-            }
-        } else {
-            switch (p.algorithm) {
-                case 0: k_horizon_wq5<0, false><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
-                case 1: k_horizon_wq5<1, false><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
-                default: k_horizon_wq5<2, false><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, s.d_tile_counter, w_refill, w_wait); break;
-            }
+        // a warp leaves the traversal loop to refill when fewer than w_refill lanes hold a packet; pending
+        // candidates are flushed when w_wait lanes wait on theirs (tuned on B200)
+        const int w_refill = o.wrefill, w_wait = o.wwait, stack_lim = std::max(1, std::min(o.stack_limit, WQ_STACK_N));
+        constexpr int MB = 5;   // resident CTAs per SM (93 registers, 31 KB shared memory)
+        switch (p.algorithm) {
+            case 0: k_horizon_wq6<0, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+            case 1: k_horizon_wq6<1, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+            default: k_horizon_wq6<2, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
         }
     }
     HZB_CUDA(cudaGetLastError());
@@ -590,8 +511,9 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
 
 int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationParams& lp, cudaStream_t st) {
     if (lp.num_loc <= 0) return 0;
-    float4* d_org = nullptr;
-    HZB_CUDA(cudaMalloc((void**)&d_org, (size_t)lp.num_loc * sizeof(float4)));
+    float4* d_org = (float4*)pool_alloc((size_t)lp.num_loc * sizeof(float4));
+    if (!d_org) return 1;
+    struct OrgGuard { float4* p; ~OrgGuard() { pool_free(p); } } org_guard{d_org};
     const SceneView sv = s.view();
     const int nb_loc = (lp.num_loc + 63) / 64;
     k_loc_snap<<<nb_loc, 64, 0, st>>>(sv, lp, d_org, s.d_counters);
@@ -611,7 +533,6 @@ int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationPar
     }
     HZB_CUDA(cudaGetLastError());
     HZB_CUDA(cudaStreamSynchronize(st));
-    cudaFree(d_org);
     return 0;
 }
 

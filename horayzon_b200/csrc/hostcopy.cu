@@ -195,7 +195,7 @@ int staged_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s
 // The wrappers allocate the arrays they return; backing the big ones (the 2 GB horizon
 // array) with page-locked memory lets the finished row blocks leave by plain DMA while the
 // kernel runs and lets sky_view_factor read them back by DMA.  Page-locking 2 GB costs a
-// few 100 ms, so freed blocks are kept (at most two) and handed out again.
+// few 100 ms, so ONE freed block (of at most 4 GB) is kept and handed out again.
 namespace {
 struct PinPool {
     std::mutex mu;
@@ -231,12 +231,20 @@ void host_block_free(void* p) {
         if (P.live[i].p == p) {
             P.free_blocks.push_back(P.live[i]);
             P.live.erase(P.live.begin() + i);
-            while (P.free_blocks.size() > 2) {          // bound the idle page-locked memory: drop the oldest
+            // bound the idle page-locked memory: one block of at most 4 GB stays (hzb_trim() releases it too)
+            while (P.free_blocks.size() > 1 || (!P.free_blocks.empty() && P.free_blocks[0].cap > ((size_t)4 << 30))) {
                 if (cudaFreeHost(P.free_blocks[0].p) != cudaSuccess) cudaGetLastError();
                 P.free_blocks.erase(P.free_blocks.begin());
             }
             return;
         }
+}
+
+void host_block_trim() {
+    PinPool& P = pin_pool();
+    std::lock_guard<std::mutex> l(P.mu);
+    for (PinPool::Blk& b : P.free_blocks) if (cudaFreeHost(b.p) != cudaSuccess) cudaGetLastError();
+    P.free_blocks.clear();
 }
 
 bool host_is_pinned(const void* p) {

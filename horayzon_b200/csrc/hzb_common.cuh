@@ -67,8 +67,22 @@ struct SceneView {
 };
 
 struct Counters {  // device-side accumulators (one struct per scene / terrain)
-    unsigned long long rays, node_visits, prim_tests, units, warp_node_visits, stack_overflow;
+    unsigned long long rays, node_visits, prim_tests, units, warp_node_visits;
+    unsigned long long stack_overflow;     // binary-BVH walker ran out of its 96-entry stack (results invalid: reported as an error)
+    unsigned long long fallback_packets;   // packets re-decided by the binary-BVH walker after a full shared-memory stack (informational)
 };
+
+// Test-only switches (hzb_debug_option): second implementations and tuning knobs the parity tests
+// and A/B runs select explicitly.  Production code never changes them; no environment variable does.
+struct DebugOptions {
+    int horizon_kernel = 0;   // 0 production packet kernel, 1 reference-shaped per-lane kernel on the binary BVH
+    int shadow_kernel = 0;    // 0 production, 1 reference-shaped per-lane kernel, 2 production step with nearest-first order
+    int wrefill = 24, wwait = 2;
+    int no_overlap = 0;       // host tier: copy the horizon array after the kernel instead of while it runs
+    int stack_limit = 36;     // <= WQ_STACK_N; lowered by the tests to force the full-stack fallback
+    int horizon_variant = 0;  // A/B experiments inside the production kernel family
+};
+DebugOptions& debug_options();
 
 // ------------------------------------------------------------------- scene
 struct Scene {
@@ -82,13 +96,18 @@ struct Scene {
     float qorg[3] = {0, 0, 0}, qstep[3] = {1, 1, 1};
     uint32_t* d_prim_ids = nullptr;
     Counters* d_counters = nullptr;
+    // Work-queue counters: a ring of HZB_TILE_SLOTS words, one per launch in flight, so that launches on
+    // different streams against the same scene never share (or reset) each other's queue.
     unsigned int* d_tile_counter = nullptr;
+    unsigned int tile_slot = 0;
     float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}, pad = 0.f;
     double t_h2d = 0, t_build = 0;
     size_t bvh_bytes = 0;
-    // cached per-call device tables (elevation / azimuth)
-    float* d_tables = nullptr;
-    size_t tables_cap = 0;
+    // Device trig / elevation tables, cached per parameter set (azim_num, hori_acc, low limit, dist): an entry is
+    // written once and never overwritten, so kernels in flight on other streams keep valid tables and a repeated
+    // call uploads nothing (no stream synchronisation on the launch path).
+    struct TableEntry { int azim_num; float acc_deg, low_deg, dist_km; float* d; int elev_num; };
+    std::vector<TableEntry> tables;
     SceneView view() const {
         SceneView v;
         v.vert4 = d_vert4; v.tin4 = d_tin4; v.nodes2 = d_nodes2; v.nodes4 = d_nodes4;
@@ -111,7 +130,7 @@ struct HorizonTables {  // host copies; built exactly like horizon_comp.cpp:711-
     float acc = 0, low = 0, up = 0, dist = 0;
     double step = 0;  // (double)acc / 5.0
     std::vector<float> azim_sin, azim_cos, elev_ang, elev_sin, elev_cos;
-    void make(int azim_num, float dist_km, float acc_deg, float low_deg);
+    void make(int azim_num, float dist_km, float acc_deg, float low_deg, bool fill = true);
 };
 
 struct HorizonParams {
@@ -125,10 +144,16 @@ struct HorizonParams {
     const float* vec_norm; const float* vec_north; const uint8_t* mask;
     int offset_0, offset_1, dim_in_0, dim_in_1, row_begin, row_end;
     float hori_fill, ray_org_elev;
+    // Block sharding (multi-GPU, cost-balanced): of the 4-row blocks of [row_begin, row_end) this launch computes
+    // those with (block % blk_stride) == blk_offset; (1, 0) = all of them.  packed != 0: the launch's blocks are
+    // stored back to back ([local block][4][dim_in_1][azim]) from `hori` on -- a contiguous all-gather send buffer.
+    int blk_stride, blk_offset, packed;
     float* hori;
     long long stride_c, stride_k;   // element (cell c, azimuth k) lives at hori[c * stride_c + k * stride_k]: (K, 1) = the reference's
                                     // [y][x][azim] layout, (1, cells) = azimuth-first [azim][y][x] (scope row "next 4")
     unsigned int* row_done;  // optional [ceil(rows/4)]: +1 per finished cell slot of that row block, 32 per 8x4 tile (host overlaps D2H)
+    volatile unsigned int* row_flags;  // optional, MAPPED HOST memory [ceil(rows/4)]: set to 1 by the lane that completes a row block
+    unsigned int row_full;   // cell slots per row block (32 per tile)
 };
 
 int parse_algorithm(const char* s);  // -1 if unknown
@@ -141,7 +166,9 @@ struct LocationParams {
     float* hori; float* hori_dist; int num_loc; int hori_dist_out;
 };
 int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationParams& lp, cudaStream_t st);
-int upload_tables(Scene& s, const HorizonTables& T, HorizonParams& p, cudaStream_t st);
+int scene_tables(Scene& s, int azim_num, float dist_km, float acc_deg, float low_deg, HorizonParams& p, cudaStream_t st);
+unsigned int* scene_tile_counter(Scene& s, cudaStream_t st);   // fresh (zeroed on `st`) work-queue counter for one launch
+constexpr unsigned int HZB_TILE_SLOTS = 64;
 
 // shadow.cu
 struct TerrainParams {
@@ -184,7 +211,13 @@ int staged_h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t s
 
 void* host_block_alloc(size_t bytes);      // pooled page-locked block for a large output array (nullptr: not available)
 void host_block_free(void* p);
+void host_block_trim();                    // release the idle page-locked blocks
 bool host_is_pinned(const void* p);       // page-locked (ours or cudaHostRegister'ed by the caller)
+
+// api.cu: pooled device buffers of the host tier
+void* pool_alloc(size_t bytes);            // nullptr + error set on failure
+void pool_free(void* p);
+void pool_trim();
 
 // number of SMs of the current device (cached)
 int sm_count();

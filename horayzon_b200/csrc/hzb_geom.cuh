@@ -73,26 +73,6 @@ __device__ __forceinline__ bool slab(const float* lo, const float* hi, F3 O, Ray
 
 struct LaneCounters { unsigned int rays, nodes, prims; };
 
-// Slab test of one child of a compressed 4-wide node (16-bit planes on the
-// scene grid): PRMT places the 16-bit plane into the mantissa of 2^23, the FADD
-// removes the bias exactly, t = q*A + B with A = qstep/d, B = (qorg - O)/d.
-__device__ __forceinline__ void wide_child_test(const uint4 r, unsigned int selnx, unsigned int selny, unsigned int selnz,
-                                                float Ax, float Ay, float Az, float Bx, float By, float Bz, float tfar,
-                                                float& tmin, bool& hit) {
-    const float M = 8388608.0f;
-    const float qnx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selnx)) - M;
-    const float qfx = __uint_as_float(__byte_perm(r.x, 0x4B000000u, selnx ^ 0x0022u)) - M;
-    const float qny = __uint_as_float(__byte_perm(r.y, 0x4B000000u, selny)) - M;
-    const float qfy = __uint_as_float(__byte_perm(r.y, 0x4B000000u, selny ^ 0x0022u)) - M;
-    const float qnz = __uint_as_float(__byte_perm(r.z, 0x4B000000u, selnz)) - M;
-    const float qfz = __uint_as_float(__byte_perm(r.z, 0x4B000000u, selnz ^ 0x0022u)) - M;
-    tmin = fmaxf(fmaxf(fmaf(qnx, Ax, Bx), fmaf(qny, Ay, By)), fmaxf(fmaf(qnz, Az, Bz), 0.0f));
-    const float tmax = fminf(fminf(fmaf(qfx, Ax, Bx), fmaf(qfy, Ay, By)), fminf(fmaf(qfz, Az, Bz), tfar));
-    hit = (tmin <= tmax * 1.000001f) && (r.w != WIDE_EMPTY);
-}
-
-
-
 // --------------------------------------------------- BVH2 per-thread trace
 constexpr int HZB_STACK2 = 96;
 

@@ -52,6 +52,28 @@ __device__ __forceinline__ bool wq2_start(const SceneView& sv, Wq2Shared& sh, in
     return same;
 }
 
+constexpr uint32_t WQ_OVF = 0xFFFFFFFEu;   // L.node of a packet that retired because its stack was full
+
+// Fallback for a packet whose shared-memory stack was full: both rays are decided by the per-lane
+// walker of the binary BVH (96-entry local stack), which tests the same primitives with the same
+// tri_hit -- identical decisions.  Deliberately not inlined: it must not cost the traversal loop registers.
+static __device__ __noinline__ unsigned int wq2_overflow_recast(const SceneView sv, float ox, float oy, float oz, float d1x, float d1y,
+                                                                float d1z, float d2x, float d2y, float d2z, float tfar, int two,
+                                                                Counters* counters) {
+    // everything by value: taking the address of the caller's lane state would move it to local memory
+    LaneCounters c; c.rays = c.nodes = c.prims = 0;
+    unsigned int* ovf2 = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
+    float t = tfar;
+    const bool h1 = trace_bvh2<false>(sv, f3(ox, oy, oz), f3(d1x, d1y, d1z), t, c, ovf2);
+    bool h2 = h1;
+    if (two) { t = tfar; h2 = trace_bvh2<false>(sv, f3(ox, oy, oz), f3(d2x, d2y, d2z), t, c, ovf2); }
+    atomicAdd(&counters->fallback_packets, 1ull);
+    return (h1 ? 1u : 0u) | (h2 ? 2u : 0u);
+}
+// ray = &sh.ray[warp][0][lane]
+#define HZB_WQ2_RECAST(sv, ray, tfar, two, counters) \
+    wq2_overflow_recast(sv, (ray)[0], (ray)[32], (ray)[64], (ray)[96], (ray)[128], (ray)[160], (ray)[192], (ray)[224], (ray)[256], tfar, two, counters)
+
 // Same decisions as prim_hit<false>(.., D1, ..) and (TWO) prim_hit<false>(.., D2, ..).
 template <bool TWO>
 __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 O, F3 D1, F3 D2, float tfar, bool& h1, bool& h2) {
@@ -101,10 +123,14 @@ __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 
 // the number of pending candidates.  Returns the ballot of lanes that still own a packet.
 // TWO: both rays of the packet are live (horizon search); otherwise ray 1 only (shadow).
 // SORT: nearest hit child first (pays off for single any-hit rays that are often occluded).
+//
+// A full stack never invalidates a result: the lane stops its walk, drops its pending candidates and
+// retires with L.node == WQ_OVF; the caller then decides that packet with the per-lane binary-BVH
+// walker (wq2_overflow_recast).  stack_lim <= WQ_STACK_N (the tests lower it to force that path).
 template <bool TWO, bool SORT>
 __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared& sh, const int warp, const int lane, const int tid,
                                                  Wq2Lane& L, unsigned int& pend_est, const float tfar, const int wait_thr,
-                                                 LaneCounters& cnt, unsigned int* overflow) {
+                                                 LaneCounters& cnt, const int stack_lim) {
     const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     // ---- 1. node step (all lanes; lanes without a traversing packet read the root and are masked)
     const bool trav = L.state == 1;
@@ -131,8 +157,8 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
         const uint32_t firstc = (first & 1u) ? r0.w : ((first & 2u) ? r1.w : ((first & 4u) ? r2.w : r3.w));
         const unsigned int others = im & ~first;
         int sp = L.sp;
-        if (sp + 3 > WQ_STACK_N) { if (others) atomicAdd(overflow, 1u); }
-        else {
+        const bool full = others != 0u && sp + 3 > stack_lim;
+        if (!full) {
             if (others & 1u) { sh.stack[sp][tid] = r0.w; ++sp; }
             if (others & 2u) { sh.stack[sp][tid] = r1.w; ++sp; }
             if (others & 4u) { sh.stack[sp][tid] = r2.w; ++sp; }
@@ -146,6 +172,7 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
             }
             L.sp = sp; L.node = next;
             if (next == WQ_NONE) L.state = 2;
+            if (full) { L.node = WQ_OVF; L.state = 2; L.pc = 0; lf0 = lf1 = lf2 = lf3 = false; }
         }
     } else {
         // Children in slot order with three running values: the next node (first hit internal child), the
@@ -170,11 +197,12 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
 #undef HZB_WQ2_CHILD
         lf0 = pc != L.pc; lf1 = lf2 = lf3 = false;
         L.pc = pc;
-        if (sp > WQ_STACK_N) { atomicAdd(overflow, 1u); sp = WQ_STACK_N; }     // results invalid, reported through the counter
         if (trav) {
+            const bool full = sp > stack_lim;            // the three spare rows took this step's pushes
             if (next == WQ_NONE && sp > 0) { --sp; next = sh.stack[sp][tid]; }
             L.sp = sp; L.node = next;
             if (next == WQ_NONE) L.state = 2;
+            if (full) { L.node = WQ_OVF; L.state = 2; L.pc = 0; lf0 = false; }   // decided by the caller's fallback
         }
     }
     // ---- 2. leaf hits -> the lane's own pending list (room for 4 is guaranteed by the flush rule); the

@@ -7,11 +7,9 @@
 // refraction branch evaluates the libm calls in double and rounds once (the
 // closest available stand-in for glibc's float functions).
 #include "hzb_geom.cuh"
-#include "hzb_wq.cuh"
 #include "hzb_wq2.cuh"
 #include <math.h>
-#include <stdlib.h>
-#include <string.h>
+#include <algorithm>
 
 namespace hzb {
 namespace {
@@ -110,10 +108,11 @@ __global__ void __launch_bounds__(128) k_terrain(SceneView sv, TerrainParams tp,
 
 // ---------------------------------------------------------------------------
 // Production kernel: persistent warps, one lane per cell, the shared warp-queue
-// traversal of the compressed 4-wide BVH (hzb_wq.cuh): lanes refill with the
+// traversal of the compressed 4-wide BVH (hzb_wq2.cuh): lanes refill with the
 // next cell of the warp's block as soon as their ray retires; leaf candidates
 // of all lanes are tested 32 at a time.  (k_terrain above is the reference-
-// shaped per-lane kernel on the binary BVH, HZB_SHADOW_KERNEL=simple.)
+// shaped per-lane kernel on the binary BVH: second implementation for the
+// parity tests, hzb_debug_option("shadow_kernel", 1).)
 // ---------------------------------------------------------------------------
 constexpr int TW_BLOCK = 512;   // cells per warp work block
 
@@ -154,93 +153,13 @@ __device__ __forceinline__ bool terrain_cell_setup(const SceneView& sv, const Te
     return dts > dot_min;
 }
 
-template <bool SW>
-__global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq(SceneView sv, TerrainParams tp, float sunx, float suny, float sunz,
-                                                            uint8_t* __restrict__ shadow, float* __restrict__ swc,
-                                                            Counters* counters, unsigned int* block_counter, int refill_thr,
-                                                            int wait_thr) {
-    __shared__ WqShared sh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
-    const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
-    const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
-    const unsigned int num_blocks = (unsigned int)((ncell + TW_BLOCK - 1) / TW_BLOCK);
-    const float dot_min = SW ? tp.dot_prod_min : 0.0f;
-    const float tfar = INFINITY;   // shadow_comp.cpp:462, 572
-    unsigned int* overflow = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
-    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
-    unsigned int units = 0;
-    if (lane == 0) sh.hitmask[warp] = 0u;
-    WqWarp W; W.pushed = 0; W.tested = 0;
-    __syncwarp();
-
-    long long next = 0, end = 0;          // warp-uniform: unassigned cells of the current block
-    bool more_blocks = true;
-    long long cell = -1; float dts = 0.f, dns = 0.f;
-    WqLane L; L.state = 0; L.hit = false; L.queued = false; L.node = WQ_NONE; L.sp = 0; L.my_last = 0;
-    L.Ax = L.Ay = L.Az = L.Bx = L.By = L.Bz = 0.f; L.selnx = L.selny = L.selnz = 0x7410u;
-
-    while (true) {
-        // (1) retire finished rays (shadow_comp.cpp:468-472 / 578-586) and hand out new cells
-        if (cell >= 0 && L.state == 0) {
-            if (SW) {
-                if (L.hit) swc[cell] = 0.0f;
-                else { if (dns < dot_min) dns = dot_min; swc[cell] = __fmul_rn(__fdiv_rn(dts, dns), tp.surf_enl_fac[cell]); }
-            } else shadow[cell] = L.hit ? 2 : 0;
-            cell = -1;
-        }
-        while (true) {
-            const bool want = L.state == 0;
-            const unsigned int wmask = __ballot_sync(FULL, want);
-            if (wmask == 0u) break;
-            if (next >= end) {
-                if (!more_blocks) break;
-                unsigned int b = 0;
-                if (lane == 0) b = atomicAdd(block_counter, 1u);
-                b = __shfl_sync(FULL, b, 0);
-                if (b >= num_blocks) { more_blocks = false; break; }
-                next = (long long)b * TW_BLOCK; end = min(next + (long long)TW_BLOCK, ncell);
-            }
-            const long long mine = next + __popc(wmask & lt_mask);
-            next += __popc(wmask);
-            if (want && mine < end) {
-                if (tp.mask[mine] != 1) {
-                    if (SW) swc[mine] = tp.sw_dir_cor_fill; else shadow[mine] = 3;
-                } else {
-                    units++;
-                    F3 org, sun;
-                    if (terrain_cell_setup<SW>(sv, tp, mine, sunx, suny, sunz, org, sun, dts, dns)) {
-                        wq_start_ray(sv, sh, warp, lane, L, org, sun);
-                        cell = mine; cnt.rays++;
-                    } else {
-                        if (SW) swc[mine] = 0.0f; else shadow[mine] = 1;   // self-shaded (:474-478 / :588-592)
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(FULL, L.state != 0) == 0u) break;
-        const int thr = (more_blocks || next < end) ? refill_thr : 1;
-        __syncwarp();
-        // (2) shared warp-queue traversal (hzb_wq.cuh)
-        while (__popc(wq_step<false>(sv, sh, nullptr, 0u, warp, lane, tid, L, W, tfar, wait_thr, cnt, overflow)) >= thr) {}
-    }
-    unsigned int r = cnt.rays, n = cnt.nodes, pp = cnt.prims, u = units;
-    for (int o = 16; o > 0; o >>= 1) {
-        r += __shfl_xor_sync(FULL, r, o); n += __shfl_xor_sync(FULL, n, o);
-        pp += __shfl_xor_sync(FULL, pp, o); u += __shfl_xor_sync(FULL, u, o);
-    }
-    if (lane == 0 && (r | n | pp | u)) {
-        atomicAdd(&counters->rays, (unsigned long long)r); atomicAdd(&counters->node_visits, (unsigned long long)n);
-        atomicAdd(&counters->prim_tests, (unsigned long long)pp); atomicAdd(&counters->units, (unsigned long long)u);
-    }
-}
-
-// Same kernel on the second-generation step (hzb_wq2.cuh, single-ray mode): folded decode bias,
-// per-lane pending lists, shared-diagonal quad test.
+// The packet step of hzb_wq2.cuh in single-ray mode: folded decode bias, per-lane pending lists,
+// shared-diagonal quad test.  SORT: nearest hit child first.
 template <bool SW, bool SORT>
 __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, TerrainParams tp, float sunx, float suny, float sunz,
                                                             uint8_t* __restrict__ shadow, float* __restrict__ swc,
                                                             Counters* counters, unsigned int* block_counter, int refill_thr,
-                                                            int wait_thr) {
+                                                            int wait_thr, int stack_lim) {
     __shared__ Wq2Shared sh;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
@@ -248,7 +167,6 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, Terra
     const unsigned int num_blocks = (unsigned int)((ncell + TW_BLOCK - 1) / TW_BLOCK);
     const float dot_min = SW ? tp.dot_prod_min : 0.0f;
     const float tfar = INFINITY;   // shadow_comp.cpp:462, 572
-    unsigned int* overflow = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
     unsigned int units = 0;
     if (lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
@@ -265,6 +183,10 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, Terra
     while (true) {
         // (1) retire finished rays (shadow_comp.cpp:468-472 / 578-586) and hand out new cells
         if (cell >= 0 && L.state == 0) {
+            if (L.node == WQ_OVF) {   // full stack: decided by the binary-BVH walker instead (same decision)
+                const unsigned int hb = HZB_WQ2_RECAST(sv, &sh.ray[warp][0][lane], tfar, 0, counters);
+                L.hit1 = hb & 1u; L.hit2 = hb & 2u; L.node = WQ_NONE;
+            }
             if (SW) {
                 if (L.hit1) swc[cell] = 0.0f;
                 else { if (dns < dot_min) dns = dot_min; swc[cell] = __fmul_rn(__fdiv_rn(dts, dns), tp.surf_enl_fac[cell]); }
@@ -304,7 +226,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, Terra
         const int thr = (more_blocks || next < end) ? refill_thr : 1;
         __syncwarp();
         // (2) shared warp-queue traversal (hzb_wq2.cuh)
-        while (__popc(wq2_step<false, SORT>(sv, sh, warp, lane, tid, L, pend_est, tfar, wait_thr, cnt, overflow)) >= thr) {}
+        while (__popc(wq2_step<false, SORT>(sv, sh, warp, lane, tid, L, pend_est, tfar, wait_thr, cnt, stack_lim)) >= thr) {}
     }
     unsigned int r = cnt.rays, n = cnt.nodes, pp = cnt.prims, u = units;
     for (int o = 16; o > 0; o >>= 1) {
@@ -319,35 +241,29 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, Terra
 
 }  // namespace
 
-int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* d_out, cudaStream_t st) {
+template <bool SW>
+static int launch_terrain(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* d_shadow, float* d_swc, cudaStream_t st) {
     const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
     if (ncell <= 0) return 0;
-    const bool simple = getenv("HZB_SHADOW_KERNEL") && !strcmp(getenv("HZB_SHADOW_KERNEL"), "simple");
-    if (simple) k_terrain<false><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters);
-    else {
-        HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-        const char* kv = getenv("HZB_SHADOW_KERNEL");
-        if (kv && !strcmp(kv, "wq1")) k_terrain_wq<false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 6);
-        else if (!(kv && !strcmp(kv, "sort"))) k_terrain_wq2<false, false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 3);
-        else k_terrain_wq2<false, true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_out, nullptr, s.d_counters, s.d_tile_counter, 24, 3);
+    const int kind = debug_options().shadow_kernel;
+    if (kind == 1) {
+        k_terrain<SW><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters);
+    } else {
+        unsigned int* block_counter = scene_tile_counter(s, st);
+        if (!block_counter) return 1;
+        const int stack_lim = std::max(1, std::min(debug_options().stack_limit, WQ_STACK_N));
+        if (kind == 2) k_terrain_wq2<SW, true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters, block_counter, 24, 3, stack_lim);
+        else k_terrain_wq2<SW, false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters, block_counter, 24, 3, stack_lim);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;
 }
+
+int launch_shadow(Scene& s, const TerrainParams& tp, const float* sun, uint8_t* d_out, cudaStream_t st) {
+    return launch_terrain<false>(s, tp, sun, d_out, nullptr, st);
+}
 int launch_sw_dir_cor(Scene& s, const TerrainParams& tp, const float* sun, float* d_out, cudaStream_t st) {
-    const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
-    if (ncell <= 0) return 0;
-    const bool simple = getenv("HZB_SHADOW_KERNEL") && !strcmp(getenv("HZB_SHADOW_KERNEL"), "simple");
-    if (simple) k_terrain<true><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters);
-    else {
-        HZB_CUDA(cudaMemsetAsync(s.d_tile_counter, 0, sizeof(unsigned int), st));
-        const char* kv = getenv("HZB_SHADOW_KERNEL");
-        if (kv && !strcmp(kv, "wq1")) k_terrain_wq<true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 6);
-        else if (!(kv && !strcmp(kv, "sort"))) k_terrain_wq2<true, false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 3);
-        else k_terrain_wq2<true, true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], nullptr, d_out, s.d_counters, s.d_tile_counter, 24, 3);
-    }
-    HZB_CUDA(cudaGetLastError());
-    return 0;
+    return launch_terrain<true>(s, tp, sun, nullptr, d_out, st);
 }
 
 }  // namespace hzb

@@ -41,6 +41,16 @@ cdef extern from "horayzon_b200.h":
         const int32_t* tri_ind_simp, int num_tri_simp,
         float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
         float ray_org_elev, int azim_first) nogil
+    int hzb_horizon_gridded_svf(
+        const float* vert_grid, int dem_dim_0, int dem_dim_1,
+        const float* vec_norm, const float* vec_north,
+        int offset_0, int offset_1, float* hori_buffer,
+        int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+        float hori_acc, const char* ray_algorithm, const char* geom_type,
+        const float* vert_simp, int num_vert_simp,
+        const int32_t* tri_ind_simp, int num_tri_simp,
+        float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+        float ray_org_elev, const float* vec_tilt, float* svf_buffer) nogil
     int hzb_horizon_locations(
         const float* vert_grid, int dem_dim_0, int dem_dim_1,
         const float* coords, const float* vec_norm, const float* vec_north,
@@ -139,7 +149,8 @@ def horizon_gridded(
         np.ndarray[np.uint8_t, ndim = 2] mask=None,
         float hori_fill=0.0,
         float ray_org_elev=0.01,
-        bint azim_first=False):
+        bint azim_first=False,
+        np.ndarray[np.float32_t, ndim = 3] svf_vec_tilt=None):
     """Horizon of every unmasked cell of a gridded inner domain.
 
     Arguments, units and defaults are those of ``horayzon.horizon.horizon_gridded``
@@ -157,6 +168,13 @@ def horizon_gridded(
     ``np.moveaxis(hori, 2, 0)`` before writing NetCDF
     (``examples/horizon/gridded_curved_DEM.py:113-125``) -- written in that order by
     the kernel, with the same values.
+
+    Additive keyword: ``svf_vec_tilt`` (float32 (y, x, 3), the ``vec_tilt`` argument of
+    ``topo_param.sky_view_factor``) makes the call return ``(hori_buffer, azim, svf)``: the sky
+    view factor is integrated on the device right behind the search, from the horizon array
+    still resident in HBM -- the same values as calling ``topo_param.sky_view_factor(azim, hori,
+    vec_tilt)`` afterwards (``examples/horizon/gridded_curved_DEM.py:104-144``), without uploading
+    the horizon array again.
     """
     # argument checks, in the reference's order and wording (horizon.pyx:109-156)
     if len(vert_grid) < (dem_dim_0 * dem_dim_1 * 3):
@@ -201,6 +219,17 @@ def horizon_gridded(
                          "dem_dim_1 is 32'767")
     if vert_simp.nbytes > (16.0 * 10 ** 9):
         raise ValueError("vertex buffer vert_simp is larger than 16 GB")
+    if tri_ind_simp.min() < 0:
+        raise ValueError("triangle indices of simplified outer domain must not "
+                         "be negative")
+    if svf_vec_tilt is not None:
+        if azim_first:
+            raise ValueError("svf_vec_tilt needs the reference layout (azim_first=False)")
+        if ((svf_vec_tilt.shape[0] != vec_norm.shape[0]) or (svf_vec_tilt.shape[1] != vec_norm.shape[1])
+                or (svf_vec_tilt.shape[2] != 3)):   # topo_param.pyx:400-405
+            raise ValueError("Input array(s) has/have incorrect shape(s)")
+        if azim_num < 2:
+            raise ValueError("the sky view factor needs at least two azimuth sectors")
 
     cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] vg = np.ascontiguousarray(vert_grid)
     cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] vn = np.ascontiguousarray(vec_norm)
@@ -221,6 +250,25 @@ def horizon_gridded(
     # element (masked cells get hori_fill), so the 2 GB-scale fill pass is skipped and
     # the pages are first touched by the overlapped device-to-host copy instead.
     cdef int rc = 0
+    cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] tilt
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] svf
+    if svf_vec_tilt is not None:
+        tilt = np.ascontiguousarray(svf_vec_tilt)
+        svf = np.empty((ny, nx), dtype=np.float32)
+        if ny > 0 and nx > 0:
+            with nogil:
+                rc = hzb_horizon_gridded_svf(
+                    <const float*> vg.data, dem_dim_0, dem_dim_1,
+                    <const float*> vn.data, <const float*> vno.data,
+                    offset_0, offset_1, <float*> hori_buffer.data, ny, nx,
+                    azim_num, dist_search, hori_acc, alg_c, geom_c,
+                    <const float*> vs.data, num_vert_simp,
+                    <const int32_t*> ti.data, num_tri_simp,
+                    elev_ang_low_lim, <const uint8_t*> mk.data, hori_fill,
+                    ray_org_elev, <const float*> tilt.data, <float*> svf.data)
+        if rc != 0:
+            _raise_native()
+        return hori_buffer, _azimuth_axis(azim_num), svf
     if ny > 0 and nx > 0:
         with nogil:
             rc = hzb_horizon_gridded_layout(

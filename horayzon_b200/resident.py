@@ -24,7 +24,7 @@ class Stats(ctypes.Structure):
                 ("t_h2d", ctypes.c_double), ("t_build", ctypes.c_double), ("t_trace", ctypes.c_double),
                 ("t_d2h", ctypes.c_double), ("t_total", ctypes.c_double),
                 ("num_prims", ctypes.c_ulonglong), ("num_nodes", ctypes.c_ulonglong),
-                ("bvh_bytes", ctypes.c_ulonglong)]
+                ("bvh_bytes", ctypes.c_ulonglong), ("fallback_packets", ctypes.c_ulonglong)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -53,6 +53,12 @@ def lib():
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float,
             ctypes.c_char_p, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
         L.hzb_horizon_gridded_dev_layout.argtypes = L.hzb_horizon_gridded_dev.argtypes[:-1] + [ctypes.c_int, ctypes.c_void_p]
+        L.hzb_horizon_gridded_dev_sharded.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_char_p, ctypes.c_float,
+            ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+        L.hzb_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        L.hzb_trim.restype = None
         for name in ("hzb_sky_view_factor_dev", "hzb_visible_sky_fraction_dev"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -60,6 +66,16 @@ def lib():
                                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _lib = L
     return _lib
+
+
+def debug_option(name, value):
+    """Test-only switch of the library (``hzb_debug_option``): second implementations, tuning knobs."""
+    _check(lib().hzb_debug_option(name.encode(), int(value)))
+
+
+def trim():
+    """Release the idle pooled device / page-locked memory of this process (``hzb_trim``)."""
+    lib().hzb_trim()
 
 
 def last_error():
@@ -149,6 +165,30 @@ class Scene:
             int(row_end), int(K), float(dist_search), float(hori_acc), ray_algorithm.encode(),
             float(elev_ang_low_lim), float(hori_fill), float(ray_org_elev),
             ctypes.c_void_p(hori_out.data_ptr()), 1 if azim_first else 0, _stream_ptr(stream)))
+
+
+    def horizon_gridded_sharded(self, vec_norm, vec_north, mask, offset_0, offset_1, hori_out, shard_rank, shard_count,
+                                azim_num, packed=True, dist_search=50.0, hori_acc=0.25, ray_algorithm="guess_constant",
+                                elev_ang_low_lim=-15.0, hori_fill=0.0, ray_org_elev=0.01, stream=None):
+        """Asynchronous horizon computation for the 4-row blocks ``b`` of the inner domain with
+        ``b % shard_count == shard_rank`` (``hzb_horizon_gridded_dev_sharded``).  ``packed=True``: ``hori_out`` is this
+        shard's send buffer ``(shard_rows(ny, rank, count), nx, K)``; ``packed=False``: the full ``(ny, nx, K)`` array."""
+        ny, nx = int(mask.shape[0]), int(mask.shape[1])
+        assert vec_norm.is_cuda and vec_north.is_cuda and mask.is_cuda and hori_out.is_cuda
+        assert vec_norm.is_contiguous() and vec_north.is_contiguous() and mask.is_contiguous() and hori_out.is_contiguous()
+        need = shard_rows(ny, shard_rank, shard_count) if packed else ny
+        assert hori_out.numel() >= need * nx * int(azim_num), "output buffer too small for this shard"
+        _check(lib().hzb_horizon_gridded_dev_sharded(
+            self._h, ctypes.c_void_p(vec_norm.data_ptr()), ctypes.c_void_p(vec_north.data_ptr()),
+            ctypes.c_void_p(mask.data_ptr()), int(offset_0), int(offset_1), ny, nx, int(azim_num), float(dist_search),
+            float(hori_acc), ray_algorithm.encode(), float(elev_ang_low_lim), float(hori_fill), float(ray_org_elev),
+            ctypes.c_void_p(hori_out.data_ptr()), int(shard_rank), int(shard_count), 1 if packed else 0,
+            _stream_ptr(stream)))
+
+
+def shard_rows(num_rows, shard_rank, shard_count):
+    """Rows (whole 4-row blocks) in the packed buffer of one shard (``hzb_shard_rows``)."""
+    return int(lib().hzb_shard_rows(int(num_rows), int(shard_rank), int(shard_count)))
 
 
 def sky_view_factor_dev(azim, hori, vec_tilt, out, stream=None):

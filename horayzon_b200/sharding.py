@@ -41,3 +41,43 @@ def allgather_rows(local_block, num_rows, dist, group=None):
                        device=local_block.device)
     dist.all_gather_into_tensor(full, local_block.contiguous(), group=group)
     return full[:num_rows]
+
+
+# ---- block-interleaved sharding (cost-balanced) ---------------------------------------------
+# Contiguous row blocks cost different amounts (rim rows see half the terrain of centre rows), and the
+# slowest GPU sets the step time.  Dealing the inner domain out in 4-row blocks -- block b to shard
+# b % world -- gives every GPU the same mix; each shard stores its blocks back to back (the kernels'
+# packed mode), ONE all-gather joins the shards, and block j of shard r is block j * world + r of the
+# result: a reshape + permute, no arithmetic.
+
+BLOCK_ROWS = 4
+
+
+def shard_block_rows(num_rows, rank, world_size):
+    """Rows (whole 4-row blocks, the last one possibly padding) shard `rank` stores."""
+    blocks = -(-int(num_rows) // BLOCK_ROWS)
+    return BLOCK_ROWS * ((blocks - rank + world_size - 1) // world_size) if blocks > rank else 0
+
+
+def padded_block_rows(num_rows, world_size):
+    """Rows per shard after padding to an equal count (shard 0 has the most blocks)."""
+    return shard_block_rows(num_rows, 0, world_size)
+
+
+def shard_row_indices(num_rows, rank, world_size):
+    """Inner-domain row of every row of shard `rank`'s packed buffer (-1: padding)."""
+    n = shard_block_rows(num_rows, rank, world_size)
+    j = np.arange(n)
+    rows = ((j // BLOCK_ROWS) * world_size + rank) * BLOCK_ROWS + j % BLOCK_ROWS
+    return np.where(rows < num_rows, rows, -1)
+
+
+def unpack_blocks(gathered, num_rows, world_size):
+    """[world * per, ...] all-gather result of packed shards -> [num_rows, ...] in domain order."""
+    per = gathered.shape[0] // world_size
+    nb = per // BLOCK_ROWS
+    rest = tuple(gathered.shape[1:])
+    g = gathered.reshape((world_size, nb, BLOCK_ROWS) + rest)
+    order = (1, 0, 2) + tuple(range(3, 3 + len(rest)))
+    g = g.permute(*order) if hasattr(g, "permute") else g.transpose(order)
+    return g.reshape((nb * world_size * BLOCK_ROWS,) + rest)[:num_rows]

@@ -53,6 +53,7 @@ typedef struct hzb_stats {
     unsigned long long num_prims;   /* BVH primitives (grid quads + TIN triangles) */
     unsigned long long num_nodes;   /* wide-BVH nodes */
     unsigned long long bvh_bytes;   /* bytes of the traversal structure in HBM */
+    unsigned long long fallback_packets; /* packets re-decided by the binary-BVH walker after a full traversal stack */
 } hzb_stats;
 int hzb_get_stats(hzb_stats* out);
 
@@ -69,6 +70,14 @@ int hzb_horizon_tables(int azim_num, float dist_search, float hori_acc, float el
  * no device / no memory: the caller falls back to ordinary memory. */
 void* hzb_host_alloc(size_t bytes);
 void hzb_host_free(void* p);
+/* Additive: release the idle pooled memory of this process (device blocks the host tier keeps
+ * between calls, at most 6 GB; the one idle page-locked output block, at most 4 GB). */
+void hzb_trim(void);
+/* Test-only switches: second implementations ("horizon_kernel" 1, "shadow_kernel" 1/2: reference-shaped
+ * per-lane kernels on the binary BVH / nearest-first order), tuning knobs ("wrefill", "wwait"),
+ * "no_overlap", "stack_limit" (forces the full-stack fallback), "reset".  Production code never
+ * calls it; no environment variable selects a kernel. */
+int hzb_debug_option(const char* name, int value);
 
 /* --------------------------------------------------------------- host tier */
 
@@ -100,6 +109,21 @@ int hzb_horizon_gridded_layout(const float* vert_grid, int dem_dim_0, int dem_di
                                const int32_t* tri_ind_simp, int num_tri_simp,
                                float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
                                float ray_org_elev, int azim_first);
+
+/* Additive: horizon + sky view factor in one call -- horizon_gridded_comp followed by
+ * _sky_view_factor_cy (topo_param.pyx:412-460) on the device-resident horizon, as
+ * examples/horizon/gridded_curved_DEM.py:104-144 calls them back to back.  vec_tilt:
+ * [dim_in_0][dim_in_1][3] (local frame); svf_buffer: [dim_in_0][dim_in_1].  Same values as
+ * hzb_horizon_gridded + hzb_sky_view_factor; the horizon array is not uploaded a second time. */
+int hzb_horizon_gridded_svf(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                            const float* vec_norm, const float* vec_north,
+                            int offset_0, int offset_1, float* hori_buffer,
+                            int dim_in_0, int dim_in_1, int azim_num,
+                            float dist_search, float hori_acc, const char* ray_algorithm,
+                            const char* geom_type, const float* vert_simp, int num_vert_simp,
+                            const int32_t* tri_ind_simp, int num_tri_simp,
+                            float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+                            float ray_org_elev, const float* vec_tilt, float* svf_buffer);
 
 /* Replaces horizon_locations_comp (horizon_comp.h:23-34, horizon_comp.cpp:828-1094).
  * hori_buffer / hori_dist_buffer: float32 [num_loc][azim_num]; locations whose
@@ -227,6 +251,22 @@ int hzb_horizon_gridded_dev_layout(hzb_scene* s,
                                    float dist_search, float hori_acc, const char* ray_algorithm,
                                    float elev_ang_low_lim, float hori_fill, float ray_org_elev,
                                    float* d_hori_buffer, int azim_first, void* stream);
+
+/* Additive (multi-GPU): block-interleaved sharding.  Shard `shard_rank` of `shard_count` computes the 4-row
+ * blocks b of the inner domain with b % shard_count == shard_rank -- the reference's row partition
+ * (horizon_comp.cpp:739-744) dealt out in 4-row blocks, so that every GPU gets the same mix of cheap rim
+ * rows and expensive centre rows.  packed == 0: results land in their places of the full
+ * [dim_in_0][dim_in_1][azim_num] array; packed != 0: the shard's blocks are stored back to back from
+ * d_hori_buffer on (hzb_shard_rows rows): the contiguous send buffer of one all-gather, after which
+ * block j of shard r is block j * shard_count + r of the result. */
+int hzb_horizon_gridded_dev_sharded(hzb_scene* s,
+                                    const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                    int offset_0, int offset_1, int dim_in_0, int dim_in_1, int azim_num,
+                                    float dist_search, float hori_acc, const char* ray_algorithm,
+                                    float elev_ang_low_lim, float hori_fill, float ray_org_elev,
+                                    float* d_hori_buffer, int shard_rank, int shard_count, int packed,
+                                    void* stream);
+int hzb_shard_rows(int dim_in_0, int shard_rank, int shard_count);
 
 /* Device-pointer variants of the azimuthal integrals (same layouts). */
 int hzb_sky_view_factor_dev(const float* d_azim, const float* d_hori, const float* d_vec_tilt,

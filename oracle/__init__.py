@@ -66,6 +66,11 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """OpenMP threads of the oracle (overrides OMP_NUM_THREADS, which torchrun exports as 1)."""
+    lib().orc_set_num_threads(int(n))
+
+
 def last_timing():
     """(BVH build seconds, ray tracing seconds) of the last oracle call."""
     b, t = ctypes.c_double(), ctypes.c_double()
@@ -125,6 +130,59 @@ def horizon_gridded(vert_grid, dem_dim_0, dem_dim_1, vec_norm, vec_north, offset
     if return_rays:
         return hori, _azim(azim_num), rays.value
     return hori, _azim(azim_num)
+
+
+class Scene:
+    """DEM (+ optional TIN) with its BVH kept between calls: the oracle twin of the reference's scene
+    (initializeScene, horizon_comp.cpp:101-231) for computing selected inner-domain ROWS without
+    rebuilding the BVH per call (stratified CPU-baseline samples, sampled-row parity checks)."""
+
+    def __init__(self, vert_grid, dem_dim_0, dem_dim_1, vert_simp=None, num_vert_simp=0, tri_ind_simp=None,
+                 num_tri_simp=0):
+        self.vert_grid = np.ascontiguousarray(vert_grid, np.float32)     # must outlive the native scene
+        self.dims = (int(dem_dim_0), int(dem_dim_1))
+        vs = ti = None
+        if vert_simp is not None and num_vert_simp >= 3:
+            vs = np.ascontiguousarray(vert_simp, np.float32); ti = np.ascontiguousarray(tri_ind_simp, np.int32)
+        self._keep = (vs, ti)
+        L = lib()
+        L.orc_scene_create.restype = ctypes.c_void_p
+        L.orc_scene_destroy.argtypes = [ctypes.c_void_p]
+        self._h = ctypes.c_void_p(L.orc_scene_create(
+            _p(self.vert_grid, _f32p), self.dims[0], self.dims[1], _p(vs, _f32p) if vs is not None else None,
+            int(num_vert_simp) if vs is not None else 0, _p(ti, _i32p) if ti is not None else None,
+            int(num_tri_simp) if vs is not None else 0))
+        self.build_s = last_timing()[0]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def horizon_rows(self, rows, vec_norm, vec_north, offset_0, offset_1, dist_search, azim_num=360, hori_acc=0.25,
+                     ray_algorithm="guess_constant", elev_ang_low_lim=-15.0, mask=None, hori_fill=0.0,
+                     ray_org_elev=0.01, return_rays=False):
+        """Horizon of the inner-domain rows ``rows`` (``vec_norm`` / ``vec_north`` / ``mask`` are the FULL
+        inner-domain arrays).  Returns float32 (len(rows), nx, azim_num)."""
+        rows = np.ascontiguousarray(rows, np.int32)
+        vn = np.ascontiguousarray(vec_norm[rows], np.float32)
+        vno = np.ascontiguousarray(vec_north[rows], np.float32)
+        nx = vn.shape[1]
+        mk = np.ones((len(rows), nx), np.uint8) if mask is None else np.ascontiguousarray(mask[rows], np.uint8)
+        hori = np.full((len(rows), nx, azim_num), np.nan, np.float32)
+        rays = ctypes.c_ulonglong(0)
+        _check(lib().orc_scene_horizon_rows(
+            self._h, _p(rows, _i32p), len(rows), nx, _p(vn, _f32p), _p(vno, _f32p), int(offset_0), int(offset_1),
+            _p(hori, _f32p), int(azim_num), ctypes.c_float(dist_search), ctypes.c_float(hori_acc),
+            ray_algorithm.encode(), ctypes.c_float(elev_ang_low_lim), _p(mk, _u8p), ctypes.c_float(hori_fill),
+            ctypes.c_float(ray_org_elev), ctypes.byref(rays)))
+        return (hori, rays.value) if return_rays else hori
 
 
 def horizon_locations(vert_grid, dem_dim_0, dem_dim_1, coords, vec_norm, vec_north, dist_search,

@@ -125,6 +125,7 @@ struct Scene {
     std::vector<Tri> ltris;  // triangles in leaf order (filled by build(); leaves index this directly)
     float pad = 0.f;
     double build_s = 0.0;
+    int node_count = 0;
 
     void add_grid(const float* vg, int H, int W) {
         auto P = [&](int i, int j) {
@@ -169,9 +170,11 @@ struct Scene {
         }
         for (int a = 0; a < 3; ++a) { nd.lo[a] -= pad; nd.hi[a] += pad; }
         nd.left = nd.right = -1; nd.first = begin; nd.count = end - begin;
+        // nodes is pre-sized (a leaf holds >= 2 triangles, so there are fewer than n nodes): lock-free slot claim
         int self;
-#pragma omp critical(hzb_oracle_nodes)
-        { self = (int)nodes.size(); nodes.push_back(nd); }
+#pragma omp atomic capture
+        self = node_count++;
+        nodes[self] = nd;
         if (end - begin <= 4) return self;
         int ax = 0;
         if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
@@ -190,8 +193,7 @@ struct Scene {
             l = build_rec(begin, mid, cen);
             r = build_rec(mid, end, cen);
         }
-#pragma omp critical(hzb_oracle_nodes)
-        { nodes[self].left = l; nodes[self].right = r; nodes[self].count = 0; }
+        nodes[self].left = l; nodes[self].right = r; nodes[self].count = 0;
         return self;
     }
     void build() {
@@ -214,13 +216,14 @@ struct Scene {
         for (int a = 0; a < 3; ++a)
             scale = fmaxf(scale, fmaxf(fmaxf(fabsf(slo[a]), fabsf(shi[a])), shi[a] - slo[a]));
         pad = scale * 4.0e-6f;
-        nodes.clear();
-        nodes.reserve(n / 2 + 16);
+        nodes.assign(n + 16, BNode{});
+        node_count = 0;
         if (n > 0) {
 #pragma omp parallel
 #pragma omp single
             build_rec(0, (int)n, cen);
         }
+        nodes.resize(node_count);
         ltris.resize(n);
 #pragma omp parallel for schedule(static)
         for (long long k = 0; k < (long long)n; ++k) ltris[k] = tris[order[k]];
@@ -477,6 +480,46 @@ int orc_tables(int azim_num, float dist_km, float acc_deg, float low_deg, int ca
     return T.elev_num;
 }
 
+}  // extern "C"
+
+namespace {
+// The row loop of horizon_gridded_comp (horizon_comp.cpp:739-800) over a LIST of inner-domain rows:
+// listed row r is inner row rows[r] (rows == nullptr: r itself); vec_norm / vec_north / mask / hori hold
+// the listed rows only.  Rows in parallel like the reference's tbb::blocked_range over dim_in_0
+// (:739-744); collapse(2) so that a bounded row sample still occupies every core.
+static uint64_t horizon_rows(const Scene& sc, const Tables& T, int alg, bool brute, const float* vert_grid, int dem_dim_1,
+                             const int* rows, int num_rows, int dim_in_1, const float* vec_norm, const float* vec_north,
+                             int offset_0, int offset_1, const uint8_t* mask, float hori_fill, float ray_org_elev,
+                             float* hori_buffer) {
+    const int azim_num = T.azim_num;
+    uint64_t rays = 0;
+#pragma omp parallel for collapse(2) schedule(dynamic, 8) reduction(+ : rays)
+    for (int r = 0; r < num_rows; ++r) {
+        for (int j = 0; j < dim_in_1; ++j) {
+            const int i = rows ? rows[r] : r;
+            const size_t c = (size_t)r * dim_in_1 + j;
+            float* out = hori_buffer + c * azim_num;
+            if (mask[c] != 1) { for (int k = 0; k < azim_num; ++k) out[k] = hori_fill; continue; }   // :789-794
+            const V3 nrm = {vec_norm[3 * c], vec_norm[3 * c + 1], vec_norm[3 * c + 2]};
+            const V3 nth = {vec_north[3 * c], vec_north[3 * c + 1], vec_north[3 * c + 2]};
+            const float* vp = vert_grid + 3 * ((size_t)(i + offset_0) * dem_dim_1 + (j + offset_1));
+            const Frame fr = make_frame({vp[0], vp[1], vp[2]}, nrm, nth, ray_org_elev);
+            Caster<false> cast{sc, T, fr, brute};
+            if (alg == 0) algo_discrete(cast, T, out, nullptr);
+            else if (alg == 1) algo_binary(cast, T, out, nullptr);
+            else algo_guess(cast, T, out);
+            rays += cast.rays;
+        }
+    }
+    return rays;
+}
+struct OrcScene { Scene sc; const float* vert_grid; int H, W; };
+}  // namespace
+
+extern "C" {
+
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 // horizon_gridded_comp (horizon_comp.cpp:629-822); argument order as horizon_comp.h:8-20
 int orc_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
                         const float* vec_norm, const float* vec_north, int offset_0, int offset_1,
@@ -494,28 +537,44 @@ int orc_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
     if (!brute_force) sc.build();
     g_build_s = sc.build_s;
     Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
-    uint64_t rays = 0;
     auto t0 = std::chrono::steady_clock::now();
-    // rows in parallel like the reference's tbb::blocked_range over dim_in_0 (:739-744);
-    // collapse(2) so that a bounded row sample still occupies every core
-#pragma omp parallel for collapse(2) schedule(dynamic, 8) reduction(+ : rays)
-    for (int i = 0; i < dim_in_0; ++i) {
-        for (int j = 0; j < dim_in_1; ++j) {
-            const size_t c = (size_t)i * dim_in_1 + j;
-            float* out = hori_buffer + c * azim_num;
-            if (mask[c] != 1) { for (int k = 0; k < azim_num; ++k) out[k] = hori_fill; continue; }
-            const V3 nrm = {vec_norm[3 * c], vec_norm[3 * c + 1], vec_norm[3 * c + 2]};
-            const V3 nth = {vec_north[3 * c], vec_north[3 * c + 1], vec_north[3 * c + 2]};
-            const float* vp = vert_grid + 3 * ((size_t)(i + offset_0) * dem_dim_1 + (j + offset_1));
-            const Frame fr = make_frame({vp[0], vp[1], vp[2]}, nrm, nth, ray_org_elev);
-            Caster<false> cast{sc, T, fr, brute_force != 0};
-            if (alg == 0) algo_discrete(cast, T, out, nullptr);
-            else if (alg == 1) algo_binary(cast, T, out, nullptr);
-            else algo_guess(cast, T, out);
-            rays += cast.rays;
-        }
-    }
+    const uint64_t rays = horizon_rows(sc, T, alg, brute_force != 0, vert_grid, dem_dim_1, nullptr, dim_in_0, dim_in_1, vec_norm,
+                                       vec_north, offset_0, offset_1, mask, hori_fill, ray_org_elev, hori_buffer);
     g_trace_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (num_rays_out) *num_rays_out = rays;
+    return 0;
+}
+
+// The same computation with the scene (initializeScene, :101-231) kept between calls and an explicit list
+// of inner-domain rows: bench.py times a stratified row sample, the tests check sampled rows of the big
+// configurations, both without rebuilding the BVH per row.  vert_grid must outlive the scene.
+void* orc_scene_create(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vert_simp, int num_vert_simp,
+                       const int32_t* tri_ind_simp, int num_tri_simp) {
+    OrcScene* h = new OrcScene();
+    h->vert_grid = vert_grid; h->H = dem_dim_0; h->W = dem_dim_1;
+    h->sc.add_grid(vert_grid, dem_dim_0, dem_dim_1);
+    if (vert_simp && tri_ind_simp) h->sc.add_tin(vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp);
+    h->sc.build();
+    g_build_s = h->sc.build_s;
+    return h;
+}
+void orc_scene_destroy(void* h) { delete (OrcScene*)h; }
+int orc_scene_horizon_rows(void* handle, const int* rows, int num_rows, int dim_in_1, const float* vec_norm, const float* vec_north,
+                           int offset_0, int offset_1, float* hori_buffer, int azim_num, float dist_search, float hori_acc,
+                           const char* ray_algorithm, float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+                           float ray_org_elev, unsigned long long* num_rays_out) {
+    OrcScene* h = (OrcScene*)handle;
+    const int alg = algo_id(ray_algorithm);
+    if (!h || alg < 0) { g_err = "invalid scene or ray_algorithm"; return 1; }
+    for (int r = 0; r < num_rows; ++r)
+        if (rows[r] < 0 || rows[r] + offset_0 >= h->H) { g_err = "row outside the DEM"; return 1; }
+    if (offset_1 < 0 || offset_1 + dim_in_1 > h->W) { g_err = "columns outside the DEM"; return 1; }
+    Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    auto t0 = std::chrono::steady_clock::now();
+    const uint64_t rays = horizon_rows(h->sc, T, alg, false, h->vert_grid, h->W, rows, num_rows, dim_in_1, vec_norm, vec_north,
+                                       offset_0, offset_1, mask, hori_fill, ray_org_elev, hori_buffer);
+    g_trace_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_build_s = h->sc.build_s;
     if (num_rays_out) *num_rays_out = rays;
     return 0;
 }
