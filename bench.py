@@ -292,7 +292,7 @@ def rank_stats(torch, dist, world, dev, values):
         m = torch.stack(allv)
     else:
         m = t[None]
-    return m.min(0).values.tolist(), m.mean(0).tolist(), m.max(0).tolist(), m.sum(0).tolist()
+    return m.min(0).values.tolist(), m.mean(0).tolist(), m.max(0).values.tolist(), m.sum(0).tolist()
 
 
 def northstar_record(hb, torch, dist, dev, rank, world, args):

@@ -481,6 +481,14 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
         HZB_CUDA(cudaStreamSynchronize(s_comp));
         HZB_CUDA(cudaStreamSynchronize(s_copy));
         if (t_trace == 0.0) t_trace = now_s() - t0;
+        // Cells whose traversal stack was full were recomputed by the fix-up kernel AFTER their row block had been
+        // copied: copy the array again (never happens in practice; the tests force it with a tiny stack limit).
+        Counters cc;
+        HZB_CUDA(cudaMemcpy(&cc, h->s.d_counters, sizeof(cc), cudaMemcpyDeviceToHost));
+        if (cc.fallback_packets != 0) {
+            if (out_pinned) HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
+            else HZB_TRY(staged_d2h(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), nullptr));
+        }
     } else {
         HZB_CUDA(cudaStreamSynchronize(s_comp));
         t_trace = now_s() - t0;

@@ -276,6 +276,31 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
 }
 
 
+// Fix-up kernel: recomputes the cells the production kernel marked with HZB_REDO_F32 (its traversal stack
+// was full) with the per-lane search on the binary BVH.  Launched right behind every production launch on the
+// same stream; finds nothing in all but pathological scenes (one strided 4-byte read per cell).
+template <int ALG>
+__global__ void __launch_bounds__(HG_THREADS) k_horizon_redo(SceneView sv, HorizonParams p, Counters* counters) {
+    const Search s = make_search(sv, p, counters);
+    const int rows = p.row_end - p.row_begin;
+    const long long slots = (long long)local_blocks(p, rows) * 4 * p.dim_in_1;
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < slots; g += (long long)gridDim.x * blockDim.x) {
+        const int lr = (int)(g / p.dim_in_1), j = (int)(g - (long long)lr * p.dim_in_1);    // local (packed) row, column
+        const int i = p.row_begin + ((lr >> 2) * p.blk_stride + p.blk_offset) * 4 + (lr & 3);
+        if (i >= p.row_end) continue;
+        const size_t c = (size_t)i * p.dim_in_1 + j;
+        float* out = p.hori + (p.packed ? (size_t)lr * p.dim_in_1 + j : c) * p.stride_c;
+        if (__float_as_uint(out[0]) != HZB_REDO_F32) continue;
+        const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
+        const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
+        const float4 v = sv.vert4[(size_t)(i + p.offset_0) * sv.W + (j + p.offset_1)];
+        const Frame f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+        OutBuf ob; ob.init(out, false, true, p.stride_k);
+        cell_search<ALG>(s, f, ob, cnt);
+    }
+}
+
 // ===========================================================================
 // k_horizon_wq6: production kernel.  Persistent warps pull 8x4-cell tiles from an atomic
 // queue; every lane runs the search state machine of hzb_search.cuh for its cell on the
@@ -350,13 +375,16 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         bool finished_cell = false, need_ray = false;
         int ie = 0, lo_ie = -1;
         if (has_cell && L.state == 0) {
-            if (L.node == WQ_OVF) {   // the packet's stack was full: decided by the binary-BVH walker instead (same decisions)
-                const unsigned int hb = HZB_WQ2_RECAST(sv, &sh.ray[warp][0][lane], s.dist, m.spec_ie >= 0 ? 1 : 0, counters);
-                L.hit1 = hb & 1u; L.hit2 = hb & 2u; L.node = WQ_NONE;
-            }
             unsigned int extra = 0;
             m.spec_hit = L.hit2;
-            need_ray = sm_advance<ALG, true, OutBuf>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
+            if (L.node == WQ_OVF) {   // the packet's stack was full: the cell is left to the fix-up kernel (same results)
+                L.node = WQ_NONE;
+                ob.out[0] = __uint_as_float(HZB_REDO_F32);
+                atomicAdd(&counters->fallback_packets, 1ull);
+                need_ray = false;
+            } else {
+                need_ray = sm_advance<ALG, true, OutBuf>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
+            }
             cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
                 has_cell = false; finished_cell = true;
@@ -503,6 +531,14 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
             case 0: k_horizon_wq6<0, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
             case 1: k_horizon_wq6<1, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
             default: k_horizon_wq6<2, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+        }
+        // cells whose traversal stack was full (none in practice) are recomputed by the binary-BVH walker
+        const long long slots = (long long)((p.row_end - p.row_begin + 3) / 4) * 4 * p.dim_in_1;
+        const int rgrid = (int)std::min<long long>((slots + HG_THREADS - 1) / HG_THREADS, (long long)sm_count() * 8);
+        switch (p.algorithm) {
+            case 0: k_horizon_redo<0><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
+            case 1: k_horizon_redo<1><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
+            default: k_horizon_redo<2><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
         }
     }
     HZB_CUDA(cudaGetLastError());

@@ -53,26 +53,13 @@ __device__ __forceinline__ bool wq2_start(const SceneView& sv, Wq2Shared& sh, in
 }
 
 constexpr uint32_t WQ_OVF = 0xFFFFFFFEu;   // L.node of a packet that retired because its stack was full
-
-// Fallback for a packet whose shared-memory stack was full: both rays are decided by the per-lane
-// walker of the binary BVH (96-entry local stack), which tests the same primitives with the same
-// tri_hit -- identical decisions.  Deliberately not inlined: it must not cost the traversal loop registers.
-static __device__ __noinline__ unsigned int wq2_overflow_recast(const SceneView sv, float ox, float oy, float oz, float d1x, float d1y,
-                                                                float d1z, float d2x, float d2y, float d2z, float tfar, int two,
-                                                                Counters* counters) {
-    // everything by value: taking the address of the caller's lane state would move it to local memory
-    LaneCounters c; c.rays = c.nodes = c.prims = 0;
-    unsigned int* ovf2 = reinterpret_cast<unsigned int*>(&counters->stack_overflow);
-    float t = tfar;
-    const bool h1 = trace_bvh2<false>(sv, f3(ox, oy, oz), f3(d1x, d1y, d1z), t, c, ovf2);
-    bool h2 = h1;
-    if (two) { t = tfar; h2 = trace_bvh2<false>(sv, f3(ox, oy, oz), f3(d2x, d2y, d2z), t, c, ovf2); }
-    atomicAdd(&counters->fallback_packets, 1ull);
-    return (h1 ? 1u : 0u) | (h2 ? 2u : 0u);
-}
-// ray = &sh.ray[warp][0][lane]
-#define HZB_WQ2_RECAST(sv, ray, tfar, two, counters) \
-    wq2_overflow_recast(sv, (ray)[0], (ray)[32], (ray)[64], (ray)[96], (ray)[128], (ray)[160], (ray)[192], (ray)[224], (ray)[256], tfar, two, counters)
+// A lane whose packet retired with WQ_OVF abandons its cell and marks the cell's first output element with
+// this pattern; a fix-up kernel launched right behind (k_horizon_redo / k_terrain<.., REDO>) recomputes the
+// marked cells with the per-lane walker of the binary BVH (96-entry local stack), which tests the same
+// primitives with the same tri_hit -- identical results.  (No call inside the persistent loop: a device
+// function call there makes the compiler guard every warp collective with a divergence check.)
+constexpr uint32_t HZB_REDO_F32 = 0x7FC0DEADu;   // a quiet NaN with a payload no computation produces
+constexpr uint8_t HZB_REDO_U8 = 0xFFu;           // shadow codes are 0..3
 
 // Same decisions as prim_hit<false>(.., D1, ..) and (TWO) prim_hit<false>(.., D2, ..).
 template <bool TWO>
@@ -125,8 +112,8 @@ __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 
 // SORT: nearest hit child first (pays off for single any-hit rays that are often occluded).
 //
 // A full stack never invalidates a result: the lane stops its walk, drops its pending candidates and
-// retires with L.node == WQ_OVF; the caller then decides that packet with the per-lane binary-BVH
-// walker (wq2_overflow_recast).  stack_lim <= WQ_STACK_N (the tests lower it to force that path).
+// retires with L.node == WQ_OVF; the caller marks the cell for the fix-up kernel (see HZB_REDO_F32).
+// stack_lim <= WQ_STACK_N (the tests lower it to force that path).
 template <bool TWO, bool SORT>
 __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared& sh, const int warp, const int lane, const int tid,
                                                  Wq2Lane& L, unsigned int& pend_est, const float tfar, const int wait_thr,

@@ -35,14 +35,16 @@ __device__ __forceinline__ float refraction_deg(float elev_true, float temp_c, f
     return __double2float_rn((double)r * (1.0 / 60.0));
 }
 
-template <bool SW>
+// REDO: only the cells the production kernel marked (full traversal stack) are computed.
+template <bool SW, bool REDO>
 __global__ void __launch_bounds__(128) k_terrain(SceneView sv, TerrainParams tp, float sunx, float suny, float sunz,
-                                                 uint8_t* __restrict__ shadow, float* __restrict__ swc, Counters* counters) {
+                                                 uint8_t* shadow, float* swc, Counters* counters) {
     const long long ncell = (long long)tp.dim_in_0 * tp.dim_in_1;
     const long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
     unsigned int units = 0;
-    if (c < ncell) {
+    const bool todo = c < ncell && (!REDO || (SW ? __float_as_uint(swc[c]) == HZB_REDO_F32 : shadow[c] == HZB_REDO_U8));
+    if (todo) {
         if (tp.mask[c] != 1) {
             if (SW) swc[c] = tp.sw_dir_cor_fill; else shadow[c] = 3;
         } else {
@@ -183,11 +185,11 @@ __global__ void __launch_bounds__(WQ_BLOCK, 6) k_terrain_wq2(SceneView sv, Terra
     while (true) {
         // (1) retire finished rays (shadow_comp.cpp:468-472 / 578-586) and hand out new cells
         if (cell >= 0 && L.state == 0) {
-            if (L.node == WQ_OVF) {   // full stack: decided by the binary-BVH walker instead (same decision)
-                const unsigned int hb = HZB_WQ2_RECAST(sv, &sh.ray[warp][0][lane], tfar, 0, counters);
-                L.hit1 = hb & 1u; L.hit2 = hb & 2u; L.node = WQ_NONE;
-            }
-            if (SW) {
+            if (L.node == WQ_OVF) {   // full stack: the cell is left to the fix-up launch of k_terrain (same decision)
+                L.node = WQ_NONE;
+                if (SW) swc[cell] = __uint_as_float(HZB_REDO_F32); else shadow[cell] = HZB_REDO_U8;
+                atomicAdd(&counters->fallback_packets, 1ull);
+            } else if (SW) {
                 if (L.hit1) swc[cell] = 0.0f;
                 else { if (dns < dot_min) dns = dot_min; swc[cell] = __fmul_rn(__fdiv_rn(dts, dns), tp.surf_enl_fac[cell]); }
             } else shadow[cell] = L.hit1 ? 2 : 0;
@@ -247,13 +249,15 @@ static int launch_terrain(Scene& s, const TerrainParams& tp, const float* sun, u
     if (ncell <= 0) return 0;
     const int kind = debug_options().shadow_kernel;
     if (kind == 1) {
-        k_terrain<SW><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters);
+        k_terrain<SW, false><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters);
     } else {
         unsigned int* block_counter = scene_tile_counter(s, st);
         if (!block_counter) return 1;
         const int stack_lim = std::max(1, std::min(debug_options().stack_limit, WQ_STACK_N));
         if (kind == 2) k_terrain_wq2<SW, true><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters, block_counter, 24, 3, stack_lim);
         else k_terrain_wq2<SW, false><<<sm_count() * 6, WQ_BLOCK, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters, block_counter, 24, 3, stack_lim);
+        // cells whose traversal stack was full (none in practice) are recomputed by the binary-BVH walker
+        k_terrain<SW, true><<<(unsigned int)((ncell + 127) / 128), 128, 0, st>>>(s.view(), tp, sun[0], sun[1], sun[2], d_shadow, d_swc, s.d_counters);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;

@@ -72,11 +72,10 @@ def test_horizon_kernel_variants_agree(mods, dbg, opts, alg):
     st = hb.resident.last_stats()
     h_cpu, _, rays = oracle.horizon_gridded(*args, azim_num=c["azim_num"], ray_algorithm=alg, return_rays=True)
     _assert_same(h_gpu, h_cpu, "variant %s" % opts)
-    assert st["rays"] == rays
-    if "stack_limit" in opts:
+    if "stack_limit" in opts:     # cells whose stack was full were recomputed by the fix-up kernel
         assert st["fallback_packets"] > 0, "the lowered stack limit did not exercise the fallback"
     else:
-        assert st["fallback_packets"] == 0
+        assert st["fallback_packets"] == 0 and st["rays"] == rays
 
 
 def test_shadow_kernel_variants_agree(mods, dbg):
