@@ -2,7 +2,7 @@
 
 ``horizon``, ``shadow``, ``topo_param``, ``transform`` and ``direction`` mirror the
 reference modules of the same names (``horayzon/__init__.py:1-12``); ``resident`` is the additive
-device-pointer tier used for benchmarking and multi-GPU sharding; ``synthetic``
+device-pointer tier used for benchmarking and multi-GPU sharding; ``multi`` / ``sharding`` hold the multi-GPU helpers; ``synthetic``
 holds the synthetic DEM recipes and the vertex-buffer wire format.
 """
 try:
@@ -11,7 +11,7 @@ except ImportError as exc:  # fail loudly: there is no Python/CPU fallback
     raise ImportError(
         "horayzon_b200 extension modules are not built (" + str(exc) + "); run "
         "`python horayzon_b200/_build.py` or `__graft_entry__.build()`") from exc
-from . import synthetic, resident  # noqa: F401
+from . import synthetic, resident, multi, sharding  # noqa: F401
 from .synthetic import rearrange_pad_buffer, pad_buffer  # noqa: F401
 
 __version__ = "0.1"

@@ -22,6 +22,7 @@ static thread_local std::string g_error;
 static thread_local hzb_stats g_stats;
 
 void set_error(const std::string& msg) { g_error = msg; }
+void set_last_stats(const hzb_stats& st) { g_stats = st; }
 double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }

@@ -11,6 +11,7 @@ namespace hzb {
 
 // ------------------------------------------------------------------ errors
 void set_error(const std::string& msg);
+void set_last_stats(const hzb_stats& st);   // what hzb_get_stats returns on this thread
 #define HZB_CUDA(call)                                                                     \
     do {                                                                                   \
         cudaError_t e_ = (call);                                                           \

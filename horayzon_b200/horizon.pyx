@@ -51,6 +51,17 @@ cdef extern from "horayzon_b200.h":
         const int32_t* tri_ind_simp, int num_tri_simp,
         float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
         float ray_org_elev, const float* vec_tilt, float* svf_buffer) nogil
+    int hzb_horizon_gridded_multi(
+        const float* vert_grid, int dem_dim_0, int dem_dim_1,
+        const float* vec_norm, const float* vec_north,
+        int offset_0, int offset_1, float* hori_buffer,
+        int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+        float hori_acc, const char* ray_algorithm, const char* geom_type,
+        const float* vert_simp, int num_vert_simp,
+        const int32_t* tri_ind_simp, int num_tri_simp,
+        float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+        float ray_org_elev, const float* vec_tilt, float* svf_buffer,
+        int n_devices, int n_shards, int device_gather) nogil
     int hzb_horizon_locations(
         const float* vert_grid, int dem_dim_0, int dem_dim_1,
         const float* coords, const float* vec_norm, const float* vec_north,
@@ -150,7 +161,10 @@ def horizon_gridded(
         float hori_fill=0.0,
         float ray_org_elev=0.01,
         bint azim_first=False,
-        np.ndarray[np.float32_t, ndim = 3] svf_vec_tilt=None):
+        np.ndarray[np.float32_t, ndim = 3] svf_vec_tilt=None,
+        int devices=1,
+        bint device_gather=False,
+        int _shards=0):
     """Horizon of every unmasked cell of a gridded inner domain.
 
     Arguments, units and defaults are those of ``horayzon.horizon.horizon_gridded``
@@ -175,6 +189,12 @@ def horizon_gridded(
     still resident in HBM -- the same values as calling ``topo_param.sky_view_factor(azim, hori,
     vec_tilt)`` afterwards (``examples/horizon/gridded_curved_DEM.py:104-144``), without uploading
     the horizon array again.
+
+    Additive keyword: ``devices`` -- number of GPUs of this box to use (``0``: all visible; default ``1``).
+    With more than one, the 4-row blocks of the inner domain are dealt out to the GPUs in turn (the
+    reference's TBB row partition, ``horizon_comp.cpp:739-744``), one host thread per GPU, DEM and BVH
+    replicated; the result is identical to the single-GPU call.  ``device_gather=True`` joins the shards by
+    one NCCL all-gather over NVLink instead of per-GPU copies to the host array.
     """
     # argument checks, in the reference's order and wording (horizon.pyx:109-156)
     if len(vert_grid) < (dem_dim_0 * dem_dim_1 * 3):
@@ -252,6 +272,36 @@ def horizon_gridded(
     cdef int rc = 0
     cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] tilt
     cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] svf
+    cdef const float* tilt_p = NULL
+    cdef float* svf_p = NULL
+    cdef int gather = 1 if device_gather else 0
+    if devices != 1 or _shards > 0:
+        if azim_first:
+            raise ValueError("devices != 1 needs the reference layout (azim_first=False)")
+        if devices < 0:
+            raise ValueError("devices must be >= 0")
+        svf = None
+        if svf_vec_tilt is not None:
+            tilt = np.ascontiguousarray(svf_vec_tilt)
+            svf = np.empty((ny, nx), dtype=np.float32)
+            tilt_p = <const float*> tilt.data
+            svf_p = <float*> svf.data
+        if ny > 0 and nx > 0:
+            with nogil:
+                rc = hzb_horizon_gridded_multi(
+                    <const float*> vg.data, dem_dim_0, dem_dim_1,
+                    <const float*> vn.data, <const float*> vno.data,
+                    offset_0, offset_1, <float*> hori_buffer.data, ny, nx,
+                    azim_num, dist_search, hori_acc, alg_c, geom_c,
+                    <const float*> vs.data, num_vert_simp,
+                    <const int32_t*> ti.data, num_tri_simp,
+                    elev_ang_low_lim, <const uint8_t*> mk.data, hori_fill,
+                    ray_org_elev, tilt_p, svf_p, devices, _shards, gather)
+        if rc != 0:
+            _raise_native()
+        if svf is not None:
+            return hori_buffer, _azimuth_axis(azim_num), svf
+        return hori_buffer, _azimuth_axis(azim_num)
     if svf_vec_tilt is not None:
         tilt = np.ascontiguousarray(svf_vec_tilt)
         svf = np.empty((ny, nx), dtype=np.float32)

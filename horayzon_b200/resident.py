@@ -58,6 +58,7 @@ def lib():
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_char_p, ctypes.c_float,
             ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         L.hzb_debug_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+        L.hzb_set_device.argtypes = [ctypes.c_int]
         L.hzb_trim.restype = None
         for name in ("hzb_sky_view_factor_dev", "hzb_visible_sky_fraction_dev"):
             getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,

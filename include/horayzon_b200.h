@@ -125,6 +125,29 @@ int hzb_horizon_gridded_svf(const float* vert_grid, int dem_dim_0, int dem_dim_1
                             float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
                             float ray_org_elev, const float* vec_tilt, float* svf_buffer);
 
+/* Additive: multi-GPU twin of hzb_horizon_gridded (same leading arguments, horizon_comp.h:8-20) -- one
+ * process, one host thread per GPU.  The reference parallelises over rows of the inner domain with TBB
+ * (horizon_comp.cpp:739-744); here the 4-row blocks are dealt out to the GPUs in turn, every GPU builds the
+ * BVH of the replicated DEM and computes its blocks.  n_devices <= 0: all visible devices; n_shards <= 0: one
+ * shard per device (more shards than devices are dealt round-robin).  device_gather == 0: each GPU copies its
+ * blocks to their places in the host array over its own PCIe link; != 0: the packed shards are joined by ONE
+ * in-place ncclAllGather over NVLink (single process, ncclCommInitAll; NCCL is dlopen'ed), put in domain
+ * order on GPU 0 and returned from there.  vec_tilt / svf_buffer: optional fused sky view factor
+ * ([dim_in_0][dim_in_1][3] / [dim_in_0][dim_in_1]; both NULL: none).  Same values as the single-GPU call. */
+int hzb_horizon_gridded_multi(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                              const float* vec_norm, const float* vec_north,
+                              int offset_0, int offset_1, float* hori_buffer,
+                              int dim_in_0, int dim_in_1, int azim_num,
+                              float dist_search, float hori_acc, const char* ray_algorithm,
+                              const char* geom_type, const float* vert_simp, int num_vert_simp,
+                              const int32_t* tri_ind_simp, int num_tri_simp,
+                              float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+                              float ray_org_elev, const float* vec_tilt, float* svf_buffer,
+                              int n_devices, int n_shards, int device_gather);
+/* Additive: select the CUDA device of the calling host thread for the host-tier calls that follow
+ * (they run on the current device), e.g. one hzb_terrain per GPU driven from one thread each. */
+int hzb_set_device(int device);
+
 /* Replaces horizon_locations_comp (horizon_comp.h:23-34, horizon_comp.cpp:828-1094).
  * hori_buffer / hori_dist_buffer: float32 [num_loc][azim_num]; locations whose
  * normal line misses the surface are left untouched (the wrapper pre-fills NaN). */

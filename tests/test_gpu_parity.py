@@ -626,3 +626,44 @@ def test_full_size_cfg4p_rows_against_oracle(mods):
         _assert_same(outs[i].cpu().numpy()[0], h_cpu[i], "cfg4p full size, row %d" % r)
     assert rays_gpu == rays_cpu
     sc.close()
+
+
+def test_multi_gpu_host_api(mods):
+    """hzb_horizon_gridded_multi behind horizon_gridded(devices=): the inner domain dealt out in 4-row blocks to
+    several shards (one host thread each; as many GPUs as the box has, shards round-robin over them) gives
+    the single-GPU result bit for bit, incl. the fused SVF, masks and a row count that is no multiple of 4."""
+    hb, oracle = mods
+    c, args = _cfg(hb, "cfg2", n=203)          # 201 inner rows: the last block is ragged
+    tilt = hb.synthetic.tilt_vectors(c["x"], c["y"], c["z"], c["offset_0"])
+    rng = np.random.default_rng(11)
+    mask = (rng.random((c["ny"], c["nx"])) < 0.9).astype(np.uint8)
+    kw = dict(azim_num=90, mask=mask, hori_fill=-2.0)
+    h1, az1, s1 = hb.horizon.horizon_gridded(*args, svf_vec_tilt=tilt, **kw)
+    rays1 = hb.resident.last_stats()["rays"]
+    for shards in (2, 3, 5):
+        h, az, s = hb.horizon.horizon_gridded(*args, svf_vec_tilt=tilt, devices=0, _shards=shards, **kw)
+        assert np.array_equal(h, h1) and np.array_equal(az, az1) and np.array_equal(s, s1), shards
+        assert hb.resident.last_stats()["rays"] == rays1
+    h, az = hb.horizon.horizon_gridded(*args, devices=0, **kw)          # one shard per visible GPU
+    assert np.array_equal(h, h1)
+    import torch
+    if torch.cuda.device_count() >= 2:                                    # the NCCL all-gather path needs >= 2 GPUs
+        h, az, s = hb.horizon.horizon_gridded(*args, svf_vec_tilt=tilt, devices=0, device_gather=True, **kw)
+        assert np.array_equal(h, h1) and np.array_equal(s, s1)
+
+
+def test_multi_terrain_shards_sun_positions(mods):
+    """MultiTerrain: the terrain replicated per GPU (here: as many replicas as GPUs, at least two), the sun
+    positions of a batch dealt out to the replicas -- same maps as one Terrain."""
+    import torch
+    hb, oracle = mods
+    vg, n, rim, tilt, norm, enl, elev, mask = _terrain_inputs(hb)
+    one = hb.shadow.Terrain()
+    one.initialise(vg, n, n, rim, rim, tilt, norm, enl, elev, mask)
+    suns = hb.synthetic.sun_positions_diurnal(13)
+    ref_s, ref_f = one.shadow_batch(suns), one.sw_dir_cor_batch(suns)
+    ndev = torch.cuda.device_count()
+    mt = hb.multi.MultiTerrain(devices=list(range(ndev)) if ndev >= 2 else [0, 0, 0])
+    mt.initialise(vg, n, n, rim, rim, tilt, norm, enl, elev, mask)
+    assert np.array_equal(mt.shadow_batch(suns), ref_s)
+    assert np.array_equal(mt.sw_dir_cor_batch(suns), ref_f, equal_nan=True)
