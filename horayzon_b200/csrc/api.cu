@@ -306,7 +306,8 @@ static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const floa
                                   int azim_num, float dist_search, float hori_acc, const char* ray_algorithm,
                                   float elev_ang_low_lim, float hori_fill, float ray_org_elev, float* d_hori_buffer,
                                   unsigned int* d_row_done, volatile unsigned int* row_flags, cudaStream_t st, int azim_first = 0,
-                                  int shard_rank = 0, int shard_count = 1, int packed = 0) {
+                                  int shard_rank = 0, int shard_count = 1, int packed = 0,
+                                  uint16_t* d_hori_q = nullptr, float* d_hori_first = nullptr) {
     const int alg = parse_algorithm(ray_algorithm);
     if (alg < 0) { set_error("invalid input argument for ray_algorithm"); return 1; }
     if (azim_num < 1 || dim_in_0 < 0 || dim_in_1 < 0 || row_begin < 0 || row_end > dim_in_0) { set_error("invalid dimensions"); return 1; }
@@ -323,6 +324,9 @@ static int horizon_gridded_launch(Scene& sc, const float* d_vec_norm, const floa
     p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1;
     p.row_begin = row_begin; p.row_end = row_end; p.hori_fill = hori_fill; p.ray_org_elev = ray_org_elev;
     p.hori = d_hori_buffer; p.row_done = d_row_done; p.row_flags = row_flags;
+    p.hori_q = d_hori_q; p.hori_first = d_hori_first;
+    if ((d_hori_q == nullptr) != (d_hori_first == nullptr)) { set_error("quantised output needs both buffers"); return 1; }
+    if (d_hori_q && (azim_first || packed)) { set_error("quantised output needs the reference layout"); return 1; }
     p.row_full = (unsigned int)((dim_in_1 + 7) / 8) * 32u;
     p.blk_stride = shard_count; p.blk_offset = shard_rank; p.packed = packed;
     p.stride_c = azim_first ? 1 : azim_num;
@@ -352,6 +356,22 @@ int hzb_horizon_gridded_dev_layout(hzb_scene* h, const float* d_vec_norm, const 
     return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, row_begin,
                                   row_end, azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
                                   ray_org_elev, d_hori_buffer, nullptr, nullptr, (cudaStream_t)stream, azim_first);
+}
+
+// additive (scope row 8f-4): quantised output.  Every guess_constant result but the first azimuth's is a table
+// entry (horizon_comp.cpp:490-494), so d_idx_buffer [dim_in_0][dim_in_1][azim_num] receives 16-bit table indices
+// (0xFFFF: "take the cell's float": azimuth 0 and masked cells) and d_first_buffer [dim_in_0][dim_in_1] the first
+// azimuth's un-quantised midpoint (:428) or hori_fill.  Lossless: hzb_horizon_tables gives elev_ang, and
+// elev_ang[index] is bit for bit the float the other entry points store.  Half the bytes to move and keep.
+int hzb_horizon_gridded_dev_quantised(hzb_scene* h, const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                      int offset_0, int offset_1, int dim_in_0, int dim_in_1, int row_begin, int row_end,
+                                      int azim_num, float dist_search, float hori_acc, float elev_ang_low_lim, float hori_fill,
+                                      float ray_org_elev, uint16_t* d_idx_buffer, float* d_first_buffer, void* stream) {
+    if (!h) { set_error("null scene"); return 1; }
+    if (!d_idx_buffer || !d_first_buffer) { set_error("null pointer argument"); return 1; }
+    return horizon_gridded_launch(h->s, d_vec_norm, d_vec_north, d_mask, offset_0, offset_1, dim_in_0, dim_in_1, row_begin, row_end,
+                                  azim_num, dist_search, hori_acc, "guess_constant", elev_ang_low_lim, hori_fill, ray_org_elev,
+                                  nullptr, nullptr, nullptr, (cudaStream_t)stream, 0, 0, 1, 0, d_idx_buffer, d_first_buffer);
 }
 
 // additive (multi-GPU): shard `shard_rank` of `shard_count` computes the 4-row blocks b of the inner domain with
@@ -528,6 +548,48 @@ int hzb_horizon_gridded_layout(const float* vert_grid, int dem_dim_0, int dem_di
     return horizon_gridded_host(vert_grid, dem_dim_0, dem_dim_1, vec_norm, vec_north, offset_0, offset_1, hori_buffer, dim_in_0,
                                 dim_in_1, azim_num, dist_search, hori_acc, ray_algorithm, geom_type, vert_simp, num_vert_simp,
                                 tri_ind_simp, num_tri_simp, elev_ang_low_lim, mask, hori_fill, ray_org_elev, azim_first);
+}
+
+// host tier of the quantised output (guess_constant only; see hzb_horizon_gridded_dev_quantised)
+int hzb_horizon_gridded_quantised(const float* vert_grid, int dem_dim_0, int dem_dim_1, const float* vec_norm,
+                                  const float* vec_north, int offset_0, int offset_1, uint16_t* idx_buffer, float* first_buffer,
+                                  int dim_in_0, int dim_in_1, int azim_num, float dist_search, float hori_acc,
+                                  const char* geom_type, const float* vert_simp, int num_vert_simp,
+                                  const int32_t* tri_ind_simp, int num_tri_simp, float elev_ang_low_lim, const uint8_t* mask,
+                                  float hori_fill, float ray_org_elev) {
+    memset(&g_stats, 0, sizeof(g_stats));
+    const double t_start = now_s();
+    if (require_device()) return 1;
+    if (parse_geom_type(geom_type) < 0) { set_error("invalid input argument for geom_type"); return 1; }
+    if (!vert_grid || !vec_norm || !vec_north || !idx_buffer || !first_buffer || !mask) { set_error("null pointer argument"); return 1; }
+    int dev = 0; cudaGetDevice(&dev);
+    hzb_scene* h = hzb_scene_create(vert_grid, dem_dim_0, dem_dim_1, vert_simp, num_vert_simp, tri_ind_simp, num_tri_simp, dev);
+    if (!h) return 1;
+    struct Guard { hzb_scene* h; ~Guard() { hzb_scene_destroy(h); } } guard{h};
+    const size_t nc = (size_t)dim_in_0 * dim_in_1;
+    HostCtx* ctx = nullptr;
+    HZB_TRY(host_ctx(&ctx));
+    double t0 = now_s();
+    DevBuf<float> d_norm, d_north, d_first; DevBuf<uint8_t> d_mask; DevBuf<uint16_t> d_idx;
+    HZB_TRY(d_norm.upload(vec_norm, nc * 3)); HZB_TRY(d_north.upload(vec_north, nc * 3)); HZB_TRY(d_mask.upload(mask, nc));
+    HZB_TRY(d_idx.alloc(nc * (size_t)azim_num)); HZB_TRY(d_first.alloc(nc));
+    const double t_h2d_extra = now_s() - t0;
+    t0 = now_s();
+    HZB_TRY(hzb_horizon_gridded_dev_quantised(h, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0, azim_num,
+                                              dist_search, hori_acc, elev_ang_low_lim, hori_fill, ray_org_elev, d_idx.p, d_first.p, ctx->comp));
+    host_prefault(idx_buffer, nc * (size_t)azim_num * sizeof(uint16_t));      // while the kernel runs
+    HZB_CUDA(cudaStreamSynchronize(ctx->comp));
+    const double t_trace = now_s() - t0;
+    t0 = now_s();
+    if (nc > 0) {
+        if (host_is_pinned(idx_buffer)) HZB_CUDA(cudaMemcpy(idx_buffer, d_idx.p, nc * (size_t)azim_num * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+        else HZB_TRY(staged_d2h(idx_buffer, d_idx.p, nc * (size_t)azim_num * sizeof(uint16_t), nullptr));
+        HZB_CUDA(cudaMemcpy(first_buffer, d_first.p, nc * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    HZB_CUDA(cudaGetLastError());
+    HZB_TRY(read_counters(h->s, g_stats));
+    g_stats.t_h2d += t_h2d_extra; g_stats.t_trace = t_trace; g_stats.t_d2h = now_s() - t0; g_stats.t_total = now_s() - t_start;
+    return 0;
 }
 
 // additive: horizon + sky view factor in one call.  The integral (topo_param.pyx:412-460) runs on the

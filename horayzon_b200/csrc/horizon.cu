@@ -156,13 +156,41 @@ struct OutBuf {
         b0 = b1; b1 = b2; b2 = b3; b3 = v;
         if ((k & 3) == 3 && writer) *reinterpret_cast<float4*>(out + (k - 3)) = make_float4(b0, b1, b2, b3);
     }
+    __device__ __forceinline__ void put_idx(int k, int, float v) { put(k, v); }
+    __device__ __forceinline__ void mark_redo() { out[0] = __uint_as_float(HZB_REDO_F32); }
+    __device__ __forceinline__ void fill(int K, float v) { for (int k = 0; k < K; ++k) out[k * sk] = v; }
 };
+
+// Quantised output (scope row 8f-4): every guess_constant result but the first azimuth's IS a table entry
+// (horizon_comp.cpp:490-494), so the kernel stores its 16-bit table index; the first azimuth's un-quantised
+// bisection midpoint (:428) goes to a float per cell.  Lossless: elev_ang[index] is the float the other mode stores.
+constexpr unsigned short HZB_Q_FIRST = 0xFFFFu;   // "take the cell's float" (azimuth 0, masked cells)
+struct OutBufQ {
+    unsigned short* idx; float* first; long long sk;
+    __device__ __forceinline__ void init(unsigned short* q, float* f, long long stride_k) { idx = q; first = f; sk = stride_k; }
+    __device__ __forceinline__ void put(int k, float v) { *first = v; idx[k * sk] = HZB_Q_FIRST; }     // k == 0 only (guess_constant)
+    __device__ __forceinline__ void put_idx(int k, int ie, float) { idx[k * sk] = (unsigned short)ie; }
+    __device__ __forceinline__ void mark_redo() { *first = __uint_as_float(HZB_REDO_F32); }
+    __device__ __forceinline__ void fill(int K, float v) { *first = v; for (int k = 0; k < K; ++k) idx[k * sk] = HZB_Q_FIRST; }
+};
+template <bool Q> struct OutSel { typedef OutBuf type; };
+template <> struct OutSel<true> { typedef OutBufQ type; };
+template <bool Q>
+__device__ __forceinline__ void out_init(typename OutSel<Q>::type& ob, const HorizonParams& p, size_t slot, size_t cell);
+template <>
+__device__ __forceinline__ void out_init<false>(OutBuf& ob, const HorizonParams& p, size_t slot, size_t) {
+    ob.init(p.hori + slot * p.stride_c, false, true, p.stride_k);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
+}
+template <>
+__device__ __forceinline__ void out_init<true>(OutBufQ& ob, const HorizonParams& p, size_t slot, size_t) {
+    ob.init(p.hori_q + slot * p.stride_c, p.hori_first + slot, p.stride_k);
+}
 
 // One cell, all azimuths.  ALG 0 discrete_sampling (:302-333), 1 binary_search
 // (:339-381), 2 guess_constant (:387-498).  Termination rule: a hit
 // at the top index counts as a miss, a miss at index 0 as a hit.
-template <int ALG>
-__device__ void cell_search(const Search& s, const Frame& f, OutBuf& ob, LaneCounters& cnt) {
+template <int ALG, typename OB>
+__device__ void cell_search(const Search& s, const Frame& f, OB& ob, LaneCounters& cnt) {
     const int top = s.elev_num - 1;
     if (ALG == 0) {
         for (int k = 0; k < s.azim_num; ++k) {
@@ -200,7 +228,7 @@ __device__ void cell_search(const Search& s, const Frame& f, OutBuf& ob, LaneCou
                 }
             }
             const int ie = index_of(s, midpoint(__ldg(s.elev_ang + prev), __ldg(s.elev_ang + cur)));
-            ob.put(k, __ldg(s.elev_ang + ie));
+            ob.put_idx(k, ie, __ldg(s.elev_ang + ie));
             prev_az = ie;
         }
     }
@@ -279,7 +307,7 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
 // Fix-up kernel: recomputes the cells the production kernel marked with HZB_REDO_F32 (its traversal stack
 // was full) with the per-lane search on the binary BVH.  Launched right behind every production launch on the
 // same stream; finds nothing in all but pathological scenes (one strided 4-byte read per cell).
-template <int ALG>
+template <int ALG, bool Q>
 __global__ void __launch_bounds__(HG_THREADS) k_horizon_redo(SceneView sv, HorizonParams p, Counters* counters) {
     const Search s = make_search(sv, p, counters);
     const int rows = p.row_end - p.row_begin;
@@ -290,13 +318,13 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_redo(SceneView sv, Horiz
         const int i = p.row_begin + ((lr >> 2) * p.blk_stride + p.blk_offset) * 4 + (lr & 3);
         if (i >= p.row_end) continue;
         const size_t c = (size_t)i * p.dim_in_1 + j;
-        float* out = p.hori + (p.packed ? (size_t)lr * p.dim_in_1 + j : c) * p.stride_c;
-        if (__float_as_uint(out[0]) != HZB_REDO_F32) continue;
+        const size_t slot = p.packed ? (size_t)lr * p.dim_in_1 + j : c;
+        if (__float_as_uint(Q ? p.hori_first[slot] : p.hori[slot * p.stride_c]) != HZB_REDO_F32) continue;
         const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
         const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
         const float4 v = sv.vert4[(size_t)(i + p.offset_0) * sv.W + (j + p.offset_1)];
         const Frame f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
-        OutBuf ob; ob.init(out, false, true, p.stride_k);
+        typename OutSel<Q>::type ob; out_init<Q>(ob, p, slot, c);
         cell_search<ALG>(s, f, ob, cnt);
     }
 }
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_redo(SceneView sv, Horiz
 // two-ray packet traversal of hzb_wq2.cuh: the casts at prev+5 and prev-5 of a
 // guess_constant azimuth share one traversal.
 // ===========================================================================
-template <int ALG, int MINB>
+template <int ALG, int MINB, bool Q>
 __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, HorizonParams p, Counters* counters,
                                                                 unsigned int* tile_counter, int refill_thr, int wait_thr,
                                                                 int stack_lim) {
@@ -327,7 +355,8 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
     unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
     LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
     m.spec_ie = -1; m.spec_hit = false;
-    OutBuf ob; ob.init(nullptr, false);
+    typedef typename OutSel<Q>::type OB;
+    OB ob;
     unsigned int my_cell = 0;   // (row << 16) | column of the lane's cell: its frame is rebuilt at every ray set-up
     bool has_cell = false, have_result = false;
     Wq2Lane L; L.state = 0; L.hit1 = L.hit2 = false; L.node = WQ_NONE; L.sp = 0; L.pc = 0;
@@ -356,15 +385,16 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                 bool done_now = true;
                 if (ci < p.row_end && cj < p.dim_in_1) {
                     const size_t c = (size_t)ci * p.dim_in_1 + cj;
-                    float* out = p.hori + (p.packed ? (size_t)(ty * 4 + (mine >> 3)) * p.dim_in_1 + cj : c) * p.stride_c;
+                    const size_t slot = p.packed ? (size_t)(ty * 4 + (mine >> 3)) * p.dim_in_1 + cj : c;
                     if (p.mask[c] == 1) {
                         my_cell = ((unsigned int)ci << 16) | (unsigned int)cj;    // dims <= 32767 (horizon.pyx:149-151)
-                        ob.init(out, false, true, p.stride_k);   // one 4-byte store per azimuth: L2 merges them long before the sector is evicted
+                        out_init<Q>(ob, p, slot, c);
                         m.phase = 0; m.k = 0; m.spec_ie = -1;
                         has_cell = true; have_result = false; units += p.azim_num;
                         done_now = false;
                     } else {
-                        for (int k = 0; k < p.azim_num; ++k) out[k * p.stride_k] = p.hori_fill;  // horizon_comp.cpp:789-794
+                        OB fo; out_init<Q>(fo, p, slot, c);
+                        fo.fill(p.azim_num, p.hori_fill);  // horizon_comp.cpp:789-794
                     }
                 }
                 if (done_now && p.row_done) publish_cell(p, ty);
@@ -379,11 +409,11 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
             m.spec_hit = L.hit2;
             if (L.node == WQ_OVF) {   // the packet's stack was full: the cell is left to the fix-up kernel (same results)
                 L.node = WQ_NONE;
-                ob.out[0] = __uint_as_float(HZB_REDO_F32);
+                ob.mark_redo();
                 atomicAdd(&counters->fallback_packets, 1ull);
                 need_ray = false;
             } else {
-                need_ray = sm_advance<ALG, true, OutBuf>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
+                need_ray = sm_advance<ALG, true, OB>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
             }
             cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
@@ -515,7 +545,8 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
     if (!tile_counter) return 1;
     const SceneView sv = s.view();
     const DebugOptions& o = debug_options();
-    if (o.horizon_kernel == 1) {   // reference-shaped per-lane kernel on the binary BVH (second implementation for the parity tests)
+    if (p.hori_q && (p.algorithm != 2 || p.elev_num > 65534)) { set_error("quantised output needs ray_algorithm guess_constant and at most 65534 table entries"); return 1; }
+    if (o.horizon_kernel == 1 && !p.hori_q) {   // reference-shaped per-lane kernel on the binary BVH (second implementation for the parity tests)
         const int grid = sm_count() * 8;
         switch (p.algorithm) {
             case 0: k_horizon_gridded<0><<<grid, HG_THREADS, 0, st>>>(sv, p, s.d_counters, tile_counter); break;
@@ -527,18 +558,21 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
         // candidates are flushed when w_wait lanes wait on theirs (tuned on B200)
         const int w_refill = o.wrefill, w_wait = o.wwait, stack_lim = std::max(1, std::min(o.stack_limit, WQ_STACK_N));
         constexpr int MB = 5;   // resident CTAs per SM (93 registers, 31 KB shared memory)
-        switch (p.algorithm) {
-            case 0: k_horizon_wq6<0, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
-            case 1: k_horizon_wq6<1, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
-            default: k_horizon_wq6<2, MB><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+        if (p.hori_q) {   // quantised output: guess_constant only (checked by the caller)
+            k_horizon_wq6<2, MB, true><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim);
+        } else switch (p.algorithm) {
+            case 0: k_horizon_wq6<0, MB, false><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+            case 1: k_horizon_wq6<1, MB, false><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+            default: k_horizon_wq6<2, MB, false><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
         }
         // cells whose traversal stack was full (none in practice) are recomputed by the binary-BVH walker
         const long long slots = (long long)((p.row_end - p.row_begin + 3) / 4) * 4 * p.dim_in_1;
         const int rgrid = (int)std::min<long long>((slots + HG_THREADS - 1) / HG_THREADS, (long long)sm_count() * 8);
-        switch (p.algorithm) {
-            case 0: k_horizon_redo<0><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
-            case 1: k_horizon_redo<1><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
-            default: k_horizon_redo<2><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
+        if (p.hori_q) k_horizon_redo<2, true><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters);
+        else switch (p.algorithm) {
+            case 0: k_horizon_redo<0, false><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
+            case 1: k_horizon_redo<1, false><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
+            default: k_horizon_redo<2, false><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
         }
     }
     HZB_CUDA(cudaGetLastError());

@@ -150,6 +150,8 @@ struct HorizonParams {
     // stored back to back ([local block][4][dim_in_1][azim]) from `hori` on -- a contiguous all-gather send buffer.
     int blk_stride, blk_offset, packed;
     float* hori;
+    unsigned short* hori_q; float* hori_first;   // quantised output instead of `hori` (both or none): 16-bit table indices
+                                                 // [cell][azimuth] + the first azimuth's float per cell (scope row 8f-4)
     long long stride_c, stride_k;   // element (cell c, azimuth k) lives at hori[c * stride_c + k * stride_k]: (K, 1) = the reference's
                                     // [y][x][azim] layout, (1, cells) = azimuth-first [azim][y][x] (scope row "next 4")
     unsigned int* row_done;  // optional [ceil(rows/4)]: +1 per finished cell slot of that row block, 32 per 8x4 tile (host overlaps D2H)

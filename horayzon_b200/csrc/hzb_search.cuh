@@ -142,12 +142,12 @@ again:
                 HZB_SM_CAST(max(m.cur - 10, 0));
             }
             const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
-            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
+            ob.put_idx(m.k, ie, __ldg(s.elev_ang + ie)); m.prev_az = ie;      // a table entry: index and value
         } else if (m.phase == 3) {
             if (m.cur == 0) hit = true;               // termination rule
             if (!hit) { m.prev = m.cur; m.cur = max(m.cur - 10, 0); HZB_SM_CAST(max(m.cur - 10, 0)); }
             const int ie = index_of(s, midpoint(__ldg(s.elev_ang + m.prev), __ldg(s.elev_ang + m.cur)));
-            ob.put(m.k, __ldg(s.elev_ang + ie)); m.prev_az = ie;
+            ob.put_idx(m.k, ie, __ldg(s.elev_ang + ie)); m.prev_az = ie;
         } else {  // phase 4: discrete sampling (:309-331)
             if (m.cur == top) hit = false;
             if (hit) { m.prev = m.cur; m.cur = min(m.cur + 10, top); HZB_SM_CAST(min(m.cur + 10, top)); }

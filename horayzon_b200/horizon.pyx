@@ -51,6 +51,18 @@ cdef extern from "horayzon_b200.h":
         const int32_t* tri_ind_simp, int num_tri_simp,
         float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
         float ray_org_elev, const float* vec_tilt, float* svf_buffer) nogil
+    int hzb_horizon_gridded_quantised(
+        const float* vert_grid, int dem_dim_0, int dem_dim_1,
+        const float* vec_norm, const float* vec_north,
+        int offset_0, int offset_1, unsigned short* idx_buffer, float* first_buffer,
+        int dim_in_0, int dim_in_1, int azim_num, float dist_search,
+        float hori_acc, const char* geom_type,
+        const float* vert_simp, int num_vert_simp,
+        const int32_t* tri_ind_simp, int num_tri_simp,
+        float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+        float ray_org_elev) nogil
+    int hzb_horizon_tables(int azim_num, float dist_search, float hori_acc, float elev_ang_low_lim, int cap,
+                           float* elev_ang, float* elev_sin, float* elev_cos, float* azim_sin, float* azim_cos) nogil
     int hzb_horizon_gridded_multi(
         const float* vert_grid, int dem_dim_0, int dem_dim_1,
         const float* vec_norm, const float* vec_north,
@@ -333,6 +345,115 @@ def horizon_gridded(
     if rc != 0:
         _raise_native()
     return hori_buffer, _azimuth_axis(azim_num)
+
+
+def horizon_gridded_quantised(
+        np.ndarray[np.float32_t, ndim = 1] vert_grid,
+        int dem_dim_0, int dem_dim_1,
+        np.ndarray[np.float32_t, ndim = 3] vec_norm,
+        np.ndarray[np.float32_t, ndim = 3] vec_north,
+        int offset_0, int offset_1,
+        float dist_search,
+        int azim_num=360,
+        float hori_acc=0.25,
+        str geom_type="grid",
+        np.ndarray[np.float32_t, ndim = 1]
+        vert_simp=np.array([0.0, 0.0, 0.0, 0.0], dtype=np.float32),
+        int num_vert_simp=1,
+        np.ndarray[np.int32_t, ndim = 1]
+        tri_ind_simp=np.array([0, 0, 0, 0], dtype=np.int32),
+        int num_tri_simp=1,
+        float elev_ang_low_lim = -15.0,
+        np.ndarray[np.uint8_t, ndim = 2] mask=None,
+        float hori_fill=0.0,
+        float ray_org_elev=0.01):
+    """Additive (not in the reference): ``horizon_gridded`` with ``ray_algorithm="guess_constant"`` and a
+    lossless 16-bit output.  Every result but the first azimuth's is an entry of the elevation table
+    (``horizon_comp.cpp:490-494``), so the call returns
+
+    ``(idx, first, table, azim)``: uint16 (y, x, azim_num) table indices (``0xFFFF`` = "take ``first``":
+    azimuth 0 and masked cells), float32 (y, x) first-azimuth horizon (or ``hori_fill``), float32 (elev_num,)
+    elevation table, float32 (azim_num,) azimuths.  ``dequantise(idx, first, table)`` reproduces the array of
+    ``horizon_gridded`` bit for bit; the 2 GB array of a 1201 x 1201 x 360 run shrinks to 1 GB on the bus,
+    in memory and on disk (``examples/horizon/gridded_curved_DEM.py:113-125``)."""
+    if len(vert_grid) < (dem_dim_0 * dem_dim_1 * 3):
+        raise ValueError("inconsistency between input arguments vert_grid, "
+                         "dem_dim_0 and dem_dim_1")
+    if ((offset_0 + vec_norm.shape[0] > dem_dim_0)
+            or (offset_1 + vec_norm.shape[1] > dem_dim_1)):
+        raise ValueError("inconsistency between input arguments dem_dim_0, "
+                         "dem_dim_1, offset_0, offset_1 and vec_norm")
+    if ((vec_norm.shape[0] != vec_north.shape[0]) or (vec_norm.shape[1] != vec_north.shape[1])
+            or (vec_norm.shape[2] != vec_north.shape[2])):
+        raise ValueError("dimension (lengths) of vec_norm and/or vec_north "
+                         "is/are erroneous")
+    if geom_type not in _GEOM_TYPES:
+        raise ValueError("invalid input argument for geom_type")
+    if len(vert_simp) < (num_vert_simp * 3):
+        raise ValueError("inconsistency between input arguments vert_simp "
+                         "and num_vert_simp")
+    if len(tri_ind_simp) < (num_tri_simp * 3):
+        raise ValueError("inconsistency between input arguments tri_ind_simp "
+                         "and num_tri_simp")
+    if tri_ind_simp.max() > (num_vert_simp - 1) or tri_ind_simp.min() < 0:
+        raise ValueError("triangle indices of simplified outer domain exceed "
+                         "number of vertices")
+    if hori_acc > 10.0:
+        raise ValueError("limit of hori_acc (10 degree) is exceeded")
+    if mask is None:
+        mask = np.ones((vec_norm.shape[0], vec_norm.shape[1]), dtype=np.uint8)
+    if (mask.shape[0] != vec_norm.shape[0]) or (mask.shape[1] != vec_norm.shape[1]):
+        raise ValueError("shape of mask is inconsistent with other input")
+    if ray_org_elev < 0.005:
+        raise TypeError("minimal allowed value for 'ray_org_elev' is 0.005 m")
+    if (dem_dim_0 > 32767) or (dem_dim_1 > 32767):
+        raise ValueError("maximal allowed input length for dem_dim_0 and "
+                         "dem_dim_1 is 32'767")
+    cdef int elev_num
+    with nogil:
+        elev_num = hzb_horizon_tables(azim_num, dist_search, hori_acc, elev_ang_low_lim, 0, NULL, NULL, NULL, NULL, NULL)
+    if elev_num < 2 or elev_num > 65534:
+        raise ValueError("the elevation table of these parameters has %d entries; the 16-bit output holds 2 ... 65534" % elev_num)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] table = np.empty(elev_num, dtype=np.float32)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] tsin = np.empty(elev_num, dtype=np.float32)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] tcos = np.empty(elev_num, dtype=np.float32)
+    with nogil:
+        hzb_horizon_tables(azim_num, dist_search, hori_acc, elev_ang_low_lim, elev_num, <float*> table.data,
+                           <float*> tsin.data, <float*> tcos.data, NULL, NULL)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] vg = np.ascontiguousarray(vert_grid)
+    cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] vn = np.ascontiguousarray(vec_norm)
+    cdef np.ndarray[np.float32_t, ndim = 3, mode = "c"] vno = np.ascontiguousarray(vec_north)
+    cdef np.ndarray[np.float32_t, ndim = 1, mode = "c"] vs = np.ascontiguousarray(vert_simp)
+    cdef np.ndarray[np.int32_t, ndim = 1, mode = "c"] ti = np.ascontiguousarray(tri_ind_simp)
+    cdef np.ndarray[np.uint8_t, ndim = 2, mode = "c"] mk = np.ascontiguousarray(mask)
+    cdef bytes geom_b = geom_type.encode("utf-8")
+    cdef const char* geom_c = geom_b
+    cdef int ny = vn.shape[0], nx = vn.shape[1]
+    cdef np.ndarray[np.uint16_t, ndim = 3, mode = "c"] idx = np.empty((ny, nx, azim_num), dtype=np.uint16)
+    cdef np.ndarray[np.float32_t, ndim = 2, mode = "c"] first = np.empty((ny, nx), dtype=np.float32)
+    cdef int rc = 0
+    if ny > 0 and nx > 0:
+        with nogil:
+            rc = hzb_horizon_gridded_quantised(
+                <const float*> vg.data, dem_dim_0, dem_dim_1,
+                <const float*> vn.data, <const float*> vno.data,
+                offset_0, offset_1, <unsigned short*> idx.data, <float*> first.data, ny, nx,
+                azim_num, dist_search, hori_acc, geom_c,
+                <const float*> vs.data, num_vert_simp,
+                <const int32_t*> ti.data, num_tri_simp,
+                elev_ang_low_lim, <const uint8_t*> mk.data, hori_fill, ray_org_elev)
+    if rc != 0:
+        _raise_native()
+    return idx, first, table, _azimuth_axis(azim_num)
+
+
+def dequantise(idx, first, table):
+    """float32 (y, x, azim_num) horizon from the output of ``horizon_gridded_quantised``: bit for bit the
+    array ``horizon_gridded`` returns."""
+    idx = np.asarray(idx)
+    take_first = idx == 0xFFFF
+    out = np.asarray(table, dtype=np.float32)[np.where(take_first, 0, idx)]
+    return np.where(take_first, np.asarray(first, dtype=np.float32)[..., None], out).astype(np.float32, copy=False)
 
 
 def horizon_locations(

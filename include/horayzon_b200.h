@@ -125,6 +125,23 @@ int hzb_horizon_gridded_svf(const float* vert_grid, int dem_dim_0, int dem_dim_1
                             float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
                             float ray_org_elev, const float* vec_tilt, float* svf_buffer);
 
+/* Additive (scope row 8f-4): quantised horizon output for ray_algorithm "guess_constant" (the default).  Every
+ * result but the first azimuth's is an entry of the elevation table (horizon_comp.cpp:490-494), so the call
+ * returns 16-bit table indices idx_buffer [dim_in_0][dim_in_1][azim_num] (0xFFFF: "take first_buffer": azimuth 0
+ * and masked cells) and first_buffer [dim_in_0][dim_in_1] (the first azimuth's un-quantised midpoint, :428, or
+ * hori_fill).  Lossless: with elev_ang from hzb_horizon_tables, elev_ang[idx] is bit for bit what
+ * hzb_horizon_gridded stores.  Half the bytes to copy, keep and write to disk
+ * (examples/horizon/gridded_curved_DEM.py:113-125 is where the 2-400 GB float array goes to NetCDF). */
+int hzb_horizon_gridded_quantised(const float* vert_grid, int dem_dim_0, int dem_dim_1,
+                                  const float* vec_norm, const float* vec_north,
+                                  int offset_0, int offset_1, uint16_t* idx_buffer, float* first_buffer,
+                                  int dim_in_0, int dim_in_1, int azim_num,
+                                  float dist_search, float hori_acc, const char* geom_type,
+                                  const float* vert_simp, int num_vert_simp,
+                                  const int32_t* tri_ind_simp, int num_tri_simp,
+                                  float elev_ang_low_lim, const uint8_t* mask, float hori_fill,
+                                  float ray_org_elev);
+
 /* Additive: multi-GPU twin of hzb_horizon_gridded (same leading arguments, horizon_comp.h:8-20) -- one
  * process, one host thread per GPU.  The reference parallelises over rows of the inner domain with TBB
  * (horizon_comp.cpp:739-744); here the 4-row blocks are dealt out to the GPUs in turn, every GPU builds the
@@ -274,6 +291,15 @@ int hzb_horizon_gridded_dev_layout(hzb_scene* s,
                                    float dist_search, float hori_acc, const char* ray_algorithm,
                                    float elev_ang_low_lim, float hori_fill, float ray_org_elev,
                                    float* d_hori_buffer, int azim_first, void* stream);
+
+/* Resident-tier form of hzb_horizon_gridded_quantised (rows [row_begin, row_end), device buffers). */
+int hzb_horizon_gridded_dev_quantised(hzb_scene* s,
+                                      const float* d_vec_norm, const float* d_vec_north, const uint8_t* d_mask,
+                                      int offset_0, int offset_1, int dim_in_0, int dim_in_1,
+                                      int row_begin, int row_end, int azim_num,
+                                      float dist_search, float hori_acc, float elev_ang_low_lim,
+                                      float hori_fill, float ray_org_elev,
+                                      uint16_t* d_idx_buffer, float* d_first_buffer, void* stream);
 
 /* Additive (multi-GPU): block-interleaved sharding.  Shard `shard_rank` of `shard_count` computes the 4-row
  * blocks b of the inner domain with b % shard_count == shard_rank -- the reference's row partition

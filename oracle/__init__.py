@@ -71,6 +71,12 @@ def set_num_threads(n):
     lib().orc_set_num_threads(int(n))
 
 
+def set_exact_predicate(on):
+    """Evaluate every ray/triangle test in double on the exact float inputs (no epsilon) instead of the
+    specified fp32 arithmetic: the reference point for how much the outputs depend on rounding."""
+    lib().orc_set_exact_predicate(1 if on else 0)
+
+
 def last_timing():
     """(BVH build seconds, ray tracing seconds) of the last oracle call."""
     b, t = ctypes.c_double(), ctypes.c_double()

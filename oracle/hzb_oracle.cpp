@@ -81,7 +81,10 @@ struct Tri { V3 p0, p1, p2; };
 // Robust two-sided ray/triangle test (restatement of the published Pluecker
 // test of Embree's RTC_SCENE_FLAG_ROBUST intersector).  Returns true when the
 // ray org + t*dir, 0 <= t <= tfar, meets the triangle; *t_out receives t.
+static inline bool tri_hit_exact(const Tri& T, V3 O, V3 D, float tfar, float* t_out);
+static bool g_exact_predicate_fwd();
 static inline bool tri_hit(const Tri& T, V3 O, V3 D, float tfar, float* t_out) {
+    if (g_exact_predicate_fwd()) return tri_hit_exact(T, O, D, tfar, t_out);
     const V3 v0 = sub3(T.p0, O), v1 = sub3(T.p1, O), v2 = sub3(T.p2, O);
     const V3 e0 = sub3(v2, v0), e1 = sub3(v0, v1), e2 = sub3(v1, v2);
     const float U = dot_f(cross_f(e0, add3(v2, v0)), D);
@@ -107,6 +110,35 @@ static inline bool tri_hit(const Tri& T, V3 O, V3 D, float tfar, float* t_out) {
     const float t = (tn + tn) / den;
     if (!(t >= 0.0f && t <= tfar)) return false;
     *t_out = t;
+    return true;
+}
+
+// The same predicate with every operation in double on the exact float inputs (differences, cross and dot
+// products carry ~29 more bits than the fp32 evaluation): the decision an implementation with DIFFERENT
+// rounding (another instruction order, Embree's SIMD kernels, ...) would take whenever the fp32 decision is not a
+// rounding artefact.  orc_set_exact_predicate(1) switches every cast of the oracle to it; comparing the two
+// oracles measures how many casts / outputs depend on the rounding of the triangle test at all
+// (tests/test_oracle_cpu.py::test_parity_sensitivity, bench.py "parity_sensitivity").
+static bool g_exact_predicate = false;
+static bool g_exact_predicate_fwd() { return g_exact_predicate; }
+static inline bool tri_hit_exact(const Tri& T, V3 O, V3 D, float tfar, float* t_out) {
+    struct D3 { double x, y, z; };
+    auto sub = [](D3 a, D3 b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; };
+    auto add = [](D3 a, D3 b) { return D3{a.x + b.x, a.y + b.y, a.z + b.z}; };
+    auto cross = [](D3 a, D3 b) { return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; };
+    auto dot = [](D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; };
+    const D3 o = {O.x, O.y, O.z}, d = {D.x, D.y, D.z};
+    const D3 v0 = sub({T.p0.x, T.p0.y, T.p0.z}, o), v1 = sub({T.p1.x, T.p1.y, T.p1.z}, o), v2 = sub({T.p2.x, T.p2.y, T.p2.z}, o);
+    const D3 e0 = sub(v2, v0), e1 = sub(v0, v1), e2 = sub(v1, v2);
+    const double U = dot(cross(e0, add(v2, v0)), d), V = dot(cross(e1, add(v0, v1)), d), W = dot(cross(e2, add(v1, v2)), d);
+    const double mn = std::min(std::min(U, V), W), mx = std::max(std::max(U, V), W);
+    if (!((mn >= 0.0) || (mx <= 0.0))) return false;      // no epsilon: exact edge functions
+    const D3 Ng = cross(e0, e1);
+    const double den = 2.0 * dot(Ng, d);
+    if (den == 0.0) return false;
+    const double t = 2.0 * dot(v0, Ng) / den;
+    if (!(t >= 0.0 && t <= (double)tfar)) return false;
+    *t_out = (float)t;
     return true;
 }
 
@@ -519,6 +551,7 @@ struct OrcScene { Scene sc; const float* vert_grid; int H, W; };
 extern "C" {
 
 void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+void orc_set_exact_predicate(int on) { g_exact_predicate = on != 0; }
 
 // horizon_gridded_comp (horizon_comp.cpp:629-822); argument order as horizon_comp.h:8-20
 int orc_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,
@@ -1174,7 +1207,7 @@ long long orc_selftest_folded_slab(unsigned long long seed, long long n, int pad
 // Returns the number of cells that differ.  Test infrastructure only.
 // ---------------------------------------------------------------------------
 namespace {
-struct HostOut { float* out; inline void put(int k, float v) { out[k] = v; } };
+struct HostOut { float* out; inline void put(int k, float v) { out[k] = v; } inline void put_idx(int k, int, float v) { out[k] = v; } };
 
 template <int ALG>
 static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_grid, int W, int off0, int off1, int ny, int nx,

@@ -667,3 +667,23 @@ def test_multi_terrain_shards_sun_positions(mods):
     mt.initialise(vg, n, n, rim, rim, tilt, norm, enl, elev, mask)
     assert np.array_equal(mt.shadow_batch(suns), ref_s)
     assert np.array_equal(mt.sw_dir_cor_batch(suns), ref_f, equal_nan=True)
+
+
+def test_quantised_output_is_lossless(mods, dbg):
+    """Scope row 8f-4: 16-bit table indices + the first azimuth's float reproduce the float array of
+    horizon_gridded bit for bit (masked cells, fill value, a fix-up pass after a forced full stack included)."""
+    hb, oracle = mods
+    c, args = _cfg(hb, "cfg2", n=301)
+    rng = np.random.default_rng(5)
+    mask = (rng.random((c["ny"], c["nx"])) < 0.8).astype(np.uint8)
+    kw = dict(azim_num=180, mask=mask, hori_fill=-0.5)
+    h, az = hb.horizon.horizon_gridded(*args, **kw)
+    for lim in (None, 3):
+        if lim:
+            dbg("stack_limit", lim)
+        idx, first, table, az2 = hb.horizon.horizon_gridded_quantised(*args, **kw)
+        assert idx.dtype == np.uint16 and idx.shape == h.shape and first.shape == h.shape[:2]
+        assert np.array_equal(az, az2) and np.array_equal(table, oracle.tables(180, c["dist_search"], 0.25, -15.0)["elev_ang"])
+        assert np.array_equal(hb.horizon.dequantise(idx, first, table), h)
+        assert np.all(idx[:, :, 0] == 0xFFFF) and np.all(idx[mask == 0] == 0xFFFF) and np.all(first[mask == 0] == np.float32(-0.5))
+        assert idx.nbytes * 2 == h.nbytes
