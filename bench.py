@@ -31,6 +31,8 @@ configs[1]).  Default workload: cfg2 = 1201 x 1201 synthetic DEM x 360 azimuths
           (cfg4p = 6000 x 6000 x 360 azimuths) through the same sharded path,
           with rows checked bit for bit against the CPU oracle.
   shadow : (N = 1) cfg3 = 3601 x 3601 shadow map, ms per sun position.
+  locations : (N = 1) horizon_locations as the reference uses it (1440 azimuths, distance output).
+  parity_sensitivity : (N = 1) share of outputs that depend on the rounding of the triangle test.
   --impl reference : the reference's CPU path.  Embree/TBB cannot be installed
           here, so this arm times the CPU oracle (reference-algorithm restatement,
           NOT Embree; OpenMP over rows where the reference uses TBB) on a
@@ -393,6 +395,53 @@ def shadow_record(hb, torch, dev, args):
                          "unit": "GB/s", "frac": ach / peak, "kernel": "k_terrain_wq2"}}
 
 
+def locations_record(hb, args):
+    """horizon_locations in the reference's own configuration (examples/horizon/locations_curved_DEM.py: 1440
+    azimuths, hori_acc 0.1 deg, binary_search, distance to the horizon) for 1000 locations on the cfg2 DEM."""
+    c = hb.synthetic.make_config("cfg2")
+    rng = np.random.default_rng(1)
+    n, K = 1000, 1440
+    ij = rng.integers(50, c["dem_dim_0"] - 50, (n, 2))
+    coords = np.stack([c["x"][ij[:, 0], ij[:, 1]], c["y"][ij[:, 0], ij[:, 1]], c["z"][ij[:, 0], ij[:, 1]] + 50.0], axis=1).astype(np.float32)
+    nrm = np.zeros((n, 3), np.float32); nrm[:, 2] = 1.0
+    nth = np.zeros((n, 3), np.float32); nth[:, 1] = 1.0
+    roe = np.full(n, 2.0, np.float32)
+    kw = dict(azim_num=K, hori_acc=0.1, ray_algorithm="binary_search", ray_org_elev=roe, hori_dist_out=True)
+    a = (c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], coords, nrm, nth, c["dist_search"])
+    hb.horizon.horizon_locations(*a, **kw)            # warm
+    w0 = time.perf_counter()
+    hb.horizon.horizon_locations(*a, **kw)
+    dt = time.perf_counter() - w0
+    st = hb.resident.last_stats()
+    return {"workload": "1000 locations x 1440 azimuths on the cfg2 DEM, binary_search, hori_acc 0.1 deg, hori_dist_out (closest-hit casts)",
+            "units_per_s": n * K / dt, "ms_host_call": dt * 1e3, "ms_kernels": st["t_trace"] * 1e3, "casts_per_unit": st["rays"] / max(st["units"], 1),
+            "kernel": "k_loc_wq (packet step, closest-hit mode)"}
+
+
+def parity_sensitivity(c, K, nrows=6):
+    """How much do the outputs depend on the ROUNDING of the ray/triangle test (the part of the reference that lives
+    in Embree and cannot be compared here)?  The CPU oracle on sampled rows, once with the specified fp32 arithmetic
+    and once with every triangle test in double on the exact inputs (no epsilon)."""
+    import oracle
+    sc = oracle.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+    rows = stratified_rows(c["ny"], nrows)
+    kw = dict(azim_num=K, hori_acc=HORI_ACC, ray_algorithm=ALGORITHM, return_rays=True)
+    a = (rows, c["vec_norm"], c["vec_north"], c["offset_0"], c["offset_1"], c["dist_search"])
+    h32, r32 = sc.horizon_rows(*a, **kw)
+    oracle.set_exact_predicate(True)
+    try:
+        h64, r64 = sc.horizon_rows(*a, **kw)
+    finally:
+        oracle.set_exact_predicate(False)
+    sc.close()
+    nd = int((h32 != h64).sum())
+    return {"outputs_compared": int(h32.size), "outputs_that_differ": nd, "fraction": nd / h32.size,
+            "max_abs_diff_rad": float(np.abs(h32 - h64).max()), "casts_fp32": int(r32), "casts_exact": int(r64),
+            "meaning": "fp32 Pluecker test (the specification both oracle and GPU implement) vs the same predicate evaluated in "
+                       "double without epsilon, on %d sampled rows: the share of outputs an implementation with different rounding "
+                       "(e.g. Embree's SIMD kernels) can be expected to change" % len(rows)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -519,9 +568,10 @@ def run_ours(args):
     del run, flush
     torch.cuda.empty_cache()
     northstar = northstar_record(hb, torch, dist, dev, rank, world, args) if not args.no_northstar else None
-    shadow = None
+    shadow = locations = None
     if rank == 0 and world == 1 and not args.no_shadow:
         shadow = shadow_record(hb, torch, dev, args)
+        locations = locations_record(hb, args)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -566,10 +616,14 @@ def run_ours(args):
             line["northstar"] = northstar
         if shadow:
             line["shadow"] = shadow
+        if locations:
+            line["locations"] = locations
         if not args.no_cpu_baseline:
             smp = OracleSampler(c, K)
             line["cpu_baseline"] = smp.sample(smp.size_sample(args.ref_seconds))
             smp.close()
+            if world == 1:
+                line["parity_sensitivity"] = parity_sensitivity(c, K)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

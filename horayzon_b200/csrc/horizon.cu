@@ -13,7 +13,9 @@
 //   k_horizon_gridded  reference-shaped per-lane kernel on the binary BVH: the second,
 //                      structurally different implementation the full-size parity test
 //                      compares the production kernel with (hzb_debug_option, test only)
-//   k_loc_*            arbitrary locations (closest-hit queries, binary BVH)
+//   k_loc_wq           arbitrary locations on the same traversal step (any-hit / closest-hit), one lane per
+//                      (location, azimuth); k_loc_snap / k_loc_chain / k_loc_indep: per-lane binary-BVH forms
+//                      (surface snap; second implementation for the parity tests)
 #include "hzb_geom.cuh"
 #include "hzb_wq.cuh"
 #include "hzb_wq2.cuh"
@@ -527,6 +529,92 @@ __global__ void k_loc_indep(SceneView sv, HorizonParams p, LocationParams lp, co
     }
     flush_counters(cnt, units, counters);
 }
+// ---------------------------------------------------------------------------
+// k_loc_wq: horizon_locations on the production traversal (scope row 8f-2).  One lane per (location,
+// azimuth) for the independent algorithms (discrete_sampling / binary_search; the reference's own use:
+// 1440 azimuths, hori_dist_out, examples/horizon/locations_curved_DEM.py), one lane per location for the
+// guess_constant chain; all lanes of a warp share the packet step of hzb_wq2.cuh in single-ray mode --
+// any-hit, or closest-hit when the distance to the horizon is wanted (castRay_intersect1,
+// horizon_comp.cpp:268-292, 519-612).  Persistent warps, grid-stride over 32-unit groups.
+// ---------------------------------------------------------------------------
+struct LocOut {   // one azimuth row of one location
+    float* out;
+    __device__ __forceinline__ void put(int k, float v) { out[k] = v; }
+    __device__ __forceinline__ void put_idx(int k, int, float v) { out[k] = v; }
+};
+
+template <int ALG, bool WD>
+__global__ void __launch_bounds__(WQ_BLOCK, 4) k_loc_wq(SceneView sv, HorizonParams p, LocationParams lp, const float4* org_valid,
+                                                        Counters* counters, int stack_lim) {
+    __shared__ Wq2Shared sh;
+    const Search s = make_search(sv, p, counters);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const unsigned int FULL = 0xffffffffu;
+    const long long total = (ALG == 2) ? (long long)lp.num_loc : (long long)lp.num_loc * p.azim_num;
+    const long long warps_total = (long long)gridDim.x * WQ_NWARPS;
+    LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
+    unsigned int units = 0;
+    if (lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
+    unsigned int pend_est = 0;
+    __syncwarp();
+    Wq2Lane L; L.state = 0; L.hit1 = L.hit2 = false; L.node = WQ_NONE; L.sp = 0; L.pc = 0; L.tfar = 0.f;
+    L.A1x = L.A1y = L.A1z = L.B1x = L.B1y = L.B1z = 0.f; L.A2x = L.A2y = L.A2z = L.B2x = L.B2y = L.B2z = 0.f;
+    L.selxy = 0x74107410u;
+
+    for (long long base = ((long long)blockIdx.x * WQ_NWARPS + warp) * 32; base < total; base += warps_total * 32) {
+        const long long g = base + lane;
+        int loc = 0, k0 = 0;
+        bool has_unit = g < total;
+        if (has_unit) {
+            if (ALG == 2) loc = (int)g; else { loc = (int)(g / p.azim_num); k0 = (int)(g - (long long)loc * p.azim_num); }
+            if (org_valid[loc].w == 0.f) has_unit = false;          // the normal line missed the surface: output keeps NaN
+        }
+        Frame f; LocOut ob; ob.out = nullptr;
+        LaneSM m; m.phase = 0; m.k = k0; m.cur = m.prev = m.count = m.prev_az = 0; m.spec_ie = -1; m.spec_hit = false;
+        float dist_hit = -1.0f;          // -1: no cast of this azimuth hit (k_loc_dist_fix carries the previous azimuth's distance forward)
+        bool have_result = false;
+        if (has_unit) {
+            f = loc_frame(lp, org_valid, loc);
+            ob.out = lp.hori + (size_t)loc * p.azim_num;
+            units += (ALG == 2) ? (unsigned int)p.azim_num : 1u;
+        }
+        while (true) {
+            // lanes without a ray in flight consume the last result and ask the search for the next cast
+            if (has_unit && L.state == 0) {
+                bool hit = L.hit1;
+                if (have_result && L.node == WQ_OVF) {     // full traversal stack: this cast is decided by the binary-BVH walker
+                    L.node = WQ_NONE;
+                    const float* r = &sh.ray[warp][0][lane];
+                    float tf = s.dist;
+                    hit = trace_bvh2<WD>(sv, f3(r[0], r[32], r[64]), f3(r[96], r[128], r[160]), tf, cnt,
+                                         reinterpret_cast<unsigned int*>(&counters->stack_overflow));
+                    L.tfar = tf;
+                    atomicAdd(&counters->fallback_packets, 1ull);
+                }
+                if (WD && have_result && hit) dist_hit = L.tfar;                    // :546-553, :592-608
+                int ie = 0, lo_ie = -1; unsigned int extra = 0;
+                bool need = sm_advance<ALG, false, LocOut>(s, m, have_result, hit, ob, ie, lo_ie, extra);
+                if (ALG != 2 && m.k != k0) need = false;        // this lane owns ONE azimuth: the search has moved on to the next
+                if (need) {
+                    const F3 D = ray_dir(s, f, ie, ALG == 2 ? m.k : k0);
+                    wq2_start(sv, sh, warp, lane, L, f.org, D, D);
+                    L.tfar = s.dist; sh.tbest[warp][lane] = __float_as_uint(s.dist);
+                    have_result = true; cnt.rays++;
+                } else {
+                    if (WD) lp.hori_dist[(size_t)loc * p.azim_num + k0] = dist_hit;
+                    has_unit = false;
+                }
+            }
+            const unsigned int live = __ballot_sync(FULL, L.state != 0);
+            if (live == 0u) break;
+            const int thr = min(24, __popc(live));
+            __syncwarp();
+            while (__popc(wq2_step<false, false, WD>(sv, sh, warp, lane, tid, L, pend_est, s.dist, 2, cnt, stack_lim)) >= thr) {}
+        }
+    }
+    flush_counters(cnt, units, counters);
+}
+
 __global__ void k_loc_dist_fix(LocationParams lp, int azim_num, const float4* org_valid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= lp.num_loc || org_valid[i].w == 0.f) return;
@@ -586,21 +674,33 @@ int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationPar
     struct OrgGuard { float4* p; ~OrgGuard() { pool_free(p); } } org_guard{d_org};
     const SceneView sv = s.view();
     const int nb_loc = (lp.num_loc + 63) / 64;
-    k_loc_snap<<<nb_loc, 64, 0, st>>>(sv, lp, d_org, s.d_counters);
-    if (p.algorithm == 2) {
-        k_loc_chain<<<(lp.num_loc + 31) / 32, 32, 0, st>>>(sv, p, lp, d_org, s.d_counters);
-    } else {
-        const long long total = (long long)lp.num_loc * p.azim_num;
-        const int nb = (int)((total + 127) / 128);
-        if (p.algorithm == 0) {
-            if (lp.hori_dist_out) k_loc_indep<0, true><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
-            else k_loc_indep<0, false><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+    k_loc_snap<<<nb_loc, 64, 0, st>>>(sv, lp, d_org, s.d_counters);      // surface snap: two closest-hit rays per location (:951-957)
+    const long long total = (long long)lp.num_loc * p.azim_num;
+    if (debug_options().horizon_kernel == 1) {
+        // second implementation (parity tests): per-lane searches on the binary BVH
+        if (p.algorithm == 2) {
+            k_loc_chain<<<(lp.num_loc + 31) / 32, 32, 0, st>>>(sv, p, lp, d_org, s.d_counters);
         } else {
-            if (lp.hori_dist_out) k_loc_indep<1, true><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
-            else k_loc_indep<1, false><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+            const int nb = (int)((total + 127) / 128);
+            if (p.algorithm == 0) {
+                if (lp.hori_dist_out) k_loc_indep<0, true><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+                else k_loc_indep<0, false><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+            } else {
+                if (lp.hori_dist_out) k_loc_indep<1, true><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+                else k_loc_indep<1, false><<<nb, 128, 0, st>>>(sv, p, lp, d_org, s.d_counters);
+            }
         }
-        if (lp.hori_dist_out) k_loc_dist_fix<<<nb_loc, 64, 0, st>>>(lp, p.azim_num, d_org);
+    } else {
+        const long long units = p.algorithm == 2 ? (long long)lp.num_loc : total;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((units + WQ_BLOCK - 1) / WQ_BLOCK, (long long)sm_count() * 4));
+        const int stack_lim = std::max(1, std::min(debug_options().stack_limit, WQ_STACK_N));
+#define HZB_LOC(ALG_, WD_) k_loc_wq<ALG_, WD_><<<grid, WQ_BLOCK, 0, st>>>(sv, p, lp, d_org, s.d_counters, stack_lim)
+        if (p.algorithm == 2) HZB_LOC(2, false);
+        else if (p.algorithm == 0) { if (lp.hori_dist_out) HZB_LOC(0, true); else HZB_LOC(0, false); }
+        else { if (lp.hori_dist_out) HZB_LOC(1, true); else HZB_LOC(1, false); }
+#undef HZB_LOC
     }
+    if (lp.hori_dist_out && p.algorithm != 2) k_loc_dist_fix<<<nb_loc, 64, 0, st>>>(lp, p.azim_num, d_org);
     HZB_CUDA(cudaGetLastError());
     HZB_CUDA(cudaStreamSynchronize(st));
     return 0;

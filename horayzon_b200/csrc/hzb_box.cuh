@@ -15,6 +15,7 @@ struct Wq2Lane {
     float A1x, A1y, A1z, B1x, B1y, B1z;      // ray 1 (upper): t = qb * A + B, bias folded into B
     float A2x, A2y, A2z, B2x, B2y, B2z;      // ray 2 (lower)
     unsigned int selxy;                       // PRMT selectors of the near x (low half) / y (high half) planes, shared by both rays
+    float tfar;                               // closest-hit mode only: distance of the nearest hit so far (box tests cull beyond it)
 };
 
 // Reciprocal for the box tests only (never for a hit decision): the clamp keeps

@@ -38,6 +38,7 @@ struct Wq2Shared {
     float ray[WQ_NWARPS][9][32];              // O.xyz, D1.xyz, D2.xyz per lane
     unsigned int hit1[WQ_NWARPS], hit2[WQ_NWARPS];
     unsigned int rank_owner[WQ_NWARPS][32];
+    unsigned int tbest[WQ_NWARPS][32];        // closest-hit mode: bits of the nearest hit distance per lane (t >= 0: unsigned order = float order)
 };
 
 // Start the packet (D1, D2).  Returns false when the two rays cannot share the
@@ -114,10 +115,16 @@ __device__ __forceinline__ void prim_hit2(const SceneView& s, uint32_t prim, F3 
 // A full stack never invalidates a result: the lane stops its walk, drops its pending candidates and
 // retires with L.node == WQ_OVF; the caller marks the cell for the fix-up kernel (see HZB_REDO_F32).
 // stack_lim <= WQ_STACK_N (the tests lower it to force that path).
-template <bool TWO, bool SORT>
+// CLOSEST (single-ray mode only; castRay_intersect1, horizon_comp.cpp:268-292): no early exit on a hit; every
+// candidate is tested for its distance, the minimum per lane is kept in sh.tbest and in L.tfar, which culls the
+// boxes beyond it.  The result is the minimum of tri_hit's t over all triangles the ray meets -- the same value
+// in any traversal order.  The caller sets L.tfar and sh.tbest[warp][lane] to the ray's tfar at the start.
+template <bool TWO, bool SORT, bool CLOSEST = false>
 __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared& sh, const int warp, const int lane, const int tid,
-                                                 Wq2Lane& L, unsigned int& pend_est, const float tfar, const int wait_thr,
+                                                 Wq2Lane& L, unsigned int& pend_est, const float tfar_in, const int wait_thr,
                                                  LaneCounters& cnt, const int stack_lim) {
+    static_assert(!CLOSEST || !TWO, "closest-hit mode is single-ray");
+    const float tfar = CLOSEST ? L.tfar : tfar_in;
     const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     // ---- 1. node step (all lanes; lanes without a traversing packet read the root and are masked)
     const bool trav = L.state == 1;
@@ -242,7 +249,12 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
                     const float* r = &sh.ray[warp][0][owner];
                     const F3 O = f3(r[0], r[32], r[64]);
                     const F3 D1 = f3(r[96], r[128], r[160]), D2 = f3(r[192], r[224], r[256]);
-                    prim_hit2<TWO>(sv, prim, O, D1, D2, tfar, q1, q2);
+                    if (CLOSEST) {
+                        float tf = __uint_as_float(sh.tbest[warp][owner]);     // the owner's nearest hit so far
+                        if (prim_hit<true>(sv, prim, O, D1, tf)) { atomicMin(&sh.tbest[warp][owner], __float_as_uint(tf)); q1 = true; }
+                    } else {
+                        prim_hit2<TWO>(sv, prim, O, D1, D2, tfar, q1, q2);
+                    }
                     cnt.prims++;
                 }
                 if (q1) atomicOr(&sh.hit1[warp], 1u << owner);
@@ -259,6 +271,10 @@ __device__ __forceinline__ unsigned int wq2_step(const SceneView& sv, Wq2Shared&
             if ((m1 | m2) != 0u && lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
             if ((m1 >> lane) & 1u) L.hit1 = true;
             if (((TWO ? m2 : m1) >> lane) & 1u) L.hit2 = true;
+            if (CLOSEST) {
+                const float tb = __uint_as_float(sh.tbest[warp][lane]);
+                if (tb < L.tfar) L.tfar = tb;        // (a hit at exactly tfar is reported through hit1 like any other)
+            } else
             if (L.state != 0) {
                 if (L.hit1 && L.hit2) { L.state = 2; L.pc = 0; }          // both decided: drop the rest
                 else if (!TWO) {}

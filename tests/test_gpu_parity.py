@@ -172,6 +172,38 @@ def test_horizon_locations(mods, alg, dist_out):
     assert np.all(np.isnan(r_gpu[0][0]))
     for g, o in zip(r_gpu, r_cpu):
         assert np.array_equal(g, o, equal_nan=True)
+    # the per-lane binary-BVH kernels (second implementation) and a forced full-stack fallback give the same bits
+    for opt, val in (("horizon_kernel", 1), ("stack_limit", 2)):
+        hb.resident.debug_option(opt, val)
+        try:
+            r_alt = hb.horizon.horizon_locations(c["vert_grid"], 128, 128, coords, nrm, nth, 6.0, **kw)
+        finally:
+            hb.resident.debug_option("reset", 0)
+        for g, o in zip(r_alt, r_cpu):
+            assert np.array_equal(g, o, equal_nan=True), (opt, alg, dist_out)
+
+
+def test_horizon_locations_reference_use(mods):
+    """The reference's own use of horizon_locations (examples/horizon/locations_curved_DEM.py): 1440 azimuths,
+    hori_acc 0.1, distance to the horizon, per-location ray_org_elev -- here 150 locations on tilted frames."""
+    hb, oracle = mods
+    c, _ = _cfg(hb, "cfg2", n=301)
+    rng = np.random.default_rng(9)
+    n = 150
+    ij = rng.integers(20, 280, (n, 2))
+    coords = np.stack([c["x"][ij[:, 0], ij[:, 1]] + rng.uniform(-30, 30, n), c["y"][ij[:, 0], ij[:, 1]] + rng.uniform(-30, 30, n),
+                       c["z"][ij[:, 0], ij[:, 1]] + rng.uniform(-200, 200, n)], axis=1).astype(np.float32)
+    nrm = np.zeros((n, 3)); nrm[:, 2] = 1.0; nrm[:, :2] = rng.normal(0, 0.01, (n, 2)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nth = np.zeros((n, 3)); nth[:, 1] = 1.0; nth -= (nth * nrm).sum(axis=1, keepdims=True) * nrm; nth /= np.linalg.norm(nth, axis=1, keepdims=True)
+    roe = rng.uniform(0.5, 3.0, n).astype(np.float32)
+    kw = dict(azim_num=1440, hori_acc=0.1, ray_algorithm="binary_search", ray_org_elev=roe, hori_dist_out=True)
+    a = (c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], coords, nrm.astype(np.float32), nth.astype(np.float32), 15.0)
+    r_gpu = hb.horizon.horizon_locations(*a, **kw)
+    st = hb.resident.last_stats()
+    r_cpu = oracle.horizon_locations(*a, **kw)
+    for g, o in zip(r_gpu, r_cpu):
+        assert np.array_equal(g, o, equal_nan=True)
+    assert st["fallback_packets"] == 0
 
 
 def _terrain_inputs(hb, n=200, seed=5):

@@ -336,3 +336,29 @@ def test_product_state_machine_on_the_cpu(alg):
                                                             elev_ang_low_lim=low, ray_algorithm=alg, refuse_every=2)
         assert bad == 0 and ref == got
 
+
+
+def test_parity_sensitivity_to_the_rounding_of_the_triangle_test():
+    """The ray path is 'parity unpinned' (Embree absent).  What CAN be measured: how many outputs depend on the
+    rounding of the triangle test at all.  The oracle with the specified fp32 Pluecker arithmetic against the same
+    predicate in double on the exact inputs (no epsilon): a handful of outputs per million may move (by one
+    search step of 10 table entries), everything else is decided far from any rounding."""
+    import oracle
+    from horayzon_b200 import synthetic
+    total = diff = 0
+    for name, n, nrows in (("cfg1", None, 96), ("cfg2", 401, 12)):
+        c = synthetic.make_config(name, n)
+        sc = oracle.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+        rows = sorted(set(np.round(np.linspace(0, c["ny"] - 1, nrows)).astype(int).tolist()))
+        a = (rows, c["vec_norm"], c["vec_north"], c["offset_0"], c["offset_1"], c["dist_search"])
+        h32 = sc.horizon_rows(*a, azim_num=c["azim_num"])
+        oracle.set_exact_predicate(True)
+        try:
+            h64 = sc.horizon_rows(*a, azim_num=c["azim_num"])
+        finally:
+            oracle.set_exact_predicate(False)
+        sc.close()
+        total += h32.size; diff += int((h32 != h64).sum())
+        assert np.abs(h32 - h64).max() <= 2.1 * np.deg2rad(0.25) + 1e-6      # a flipped decision moves the bracket by one step
+    print("parity sensitivity: %d of %d outputs depend on the rounding of the triangle test" % (diff, total))
+    assert diff <= 1e-5 * total + 2
