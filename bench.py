@@ -442,6 +442,97 @@ def parity_sensitivity(c, K, nrows=6):
                        "(e.g. Embree's SIMD kernels) can be expected to change" % len(rows)}
 
 
+def run_cfg5(args):
+    """--workload cfg5: BASELINE configs[4], weak scaling.  24001 x 24001 DEM (576 M quads, 12.3 GB BVH) replicated on
+    every GPU; rank r computes inner rows [3000 r, 3000 (r + 1)) x 23999 columns x 180 azimuths + their SVF (SURVEY.md
+    8d/8e).  The 415 GB horizon array of the full domain cannot be gathered onto one GPU: the ranks all-gather the SVF
+    and keep their horizon shards (a host caller would copy each shard out over its own PCIe link)."""
+    import torch
+    import torch.distributed as dist
+    import horayzon_b200 as hb
+    from horayzon_b200 import resident
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = hb.synthetic.CONFIGS["cfg5"]
+    n, K, dist_km = cfg["n"], cfg["azim_num"], cfg["dist"]
+    rows_per_rank = args.cfg5_rows
+    nx = n - 2
+    vg = hb.synthetic.sinusoid_vert_grid(n, cfg["spacing"], cfg["amp"], cfg["wavelength"], cfg["seed"], cfg["octaves"])
+    scene = resident.Scene(vg, n, n, device=local_rank)
+    del vg
+    vn_np, vno_np = hb.synthetic.planar_frames(rows_per_rank, nx)
+    vn = torch.from_numpy(vn_np).to(dev); vno = torch.from_numpy(vno_np).to(dev)
+    del vn_np, vno_np
+    mask = torch.ones((rows_per_rank, nx), dtype=torch.uint8, device=dev)
+    hori = torch.empty((rows_per_rank, nx, K), dtype=torch.float32, device=dev)
+    tilt = torch.zeros((rows_per_rank, nx, 3), dtype=torch.float32, device=dev); tilt[..., 2] = 1.0   # horizontal surfaces: the SVF of the horizon alone
+    azim = torch.from_numpy(np.array([(2 * np.pi) / K * i for i in range(K)], np.float32)).to(dev)
+    svf_all = torch.empty((world * rows_per_rank, nx), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+    row0 = 1 + rank * rows_per_rank        # this rank's first DEM row (inner domain starts at row 1)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record(stream)
+        scene.horizon_gridded(vn, vno, mask, row0, 1, hori, 0, rows_per_rank, dist_search=dist_km, hori_acc=HORI_ACC,
+                              ray_algorithm=ALGORITHM, stream=stream)
+        if ev:
+            ev[1].record(stream)
+        mine = svf_all[rank * rows_per_rank:(rank + 1) * rows_per_rank]
+        resident.sky_view_factor_dev(azim, hori, tilt, mine, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(svf_all, mine)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    step(); barrier()                       # one warm pass (27 s per pass at 3000 rows: W = 1 here, stated in the line)
+    before = scene.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier(); t0.record(stream)
+    for i in range(args.steps):
+        step(kev[i])
+    t1.record(stream); barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    after = scene.stats()
+    mn, mean, mx, sm = rank_stats(torch, dist, world, dev, [t0.elapsed_time(t1), sum(a.elapsed_time(z) for a, z in kev) / args.steps,
+                                                           float(after["rays"] - before["rays"])])
+    units_rank = rows_per_rank * nx * K
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ab = 4.0 + 37.0 / K
+        ach = ab * units_rank / (mx[1] * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": world * units_rank * args.steps / (mx[0] * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": 1, "ms_per_step": mx[0] / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cfg5: 24001x24001 synthetic sinusoid DEM (spacing 90 m, 576 M quads), 180 azimuths, %s, hori_acc %.2f deg, "
+                                       "dist_search 50 km; every rank %d rows x %d columns against the replicated DEM, horizon+SVF"
+                                       % (ALGORITHM, HORI_ACC, rows_per_rank, nx),
+                           "parallelism": "rows [%d r, %d (r+1)) per rank, replicated DEM+BVH, 1 NCCL all-gather of the SVF per step" % (rows_per_rank, rows_per_rank),
+                           "l2": "per-step output %.1f GB and a 12.3 GB BVH >> 126 MB L2" % (units_rank * 4 / 1e9)},
+                "clocks": clocks, "gpu_launches": 2 * args.steps,
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                             "peak_source": peak_src, "kernel": KERNEL, "kernel_ms": mx[1],
+                             "kernel_ms_ranks": {"min": mn[1], "mean": mean[1], "max": mx[1]}, "algorithmic_bytes_per_unit": ab},
+                "counters": {"casts_per_unit": sm[2] / (world * units_rank * args.steps)},
+                "bvh": {"prims": int(after["num_prims"]), "bytes": int(after["bvh_bytes"]), "build_s": after["t_build"], "h2d_s": after["t_h2d"]}}
+        print(json.dumps(line), flush=True)
+    scene.close()
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -643,11 +734,14 @@ def main():
     ap.add_argument("--no-northstar", action="store_true")
     ap.add_argument("--northstar-rows", type=int, default=3, help="rows of the north-star pass checked against the CPU oracle")
     ap.add_argument("--no-shadow", action="store_true")
+    ap.add_argument("--cfg5-rows", type=int, default=3000, help="rows per rank of the cfg5 weak-scaling workload")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "cfg5":
+        run_cfg5(args)
     else:
         run_ours(args)
 
