@@ -115,6 +115,17 @@ int build_wide_bvh(Scene& s, cudaStream_t st) {
     }
     s.num_nodes4 = base;
     cudaFree(d_f0); cudaFree(d_f1); cudaFree(d_cnt);
+    // the node array was sized for the worst case (one wide node per binary node); a quadtree-shaped BVH needs a third
+    // of that: give the rest back when it is worth a copy (576 M quads: 36.9 GB -> 12.3 GB)
+    if ((size_t)cap > (size_t)base + base / 2 && (size_t)base * sizeof(Bvh4Node) > ((size_t)256 << 20)) {
+        Bvh4Node* exact = nullptr;
+        if (cudaMalloc((void**)&exact, (size_t)base * sizeof(Bvh4Node)) == cudaSuccess) {
+            HZB_CUDA(cudaMemcpyAsync(exact, s.d_nodes4, (size_t)base * sizeof(Bvh4Node), cudaMemcpyDeviceToDevice, st));
+            HZB_CUDA(cudaStreamSynchronize(st));
+            cudaFree(s.d_nodes4);
+            s.d_nodes4 = exact;
+        } else cudaGetLastError();
+    }
     HZB_CUDA(cudaGetLastError());
     return 0;
 }

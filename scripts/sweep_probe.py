@@ -1,5 +1,5 @@
-"""Exploratory: time the resident-tier horizon kernel under several env settings in ONE process
-(the launcher reads HZB_* at every call).  Usage: sweep_probe.py --cfg cfg2 --rows 400 "A=1,B=2" "A=3" ...
+"""Exploratory: time the resident-tier horizon kernel under several debug-option settings in ONE process
+(hzb_debug_option).  Usage: sweep_probe.py --cfg cfg2 --rows 400 "wrefill=20,wwait=3" "horizon_kernel=1" ...
 Not part of the product."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,9 +28,9 @@ hori = torch.empty((ny, nx, K), dtype=torch.float32, device=dev)
 ref = None
 touched = set()
 for setting in a.settings:
-    for k in touched: os.environ.pop(k, None)
+    resident.debug_option("reset", 0)
     for kv in filter(None, setting.split(",")):
-        k, v = kv.split("="); os.environ[k] = v; touched.add(k)
+        k, v = kv.split("="); resident.debug_option(k, int(v)); touched.add(k)
     best = None
     for rep in range(a.reps + 1):
         before = sc.stats()
