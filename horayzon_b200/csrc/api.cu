@@ -14,6 +14,7 @@
 #include <time.h>
 #include <stdlib.h>
 #include <mutex>
+#include <type_traits>
 #include <thread>
 
 namespace hzb {
@@ -62,9 +63,11 @@ int parse_ellps(const char* s) {
 
 DebugOptions& debug_options() { static DebugOptions o; return o; }
 
-// ---- device buffer pool: the big per-call buffers of the host tier (the 2 GB horizon array of a
-// 1201 x 1201 x 360 call) are kept between calls instead of cudaMalloc / cudaFree every time.
-// Idle memory is bounded (HZB_POOL_IDLE_MAX) and released by hzb_trim().
+// ---- device buffer pool: EVERY device allocation of the library (scene, BVH, build temporaries, per-call
+// buffers of the host tier such as the 2 GB horizon array of a 1201 x 1201 x 360 call) comes from here and goes
+// back here, so that a repeated host-tier call makes no cudaMalloc / cudaFree at all -- on some hosts those cost
+// tens of milliseconds EACH (a BVH build with its 30 allocations was measured at 6 ms on one box and 1.1 s on
+// another).  Idle memory is bounded (HZB_POOL_IDLE_MAX, 96 blocks) and released by hzb_trim().
 namespace {
 struct DevPool {
     std::mutex mu;
@@ -83,7 +86,7 @@ void* pool_alloc(size_t bytes) {
     std::lock_guard<std::mutex> l(P.mu);
     int best = -1;
     for (int i = 0; i < (int)P.idle.size(); ++i)
-        if (P.idle[i].dev == dev && P.idle[i].cap >= bytes && P.idle[i].cap <= bytes + bytes / 4 + 4096 &&
+        if (P.idle[i].dev == dev && P.idle[i].cap >= bytes && P.idle[i].cap <= bytes + bytes / 4 + 65536 &&
             (best < 0 || P.idle[i].cap < P.idle[best].cap)) best = i;
     DevPool::Blk b{nullptr, 0, dev};
     if (best >= 0) { b = P.idle[best]; P.idle.erase(P.idle.begin() + best); P.idle_bytes -= b.cap; }
@@ -108,9 +111,9 @@ void pool_free(void* p) {
         if (P.live[i].p == p) {
             DevPool::Blk b = P.live[i];
             P.live.erase(P.live.begin() + i);
-            if (b.cap < ((size_t)1 << 20) || b.cap > HZB_POOL_IDLE_MAX) { cudaFree(b.p); return; }
+            if (b.cap > HZB_POOL_IDLE_MAX) { cudaFree(b.p); return; }
             P.idle.push_back(b); P.idle_bytes += b.cap;
-            while (P.idle_bytes > HZB_POOL_IDLE_MAX || P.idle.size() > 8) {        // oldest first
+            while (P.idle_bytes > HZB_POOL_IDLE_MAX || P.idle.size() > 96) {       // oldest first
                 cudaFree(P.idle[0].p); P.idle_bytes -= P.idle[0].cap; P.idle.erase(P.idle.begin());
             }
             return;
@@ -127,7 +130,23 @@ void pool_trim() {
 }
 
 // ---- per-thread, per-device host-tier context: two streams (compute / copy) created once
-struct HostCtx { int dev = -1; cudaStream_t comp = nullptr, copy = nullptr; };
+struct HostCtx {
+    int dev = -1; cudaStream_t comp = nullptr, copy = nullptr;
+    cudaEvent_t done = nullptr;                                   // "compute stream finished" of the call in flight
+    unsigned int* h_flags = nullptr; unsigned int* d_flags = nullptr; size_t flags_cap = 0;   // mapped host memory: row-block progress flags
+    int flags(size_t n) {
+        if (n > flags_cap) {
+            if (h_flags) cudaFreeHost(h_flags);
+            h_flags = nullptr; flags_cap = 0;
+            const size_t cap = std::max<size_t>(n, 8192);
+            HZB_CUDA(cudaHostAlloc((void**)&h_flags, cap * sizeof(unsigned int), cudaHostAllocMapped));
+            HZB_CUDA(cudaHostGetDevicePointer((void**)&d_flags, h_flags, 0));
+            flags_cap = cap;
+        }
+        memset(h_flags, 0, n * sizeof(unsigned int));
+        return 0;
+    }
+};
 static int host_ctx(HostCtx** out) {
     static thread_local std::vector<HostCtx> ctxs;
     int dev = 0;
@@ -136,6 +155,7 @@ static int host_ctx(HostCtx** out) {
     HostCtx c; c.dev = dev;
     HZB_CUDA(cudaStreamCreateWithFlags(&c.comp, cudaStreamNonBlocking));
     HZB_CUDA(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    HZB_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
     ctxs.push_back(c);
     *out = &ctxs.back();
     return 0;
@@ -216,7 +236,7 @@ struct hzb_terrain {
         return 0;
     }
     void release() {
-        cudaFree(d_tilt); cudaFree(d_norm); cudaFree(d_enl); cudaFree(d_elev); cudaFree(d_mask); cudaFree(d_out);
+        pool_free(d_tilt); pool_free(d_norm); pool_free(d_enl); pool_free(d_elev); pool_free(d_mask); pool_free(d_out);
         d_tilt = d_norm = d_enl = d_elev = nullptr; d_mask = nullptr; d_out = nullptr; out_cap = 0;
         if (s_comp) cudaStreamDestroy(s_comp);
         if (s_copy) cudaStreamDestroy(s_copy);
@@ -444,13 +464,11 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
     const bool overlap = !azim_first && !dbg.no_overlap && dbg.horizon_kernel == 0;
     DevBuf<unsigned int> d_done;
     unsigned int* h_flags = nullptr; unsigned int* d_flags = nullptr;
-    struct PinGuard { unsigned int*& p; ~PinGuard() { if (p) cudaFreeHost(p); } } pguard{h_flags};
     if (overlap) {
         HZB_TRY(d_done.alloc((size_t)tiles_y));
         HZB_CUDA(cudaMemsetAsync(d_done.p, 0, (size_t)tiles_y * sizeof(unsigned int), s_comp));
-        HZB_CUDA(cudaHostAlloc((void**)&h_flags, (size_t)tiles_y * sizeof(unsigned int), cudaHostAllocMapped));
-        memset(h_flags, 0, (size_t)tiles_y * sizeof(unsigned int));
-        HZB_CUDA(cudaHostGetDevicePointer((void**)&d_flags, h_flags, 0));
+        HZB_TRY(ctx->flags((size_t)tiles_y));          // persistent mapped buffer of this thread / device, cleared
+        h_flags = ctx->h_flags; d_flags = ctx->d_flags;
     }
     HZB_TRY(horizon_gridded_launch(h->s, d_norm.p, d_north.p, d_mask.p, offset_0, offset_1, dim_in_0, dim_in_1, 0, dim_in_0,
                                    azim_num, dist_search, hori_acc, ray_algorithm, elev_ang_low_lim, hori_fill,
@@ -459,9 +477,7 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
         if (azim_first) { set_error("the fused sky view factor needs the reference layout (azim_first = 0)"); cudaStreamSynchronize(s_comp); return 1; }
         HZB_TRY(launch_svf(0, d_azim.p, d_hori.p, d_tilt.p, (long long)nc, azim_num, d_svf.p, s_comp));
     }
-    cudaEvent_t ev_done = nullptr;
-    HZB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
-    struct EvGuard { cudaEvent_t e; ~EvGuard() { cudaEventDestroy(e); } } evguard{ev_done};
+    cudaEvent_t ev_done = ctx->done;
     HZB_CUDA(cudaEventRecord(ev_done, s_comp));
     double t_d2h = 0.0, t_trace = 0.0;
     const size_t row_elems = (size_t)dim_in_1 * (size_t)azim_num;
@@ -665,7 +681,8 @@ int hzb_terrain_initialise(hzb_terrain* t, const float* vert_grid, int dem_dim_0
     HZB_TRY(scene_upload_and_build(t->s, vert_grid, dem_dim_0, dem_dim_1, nullptr, 0, nullptr, 0));
     const size_t nc = (size_t)dim_in_0 * dim_in_1;
     auto up = [&](auto** d, const auto* h, size_t n) -> int {
-        HZB_CUDA(cudaMalloc((void**)d, (n ? n : 1) * sizeof(**d)));
+        *d = (std::remove_reference_t<decltype(*d)>)pool_alloc((n ? n : 1) * sizeof(**d));
+        if (!*d) return 1;
         HZB_CUDA(cudaMemcpy(*d, h, n * sizeof(**d), cudaMemcpyHostToDevice));
         return 0;
     };
@@ -685,8 +702,9 @@ int hzb_terrain_initialise(hzb_terrain* t, const float* vert_grid, int dem_dim_0
 
 static int terrain_out(hzb_terrain* t, size_t bytes) {
     if (t->out_cap < bytes) {
-        cudaFree(t->d_out); t->d_out = nullptr; t->out_cap = 0;
-        HZB_CUDA(cudaMalloc(&t->d_out, bytes));
+        pool_free(t->d_out); t->d_out = nullptr; t->out_cap = 0;
+        t->d_out = pool_alloc(bytes);
+        if (!t->d_out) return 1;
         t->out_cap = bytes;
     }
     return 0;

@@ -351,8 +351,8 @@ __global__ void k_refit(PrimGeom g, const uint32_t* __restrict__ sorted_prims, u
 
 template <typename T>
 int dalloc(T** p, size_t n) {
-    HZB_CUDA(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
-    return 0;
+    *p = (T*)pool_alloc(std::max<size_t>(n, 1) * sizeof(T));     // pooled: a repeated call allocates nothing
+    return *p ? 0 : 1;
 }
 
 int exclusive_scan_u32(uint32_t* d_in, uint32_t* d_out, size_t m, uint32_t* d_sums, cudaStream_t st) {
@@ -368,9 +368,9 @@ int exclusive_scan_u32(uint32_t* d_in, uint32_t* d_out, size_t m, uint32_t* d_su
 
 
 void scene_free(Scene& s) {
-    cudaFree(s.d_vert4); cudaFree(s.d_tin4); cudaFree(s.d_nodes2); cudaFree(s.d_nodes4);
-    cudaFree(s.d_prim_ids); cudaFree(s.d_counters); cudaFree(s.d_tile_counter);
-    for (Scene::TableEntry& e : s.tables) cudaFree(e.d);
+    pool_free(s.d_vert4); pool_free(s.d_tin4); pool_free(s.d_nodes2); pool_free(s.d_nodes4);
+    pool_free(s.d_prim_ids); pool_free(s.d_counters); pool_free(s.d_tile_counter);
+    for (Scene::TableEntry& e : s.tables) pool_free(e.d);
     s.tables.clear();
     s.d_vert4 = nullptr; s.d_tin4 = nullptr; s.d_nodes2 = nullptr; s.d_nodes4 = nullptr; s.d_prim_ids = nullptr;
     s.d_counters = nullptr; s.d_tile_counter = nullptr;
@@ -391,7 +391,7 @@ int scene_upload_and_build(Scene& s, const float* vert_grid, int H, int W, const
     struct Tmp {
         std::vector<void**> slots;
         void own(void** p) { slots.push_back(p); }
-        ~Tmp() { for (void** p : slots) if (*p) { cudaFree(*p); *p = nullptr; } }
+        ~Tmp() { for (void** p : slots) if (*p) { pool_free(*p); *p = nullptr; } }
     } tmp;
 #define HZB_TMP(ptr) tmp.own((void**)&(ptr))
 

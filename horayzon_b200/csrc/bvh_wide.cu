@@ -94,10 +94,12 @@ int build_wide_bvh(Scene& s, cudaStream_t st) {
         g.inv_step[a] = 1.0 / (double)s.qstep[a];
     }
     uint32_t *d_f0 = nullptr, *d_f1 = nullptr; unsigned int* d_cnt = nullptr;
-    HZB_CUDA(cudaMalloc((void**)&s.d_nodes4, (size_t)cap * sizeof(Bvh4Node)));
-    HZB_CUDA(cudaMalloc((void**)&d_f0, (size_t)cap * sizeof(uint32_t)));
-    HZB_CUDA(cudaMalloc((void**)&d_f1, (size_t)cap * sizeof(uint32_t)));
-    HZB_CUDA(cudaMalloc((void**)&d_cnt, sizeof(unsigned int)));
+    s.d_nodes4 = (Bvh4Node*)pool_alloc((size_t)cap * sizeof(Bvh4Node));
+    d_f0 = (uint32_t*)pool_alloc((size_t)cap * sizeof(uint32_t));
+    d_f1 = (uint32_t*)pool_alloc((size_t)cap * sizeof(uint32_t));
+    d_cnt = (unsigned int*)pool_alloc(sizeof(unsigned int));
+    struct TmpGuard { uint32_t*& a; uint32_t*& b; unsigned int*& c; ~TmpGuard() { pool_free(a); pool_free(b); pool_free(c); a = b = nullptr; c = nullptr; } } tguard{d_f0, d_f1, d_cnt};
+    if (!s.d_nodes4 || !d_f0 || !d_f1 || !d_cnt) return 1;
     const uint32_t root = 0;
     HZB_CUDA(cudaMemcpyAsync(d_f0, &root, sizeof(root), cudaMemcpyHostToDevice, st));
     uint32_t count = 1, base = 0;
@@ -114,17 +116,16 @@ int build_wide_bvh(Scene& s, cudaStream_t st) {
         if (++levels > 4096) { set_error("wide BVH too deep"); return 1; }
     }
     s.num_nodes4 = base;
-    cudaFree(d_f0); cudaFree(d_f1); cudaFree(d_cnt);
     // the node array was sized for the worst case (one wide node per binary node); a quadtree-shaped BVH needs a third
     // of that: give the rest back when it is worth a copy (576 M quads: 36.9 GB -> 12.3 GB)
     if ((size_t)cap > (size_t)base + base / 2 && (size_t)base * sizeof(Bvh4Node) > ((size_t)256 << 20)) {
-        Bvh4Node* exact = nullptr;
-        if (cudaMalloc((void**)&exact, (size_t)base * sizeof(Bvh4Node)) == cudaSuccess) {
+        Bvh4Node* exact = (Bvh4Node*)pool_alloc((size_t)base * sizeof(Bvh4Node));
+        if (exact) {
             HZB_CUDA(cudaMemcpyAsync(exact, s.d_nodes4, (size_t)base * sizeof(Bvh4Node), cudaMemcpyDeviceToDevice, st));
             HZB_CUDA(cudaStreamSynchronize(st));
-            cudaFree(s.d_nodes4);
+            pool_free(s.d_nodes4);
             s.d_nodes4 = exact;
-        } else cudaGetLastError();
+        }
     }
     HZB_CUDA(cudaGetLastError());
     return 0;

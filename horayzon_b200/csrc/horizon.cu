@@ -63,7 +63,7 @@ int scene_tables(Scene& s, int azim_num, float dist_km, float acc_deg, float low
     if (!hit) {
         if (s.tables.size() >= 32) {   // bounded cache: drop everything once nothing can be in flight any more
             HZB_CUDA(cudaDeviceSynchronize());
-            for (Scene::TableEntry& e : s.tables) cudaFree(e.d);
+            for (Scene::TableEntry& e : s.tables) pool_free(e.d);
             s.tables.clear();
         }
         const size_t need = (size_t)2 * T.azim_num + (size_t)3 * T.elev_num;
@@ -75,10 +75,11 @@ int scene_tables(Scene& s, int azim_num, float dist_km, float acc_deg, float low
         memcpy(q, T.elev_sin.data(), 4 * (size_t)T.elev_num); q += T.elev_num;
         memcpy(q, T.elev_cos.data(), 4 * (size_t)T.elev_num);
         Scene::TableEntry e{azim_num, acc_deg, low_deg, dist_km, nullptr, T.elev_num};
-        HZB_CUDA(cudaMalloc((void**)&e.d, need * sizeof(float)));
+        e.d = (float*)pool_alloc(need * sizeof(float));
+        if (!e.d) return 1;
         // pageable source: the call returns once the data has left `h` (first use of a parameter set only)
         if (cudaMemcpyAsync(e.d, h.data(), need * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(e.d); set_error("table upload failed"); cudaGetLastError(); return 1; }
+            cudaStreamSynchronize(st) != cudaSuccess) { pool_free(e.d); set_error("table upload failed"); cudaGetLastError(); return 1; }
         s.tables.push_back(e);
         hit = &s.tables.back();
     }
