@@ -118,6 +118,7 @@ int hzb_horizon_gridded_multi(const float* vert_grid, int dem_dim_0, int dem_dim
     for (int i = 0; i < azim_num; ++i) az[i] = (float)((2 * M_PI) / azim_num * i);    // horizon.pyx:190-195
     const size_t nc = (size_t)dim_in_0 * dim_in_1;
 
+    const bool out_pinned = host_is_pinned(hori_buffer);
     auto fail = [&](int r, const std::string& m) { res[r].rc = 1; res[r].err = m; };
     // ---- phase 1 (thread per shard): scene, inputs, kernels into the packed shard buffer
     auto phase1 = [&](int r) {
@@ -174,7 +175,11 @@ int hzb_horizon_gridded_multi(const float* vert_grid, int dem_dim_0, int dem_dim
             const int row0 = (j * n + r) * 4;
             const int nrows = std::min(4, dim_in_0 - row0);
             if (nrows <= 0) break;
-            if (staged_d2h(hori_buffer + (size_t)row0 * row_elems, mine + (size_t)j * 4 * row_elems, (size_t)nrows * row_elems * sizeof(float), streams[r])) {
+            float* dst = hori_buffer + (size_t)row0 * row_elems;
+            const size_t bytes = (size_t)nrows * row_elems * sizeof(float);
+            if (out_pinned) {   // page-locked output (hzb_host_alloc): plain DMA, every GPU over its own PCIe link at once
+                if (cudaMemcpyAsync(dst, mine + (size_t)j * 4 * row_elems, bytes, cudaMemcpyDeviceToHost, streams[r]) != cudaSuccess) { fail(r, "copy failed"); return; }
+            } else if (staged_d2h(dst, mine + (size_t)j * 4 * row_elems, bytes, streams[r])) {   // pageable: the process-wide staging engine
                 fail(r, hzb_last_error()); return;
             }
             if (svf_buffer && cudaMemcpyAsync(svf_buffer + (size_t)row0 * dim_in_1, d_svf[r] + (size_t)j * 4 * dim_in_1, (size_t)nrows * dim_in_1 * 4,
