@@ -150,6 +150,16 @@ def test_compute_fails_loudly_without_gpu():
         hb.topo_param.sky_view_factor(np.zeros(4, np.float32), np.zeros((2, 2, 4), np.float32), np.ones((2, 2, 3), np.float32))
     with pytest.raises(RuntimeError, match="no CUDA device"):
         resident.Scene(c["vert_grid"], 48, 48)
+    # the additive entry points of round 2: fused SVF, multi-GPU, quantised output, replicated terrains
+    tilt = np.zeros((c["ny"], c["nx"], 3), np.float32); tilt[..., 2] = 1.0
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.horizon.horizon_gridded(*_hg_args(c), svf_vec_tilt=tilt)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.horizon.horizon_gridded(*_hg_args(c), devices=0)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.horizon.horizon_gridded_quantised(*_hg_args(c))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        hb.multi.MultiTerrain(devices=0)
     lon = np.array([[8.0, 8.1]]); lat = np.array([[46.0, 46.0]])
     with pytest.raises(RuntimeError, match="no CUDA device"):
         hb.transform.lonlat2ecef(lon, lat, np.zeros((1, 2), np.float32), ellps="WGS84")
@@ -232,3 +242,29 @@ def test_product_tables_equal_the_oracle_tables():
         for got, key in zip(bufs, ("elev_ang", "elev_sin", "elev_cos", "azim_sin", "azim_cos")):
             assert np.array_equal(got, want[key]), (key, azim_num, acc)
 
+
+
+def test_round2_additive_api_validation():
+    """Argument checks of the additive keywords (no device needed: they fire before any native call)."""
+    c = syn.make_config("cfg1", n=48)
+    a = _hg_args(c)
+    tilt = np.zeros((c["ny"], c["nx"], 3), np.float32); tilt[..., 2] = 1.0
+    with pytest.raises(ValueError, match="incorrect shape"):
+        hb.horizon.horizon_gridded(*a, svf_vec_tilt=tilt[1:])
+    with pytest.raises(ValueError, match="azim_first"):
+        hb.horizon.horizon_gridded(*a, svf_vec_tilt=tilt, azim_first=True)
+    with pytest.raises(ValueError, match="at least two azimuth"):
+        hb.horizon.horizon_gridded(*a, svf_vec_tilt=tilt, azim_num=1)
+    with pytest.raises(ValueError, match="must not be negative"):
+        hb.horizon.horizon_gridded(*a, vert_simp=np.zeros(9, np.float32), num_vert_simp=3,
+                                   tri_ind_simp=np.array([0, 1, -2], np.int32), num_tri_simp=1)
+    with pytest.raises(ValueError, match="16-bit output"):
+        hb.horizon.horizon_gridded_quantised(*a, hori_acc=0.001)          # 525 000 table entries
+    idx = np.array([[[0xFFFF, 3, 5], [0xFFFF, 0xFFFF, 0xFFFF]]], np.uint16)
+    got = hb.horizon.dequantise(idx, np.array([[0.25, -1.0]], np.float32), np.arange(10, dtype=np.float32))
+    assert got.dtype == np.float32 and np.array_equal(got, np.array([[[0.25, 3, 5], [-1, -1, -1]]], np.float32))
+    # the debug switches are explicit calls, not environment variables; unknown names are refused
+    assert resident.lib().hzb_debug_option(b"reset", 0) == 0
+    assert resident.lib().hzb_debug_option(b"no_such_option", 1) != 0
+    assert resident.lib().hzb_shard_rows(1199, 0, 8) == 152 and resident.lib().hzb_shard_rows(1199, 7, 8) == 148
+    assert sum(resident.lib().hzb_shard_rows(1199, r, 8) for r in range(8)) == 1200
