@@ -202,7 +202,9 @@ def run_reference(args):
     c = syn.make_config(args.workload)
     K = c["azim_num"]
     smp = OracleSampler(c, K)
-    rows = smp.size_sample(args.ref_seconds)
+    # a step = a bounded sample of the workload, sized so that the whole run (warm-up + steps) stays near two minutes
+    per_step = max(2.0, min(args.ref_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    rows = smp.size_sample(per_step)
     for _ in range(args.warmup):
         smp.sample(rows)
     vals = [smp.sample(rows) for _ in range(args.steps)]
