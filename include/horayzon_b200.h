@@ -269,8 +269,13 @@ int hzb_scene_stats(const hzb_scene* s, hzb_stats* out);
 /* Horizon for rows [row_begin, row_end) of the inner domain.  d_* are DEVICE
  * pointers to the FULL inner-domain arrays ([dim_in_0][dim_in_1][...]); only
  * the selected rows are read / written.  stream is a cudaStream_t (NULL = the
- * legacy default stream).  Asynchronous; counters accumulate into the scene
- * and are read (after synchronising) with hzb_scene_stats. */
+ * legacy default stream).  Asynchronous: nothing on the launch path synchronises
+ * once the tables of a parameter set (azim_num, dist_search, hori_acc,
+ * elev_ang_low_lim) have been uploaded by their first use.  Launches on DIFFERENT
+ * streams against one scene may overlap (every launch has its own work-queue
+ * counter, the cached tables are never overwritten); calls on one scene must come
+ * from one host thread at a time.  Counters accumulate into the scene and are read
+ * (after synchronising) with hzb_scene_stats. */
 int hzb_horizon_gridded_dev(hzb_scene* s,
                             const float* d_vec_norm, const float* d_vec_north,
                             const uint8_t* d_mask,
