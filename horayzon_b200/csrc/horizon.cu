@@ -646,7 +646,10 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
         // a warp leaves the traversal loop to refill when fewer than w_refill lanes hold a packet; pending
         // candidates are flushed when w_wait lanes wait on theirs (tuned on B200)
         const int w_refill = o.wrefill, w_wait = o.wwait, stack_lim = std::max(1, std::min(o.stack_limit, WQ_STACK_N));
-        constexpr int MB = 5;   // resident CTAs per SM (93 registers, 31 KB shared memory)
+#ifndef HZB_MB
+#define HZB_MB 6
+#endif
+        constexpr int MB = HZB_MB;   // resident CTAs per SM (80 registers, 26 KB shared memory): the walk is bound by per-warp latency, a sixth CTA is worth 2-7 %
         if (p.hori_q) {   // quantised output: guess_constant only (checked by the caller)
             k_horizon_wq6<2, MB, true><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim);
         } else switch (p.algorithm) {

@@ -80,7 +80,7 @@ struct DebugOptions {
     int shadow_kernel = 0;    // 0 production, 1 reference-shaped per-lane kernel, 2 production step with nearest-first order
     int wrefill = 24, wwait = 2;
     int no_overlap = 0;       // host tier: copy the horizon array after the kernel instead of while it runs
-    int stack_limit = 36;     // <= WQ_STACK_N; lowered by the tests to force the full-stack fallback
+    int stack_limit = 1 << 20; // clamped to WQ_STACK_N; lowered by the tests to force the full-stack fallback
     int horizon_variant = 0;  // A/B experiments inside the production kernel family
 };
 DebugOptions& debug_options();

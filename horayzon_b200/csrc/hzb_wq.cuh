@@ -6,7 +6,12 @@ namespace hzb {
 
 constexpr int WQ_BLOCK = 128;                 // threads per CTA
 constexpr int WQ_NWARPS = WQ_BLOCK / 32;
-constexpr int WQ_STACK_N = 36;                // shared-memory stack entries per lane (a full stack ends the walk safely, see hzb_wq2.cuh)
+#ifndef HZB_WQ_STACK_N
+#define HZB_WQ_STACK_N 26
+#endif
+constexpr int WQ_STACK_N = HZB_WQ_STACK_N;    // shared-memory stack entries per lane.  26 (+3 spare rows) keeps six CTAs per SM inside the
+                                              // 164 KB shared-memory carve-out (92 KB of L1 left); a full stack ends the walk safely (hzb_wq2.cuh):
+                                              // the cell is recomputed by the fix-up kernel.  No scene up to 576 M quads has needed more than 26.
 constexpr uint32_t WQ_NONE = 0xFFFFFFFFu;
 
 }  // namespace hzb
