@@ -178,6 +178,7 @@ static int read_counters(const Scene& s, hzb_stats& st) {
     HZB_CUDA(cudaMemcpy(&c, s.d_counters, sizeof(c), cudaMemcpyDeviceToHost));
     st.rays = c.rays; st.node_visits = c.node_visits; st.prim_tests = c.prim_tests; st.units = c.units;
     st.warp_node_visits = c.warp_node_visits; st.fallback_packets = c.fallback_packets;
+    st.segment_tasks = c.segment_tasks; st.segment_redos = c.segment_redos;
     st.num_prims = s.num_prims; st.num_nodes = s.num_nodes4; st.bvh_bytes = s.bvh_bytes;
     st.t_h2d = s.t_h2d; st.t_build = s.t_build;
     if (c.stack_overflow) { set_error("binary-BVH walker stack overflow (results invalid)"); return 1; }
@@ -284,6 +285,10 @@ int hzb_debug_option(const char* name, int value) {
     if (!strcmp(name, "no_overlap")) { o.no_overlap = value; return 0; }
     if (!strcmp(name, "stack_limit")) { o.stack_limit = value; return 0; }
     if (!strcmp(name, "horizon_variant")) { o.horizon_variant = value; return 0; }
+    if (!strcmp(name, "ctas_per_sm")) { o.ctas_per_sm = value; return 0; }
+    if (!strcmp(name, "tail_segments")) { o.tail_segments = value; return 0; }
+    if (!strcmp(name, "tail_tiles")) { o.tail_tiles = value; return 0; }
+    if (!strcmp(name, "tail_band")) { o.tail_band = value; return 0; }
     set_error(std::string("unknown debug option ") + name);
     return 1;
 }
@@ -518,13 +523,16 @@ static int horizon_gridded_host(const float* vert_grid, int dem_dim_0, int dem_d
         HZB_CUDA(cudaStreamSynchronize(s_comp));
         HZB_CUDA(cudaStreamSynchronize(s_copy));
         if (t_trace == 0.0) t_trace = now_s() - t0;
-        // Cells whose traversal stack was full were recomputed by the fix-up kernel AFTER their row block had been
-        // copied: copy the array again (never happens in practice; the tests force it with a tiny stack limit).
-        Counters cc;
-        HZB_CUDA(cudaMemcpy(&cc, h->s.d_counters, sizeof(cc), cudaMemcpyDeviceToHost));
-        if (cc.fallback_packets != 0) {
-            if (out_pinned) HZB_CUDA(cudaMemcpy(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), cudaMemcpyDeviceToHost));
-            else HZB_TRY(staged_d2h(hori_buffer, d_hori.p, nc * (size_t)azim_num * sizeof(float), nullptr));
+        // Row blocks the fix-up kernel rewrote (cells whose traversal stack was full, azimuth segments that started
+        // from a wrong index) AFTER they had been copied carry flag 2: they are copied again (rare; the tests force it).
+        for (int b = 0; b < tiles_y; ++b) {
+            if (flags[b] != 2u) continue;
+            int e = b + 1;
+            while (e < tiles_y && flags[e] == 2u) ++e;
+            const size_t r0 = (size_t)b * 4, r1 = std::min<size_t>((size_t)e * 4, (size_t)dim_in_0);
+            if (out_pinned) HZB_CUDA(cudaMemcpy(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float), cudaMemcpyDeviceToHost));
+            else HZB_TRY(staged_d2h(hori_buffer + r0 * row_elems, d_hori.p + r0 * row_elems, (r1 - r0) * row_elems * sizeof(float), nullptr));
+            b = e - 1;
         }
     } else {
         HZB_CUDA(cudaStreamSynchronize(s_comp));

@@ -23,6 +23,8 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
+#include <vector>
 
 namespace hzb {
 
@@ -189,14 +191,16 @@ __device__ __forceinline__ void out_init<true>(OutBufQ& ob, const HorizonParams&
     ob.init(p.hori_q + slot * p.stride_c, p.hori_first + slot, p.stride_k);
 }
 
-// One cell, all azimuths.  ALG 0 discrete_sampling (:302-333), 1 binary_search
-// (:339-381), 2 guess_constant (:387-498).  Termination rule: a hit
+// One cell, the azimuths [k_begin, k_end) (all of them by default).  ALG 0 discrete_sampling (:302-333), 1 binary_search
+// (:339-381), 2 guess_constant (:387-498); a guess_constant range that does not start at azimuth 0 continues the
+// chain from prev_az, the table index of azimuth k_begin - 1.  Termination rule: a hit
 // at the top index counts as a miss, a miss at index 0 as a hit.
 template <int ALG, typename OB>
-__device__ void cell_search(const Search& s, const Frame& f, OB& ob, LaneCounters& cnt) {
+__device__ void cell_search(const Search& s, const Frame& f, OB& ob, LaneCounters& cnt, int k_begin = 0, int k_end = -1, int prev_az = 0) {
     const int top = s.elev_num - 1;
+    if (k_end < 0) k_end = s.azim_num;
     if (ALG == 0) {
-        for (int k = 0; k < s.azim_num; ++k) {
+        for (int k = k_begin; k < k_end; ++k) {
             int cur = 0, prev = 0; bool hit = true;
             while (hit) {
                 prev = cur; cur = min(cur + 10, top);
@@ -206,16 +210,19 @@ __device__ void cell_search(const Search& s, const Frame& f, OB& ob, LaneCounter
             ob.put(k, midpoint(__ldg(s.elev_ang + prev), __ldg(s.elev_ang + cur)));
         }
     } else if (ALG == 1) {
-        for (int k = 0; k < s.azim_num; ++k) {
+        for (int k = k_begin; k < k_end; ++k) {
             float mid, dh = 0.f;
             bisect<false>(s, f, k, cnt, mid, dh);
             ob.put(k, mid);
         }
     } else {
-        float mid, dh = 0.f;
-        int prev_az = bisect<false>(s, f, 0, cnt, mid, dh);
-        ob.put(0, mid);
-        for (int k = 1; k < s.azim_num; ++k) {
+        if (k_begin == 0) {
+            float mid, dh = 0.f;
+            prev_az = bisect<false>(s, f, 0, cnt, mid, dh);
+            ob.put(0, mid);
+            k_begin = 1;
+        }
+        for (int k = k_begin; k < k_end; ++k) {
             int cur = max(prev_az - 5, 0), prev = 0, count = 0; bool hit = true;
             while (hit) {
                 prev = cur; cur = min(cur + 10, top);
@@ -253,9 +260,9 @@ __device__ __forceinline__ void flush_counters(LaneCounters& cnt, unsigned int u
 // A finished cell (or empty cell slot) of row block `blk`: its outputs are made visible system-wide, the
 // block's counter goes up, and the lane that completes the block raises the block's flag in mapped host
 // memory -- the host tier polls those flags and copies finished blocks while the kernel is still running.
-__device__ __forceinline__ void publish_cell(const HorizonParams& p, int blk) {
+__device__ __forceinline__ void publish_cell(const HorizonParams& p, int blk, unsigned int slots) {
     __threadfence_system();
-    if (atomicAdd(p.row_done + blk, 1u) == p.row_full - 1u && p.row_flags) {
+    if (atomicAdd(p.row_done + blk, 1u) == slots - 1u && p.row_flags) {
         __threadfence_system();
         p.row_flags[blk] = 1u;
     }
@@ -265,6 +272,84 @@ __device__ __forceinline__ void publish_cell(const HorizonParams& p, int blk) {
 __device__ __forceinline__ int local_blocks(const HorizonParams& p, int rows) {
     const int all = (rows + 3) >> 2;
     return all > p.blk_offset ? (all - p.blk_offset + p.blk_stride - 1) / p.blk_stride : 0;
+}
+
+// ---------------------------------------------------------------------------
+// Queue order and azimuth segments.
+//
+// A cell's guess_constant search is a chain over the azimuths (azimuth k starts from the index of k-1), ~40 ms long on
+// cfg2, and a launch ends when the last chain ends: with few cells per resident lane (the eighth of cfg2 one GPU of an
+// 8-GPU run owns has 1.6) the lanes that happen to start a chain late set the time while the others idle.  The tail
+// of the queue is therefore made of shorter tasks: the cells of the last q_tail tiles are split into SEG_COUNT
+// azimuth SEGMENTS, each a queue entry of its own.  Segment 0 is the head of the chain; a later segment does not know
+// the chain's index at its first azimuth and starts with the prelude of hzb_search.cuh, which finds it from the
+// residue class the chain keeps (two bisections, ~16 casts).  That value is an assumption -- it is wrong when the
+// chain ran into the lower end of the elevation table on its way (horizon below the table's low limit, i.e. cells
+// that look out over the DEM's edge: the index is clamped there and the residue changes) -- so every segment
+// records it, and the fix-up kernel (k_horizon_redo, behind every launch) compares it with the index the preceding
+// segment really produced; a segment that started from anything else is recomputed there.  The outputs are the
+// sequential chain's in every case; the cast counters too (a recomputed segment's first count is taken back).
+// To keep recomputation out of the picture, the tiles within the BAND along the DEM's edge where such clamping
+// can happen (host: relief / tan(-low limit)) are never split; they are queued first, as whole chains.
+// The azimuths of discrete_sampling / binary_search are independent: their segments need no prelude and no check.
+//
+// Queue: [band tiles: top block rows, bottom block rows, left / right tile columns of the rows between]
+//        [interior tiles in row order, whole chains] [the last q_tail interior tiles x SEG_COUNT segments, segment-major]
+// (rows still complete in order for the host tier's overlapped copy: the interior is the last part of every row).
+// ---------------------------------------------------------------------------
+// queue entry q -> tile (ty, tx) and task: seg 0 = the whole chain, 1 + n = azimuth segment n
+__device__ __forceinline__ void queue_decode(const HorizonParams& p, unsigned int q, int& ty, int& tx, int& seg) {
+    seg = 0;
+    if (q < p.q_nA1) { ty = (int)(q / p.q_tiles_x); tx = (int)(q % p.q_tiles_x); return; }
+    q -= p.q_nA1;
+    if (q < p.q_nA2) { ty = p.q_by1 + (int)(q / p.q_tiles_x); tx = (int)(q % p.q_tiles_x); return; }
+    q -= p.q_nA2;
+    if (q < p.q_nA3) {
+        const int w2 = 2 * p.q_bx, c = (int)(q % w2);
+        ty = p.q_by0 + (int)(q / w2); tx = c < p.q_bx ? c : p.q_tiles_x - w2 + c;
+        return;
+    }
+    q -= p.q_nA3;
+    unsigned int b = q;
+    if (q >= p.q_nI - p.q_tail) {
+        const unsigned int u = q - (p.q_nI - p.q_tail);
+        seg = 1 + (int)(u / p.q_tail); b = p.q_nI - p.q_tail + u % p.q_tail;
+    }
+    ty = p.q_by0 + (int)(b / p.q_wi); tx = p.q_bx + (int)(b % p.q_wi);
+}
+// index of tile (local block row lb, tile column tx) among the split tiles, or -1
+__device__ __forceinline__ int tail_tile(const HorizonParams& p, int lb, int tx) {
+    if (p.seg_count <= 1 || lb < p.q_by0 || lb >= p.q_by1 || tx < p.q_bx || tx >= p.q_tiles_x - p.q_bx) return -1;
+    const int b = (lb - p.q_by0) * p.q_wi + (tx - p.q_bx);
+    return b - (int)(p.q_nI - p.q_tail);      // < 0: interior, not split
+}
+// does cell (ci, cj) belong to a split tile?  (no division: compared as global block rows, host-prepared bounds)
+__device__ __forceinline__ bool cell_is_split(const HorizonParams& p, int ci, int cj) {
+    const int gb = (ci - p.row_begin) >> 2, tx = cj >> 3;
+    return p.seg_count > 1 && tx >= p.q_bx && tx < p.q_tiles_x - p.q_bx && gb < p.q_gb_end &&
+           (gb > p.q_gb_tail || (gb == p.q_gb_tail && tx >= p.q_tx_tail));
+}
+__device__ __forceinline__ int seg_begin(const HorizonParams& p, int n) { return (int)(((long long)n * p.azim_num) / SEG_COUNT); }
+// the lane's cell word: row << 16 | column (both <= 32767, horizon.pyx:149-151) with the segment number in bits 15 and 31
+__device__ __forceinline__ int cell_row(unsigned int w) { return (int)((w >> 16) & 0x7FFFu); }
+__device__ __forceinline__ int cell_col(unsigned int w) { return (int)(w & 0x7FFFu); }
+__device__ __forceinline__ int cell_seg(unsigned int w) { return (int)(((w >> 15) & 1u) | ((w >> 30) & 2u)); }
+// record of (cell of a split tile, segment n >= 1)
+__device__ __forceinline__ SegRecord* seg_record(const HorizonParams& p, int ci, int cj, int n) {
+    const int gb = (ci - p.row_begin) >> 2, lb = (gb - p.blk_offset) / p.blk_stride;
+    const int tt = tail_tile(p, lb, cj >> 3);
+    const int in_tile = (((ci - p.row_begin) & 3) << 3) | (cj & 7);
+    return p.seg + ((size_t)tt * 32 + in_tile) * (SEG_COUNT - 1) + (n - 1);
+}
+// cell slots (one per task) of local block row lb: what publish_cell counts up to
+__device__ __forceinline__ unsigned int row_slots(const HorizonParams& p, int lb) {
+    unsigned int n = p.row_full;
+    if (p.seg_count > 1 && lb >= p.q_by0 && lb < p.q_by1) {
+        const long long over = (long long)(lb - p.q_by0 + 1) * p.q_wi - (long long)(p.q_nI - p.q_tail);
+        const long long split = over < 0 ? 0 : (over > p.q_wi ? p.q_wi : over);
+        n += (unsigned int)split * 32u * (unsigned int)(p.seg_count - 1);
+    }
+    return n;
 }
 
 constexpr int HG_THREADS = 128;
@@ -307,9 +392,14 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_gridded(SceneView sv, Ho
 }
 
 
-// Fix-up kernel: recomputes the cells the production kernel marked with HZB_REDO_F32 (its traversal stack
-// was full) with the per-lane search on the binary BVH.  Launched right behind every production launch on the
-// same stream; finds nothing in all but pathological scenes (one strided 4-byte read per cell).
+// Fix-up kernel, launched right behind every production launch on the same stream; one strided 4-byte read per
+// cell (+ three records per split cell) when there is nothing to do, which is the rule.
+//  * Cells the production kernel marked with HZB_REDO_F32 (its traversal stack was full) are recomputed with the
+//    per-lane search on the binary BVH.
+//  * Split cells ("Queue order and azimuth segments"): segment n >= 1 is valid if it started from the table index the
+//    preceding segment ended with; otherwise (or after a full stack) its azimuths are recomputed here, in order, so
+//    that the next segment is checked against the corrected value.
+// Rewritten row blocks are flagged 2 for the host tier, which copies them again.
 template <int ALG, bool Q>
 __global__ void __launch_bounds__(HG_THREADS) k_horizon_redo(SceneView sv, HorizonParams p, Counters* counters) {
     const Search s = make_search(sv, p, counters);
@@ -322,13 +412,50 @@ __global__ void __launch_bounds__(HG_THREADS) k_horizon_redo(SceneView sv, Horiz
         if (i >= p.row_end) continue;
         const size_t c = (size_t)i * p.dim_in_1 + j;
         const size_t slot = p.packed ? (size_t)lr * p.dim_in_1 + j : c;
-        if (__float_as_uint(Q ? p.hori_first[slot] : p.hori[slot * p.stride_c]) != HZB_REDO_F32) continue;
-        const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
-        const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
-        const float4 v = sv.vert4[(size_t)(i + p.offset_0) * sv.W + (j + p.offset_1)];
-        const Frame f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+        const bool marked = __float_as_uint(Q ? p.hori_first[slot] : p.hori[slot * p.stride_c]) == HZB_REDO_F32;
+        const int tt = tail_tile(p, lr >> 2, j >> 3);
+        if (!marked && tt < 0) continue;
+        if (p.mask[c] != 1) continue;
+        bool rewritten = false;
         typename OutSel<Q>::type ob; out_init<Q>(ob, p, slot, c);
-        cell_search<ALG>(s, f, ob, cnt);
+        Frame f; bool have_frame = false;
+        auto frame = [&]() {
+            if (have_frame) return;
+            const F3 nrm = f3(p.vec_norm[3 * c], p.vec_norm[3 * c + 1], p.vec_norm[3 * c + 2]);
+            const F3 nth = f3(p.vec_north[3 * c], p.vec_north[3 * c + 1], p.vec_north[3 * c + 2]);
+            const float4 v = sv.vert4[(size_t)(i + p.offset_0) * sv.W + (j + p.offset_1)];
+            f = make_frame(f3(v.x, v.y, v.z), nrm, nth, p.ray_org_elev);
+            have_frame = true;
+        };
+        if (marked) { frame(); cell_search<ALG>(s, f, ob, cnt); rewritten = true; }
+        else {
+            for (int n = 1; n < SEG_COUNT; ++n) {
+                const SegRecord rec = *seg_record(p, i, j, n);
+                const int k0 = seg_begin(p, n), k1 = seg_begin(p, n + 1);
+                bool redo = rec.guess == SEG_REDO || rec.guess == SEG_NONE;
+                int prev_az = 0;
+                if (ALG == 2) {   // the chain's index at azimuth k0 - 1 (a table entry: k0 >= 2)
+                    if (Q) prev_az = (int)p.hori_q[slot * p.stride_c + (long long)(k0 - 1) * p.stride_k];
+                    else {
+                        const float v = p.hori[slot * p.stride_c + (long long)(k0 - 1) * p.stride_k];
+                        prev_az = min(max(index_of(s, v), 1), s.elev_num - 2);
+                        if (__ldg(s.elev_ang + prev_az) != v) prev_az += (__ldg(s.elev_ang + prev_az + 1) == v) ? 1 : -1;
+                    }
+                    if (rec.guess != prev_az) redo = true;
+                }
+                if (!redo) continue;
+                frame();
+                if (rec.guess >= 0) cnt.rays -= rec.casts;      // the task ran to its end from the wrong index: its count is taken back
+                cell_search<ALG>(s, f, ob, cnt, k0, k1, prev_az);
+                atomicAdd(&counters->segment_redos, 1ull);
+                rewritten = true;
+            }
+        }
+        if (rewritten && p.row_flags) p.row_flags[(i - p.row_begin) >> 2] = 2u;
+    }
+    if (cnt.rays | cnt.nodes | cnt.prims) {
+        atomicAdd(&counters->rays, (unsigned long long)(long long)(int)cnt.rays);      // (may be negative: sign-extended, wraps correctly)
+        atomicAdd(&counters->node_visits, (unsigned long long)cnt.nodes); atomicAdd(&counters->prim_tests, (unsigned long long)cnt.prims);
     }
 }
 
@@ -346,21 +473,18 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
     const Search s = make_search(sv, p, counters);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
     const unsigned int FULL = 0xffffffffu, lt_mask = (1u << lane) - 1u;
-    const int rows = p.row_end - p.row_begin;
-    const int tiles_x = (p.dim_in_1 + 7) >> 3, tiles_y = local_blocks(p, rows);
-    const unsigned int num_tiles = (unsigned int)tiles_x * (unsigned int)tiles_y;
+    const int tiles_x = p.q_tiles_x;
     LaneCounters cnt; cnt.rays = cnt.nodes = cnt.prims = 0;
-    unsigned int units = 0;
     if (lane == 0) { sh.hit1[warp] = 0u; sh.hit2[warp] = 0u; }
     unsigned int pend_est = 0;
     __syncwarp();
 
-    unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;
+    unsigned int cur_tile = 0; int next_cell = 32; bool more_tiles = true;   // cur_tile: tile index | task << 28 (0 whole chains, 1 + n: azimuth segment n)
     LaneSM m; m.phase = 0; m.k = 0; m.cur = m.prev = m.count = m.prev_az = 0;
     m.spec_ie = -1; m.spec_hit = false;
     typedef typename OutSel<Q>::type OB;
     OB ob;
-    unsigned int my_cell = 0;   // (row << 16) | column of the lane's cell: its frame is rebuilt at every ray set-up
+    unsigned int my_cell = 0;   // (row << 16) | column of the lane's cell (+ segment number, see cell_seg): its frame is rebuilt at every ray set-up
     bool has_cell = false, have_result = false;
     Wq2Lane L; L.state = 0; L.hit1 = L.hit2 = false; L.node = WQ_NONE; L.sp = 0; L.pc = 0;
     L.A1x = L.A1y = L.A1z = L.B1x = L.B1y = L.B1z = 0.f; L.A2x = L.A2y = L.A2z = L.B2x = L.B2y = L.B2z = 0.f;
@@ -377,13 +501,16 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                 unsigned int t = 0;
                 if (lane == 0) t = atomicAdd(tile_counter, 1u);
                 t = __shfl_sync(FULL, t, 0);
-                if (t >= num_tiles) { more_tiles = false; break; }
-                cur_tile = t; next_cell = 0;
+                if (t >= p.q_total) { more_tiles = false; break; }
+                int qy, qx, task;
+                queue_decode(p, t, qy, qx, task);
+                cur_tile = (unsigned int)(qy * tiles_x + qx) | ((unsigned int)task << 28); next_cell = 0;   // (< 2^25 tiles: dims <= 32767)
             }
             const int mine = next_cell + __popc(wmask & lt_mask);
             next_cell += __popc(wmask);
             if (want && mine < 32) {
-                const int ty = cur_tile / tiles_x, tx = cur_tile - ty * tiles_x;
+                const int cur_seg = (int)(cur_tile >> 28), tile = (int)(cur_tile & 0x0FFFFFFFu);
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
                 const int ci = p.row_begin + (ty * p.blk_stride + p.blk_offset) * 4 + (mine >> 3), cj = tx * 8 + (mine & 7);
                 bool done_now = true;
                 if (ci < p.row_end && cj < p.dim_in_1) {
@@ -391,16 +518,30 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                     const size_t slot = p.packed ? (size_t)(ty * 4 + (mine >> 3)) * p.dim_in_1 + cj : c;
                     if (p.mask[c] == 1) {
                         my_cell = ((unsigned int)ci << 16) | (unsigned int)cj;    // dims <= 32767 (horizon.pyx:149-151)
+                        int k0 = 0, k1 = p.azim_num;
+                        if (cur_seg > 0) {          // azimuth segment n of a split cell
+                            const int n = cur_seg - 1;
+                            my_cell |= ((unsigned int)(n & 1) << 15) | ((unsigned int)(n & 2) << 30);
+                            k0 = seg_begin(p, n); k1 = seg_begin(p, n + 1);
+                            if (n > 0) {
+                                SegRecord* r = seg_record(p, ci, cj, n);
+                                r->guess = (ALG == 2) ? SEG_NONE : SEG_OK;
+                                r->casts = 0u - cnt.rays;          // + the lane's count at the end of the task = the task's casts
+                                atomicAdd(&counters->segment_tasks, 1ull);
+                            }
+                        }
                         out_init<Q>(ob, p, slot, c);
-                        m.phase = 0; m.k = 0; m.spec_ie = -1;
-                        has_cell = true; have_result = false; units += p.azim_num;
+                        m.phase = 0; m.spec_ie = -1;
+                        m.k = (ALG == 2) ? 0 : k0;      // guess_constant: azimuth 0, or the prelude of segment n >= 1 (sm_advance)
+                        has_cell = true; have_result = false;
+                        atomicAdd(&counters->units, (unsigned long long)(k1 - k0));      // (once per cell: no per-lane register for it)
                         done_now = false;
-                    } else {
+                    } else if (cur_seg <= 1) {
                         OB fo; out_init<Q>(fo, p, slot, c);
                         fo.fill(p.azim_num, p.hori_fill);  // horizon_comp.cpp:789-794
                     }
                 }
-                if (done_now && p.row_done) publish_cell(p, ty);
+                if (done_now && p.row_done) publish_cell(p, ty, row_slots(p, ty));
             }
         }
         // (B) lanes with a cell but no packet in flight advance their search; the ray set-up
@@ -409,25 +550,37 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         int ie = 0, lo_ie = -1;
         if (has_cell && L.state == 0) {
             unsigned int extra = 0;
+            const int seg_n = cell_seg(my_cell);
+            // end of the lane's azimuths: the segment's end, or azim_num for a whole chain (the cell word has no room for
+            // "segment 0 of a split cell": that is read off the cell's place in the queue)
+            const int k_end = (seg_n > 0 || cell_is_split(p, cell_row(my_cell), cell_col(my_cell))) ? seg_begin(p, seg_n + 1) : p.azim_num;
             m.spec_hit = L.hit2;
-            if (L.node == WQ_OVF) {   // the packet's stack was full: the cell is left to the fix-up kernel (same results)
+            if (L.node == WQ_OVF) {   // the packet's stack was full: the cell (or segment) is left to the fix-up kernel (same results)
                 L.node = WQ_NONE;
-                ob.mark_redo();
+                if (seg_n > 0) seg_record(p, cell_row(my_cell), cell_col(my_cell), seg_n)->guess = SEG_REDO;
+                else ob.mark_redo();
                 atomicAdd(&counters->fallback_packets, 1ull);
                 need_ray = false;
             } else {
-                need_ray = sm_advance<ALG, true, OB>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra);
+                int seg_guess = -1;
+                need_ray = sm_advance<ALG, true, OB>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra,
+                                                     (ALG == 2 && seg_n > 0) ? seg_begin(p, seg_n) : 0, k_end, &seg_guess);
+                if (seg_guess >= 0) seg_record(p, cell_row(my_cell), cell_col(my_cell), seg_n)->guess = seg_guess;
+                cnt.rays += extra + ((need_ray && m.phase < 5) ? 1u : 0u);      // prelude casts are not reference casts
+                if (!need_ray && seg_n > 0) seg_record(p, cell_row(my_cell), cell_col(my_cell), seg_n)->casts += cnt.rays;
             }
-            cnt.rays += extra + (need_ray ? 1u : 0u);
             if (!need_ray) {
                 has_cell = false; finished_cell = true;
-                if (p.row_done) publish_cell(p, ((int)(my_cell >> 16) - p.row_begin) >> 2);   // (row_done is only used unsharded: block == local block)
+                if (p.row_done) {   // (row_done is only used unsharded: block == local block)
+                    const int lb = (cell_row(my_cell) - p.row_begin) >> 2;
+                    publish_cell(p, lb, row_slots(p, lb));
+                }
             }
         }
         __syncwarp();
         if (need_ray) {
             // the cell's frame (12 registers) is not kept across the traversal loop: three cached loads rebuild it
-            const int ci = (int)(my_cell >> 16), cj = (int)(my_cell & 0xFFFFu);
+            const int ci = cell_row(my_cell), cj = cell_col(my_cell);
             const size_t c = (size_t)ci * p.dim_in_1 + cj;
             const F3 nrm = f3(__ldg(p.vec_norm + 3 * c), __ldg(p.vec_norm + 3 * c + 1), __ldg(p.vec_norm + 3 * c + 2));
             const F3 nth = f3(__ldg(p.vec_north + 3 * c), __ldg(p.vec_north + 3 * c + 1), __ldg(p.vec_north + 3 * c + 2));
@@ -447,7 +600,7 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
         // (C) shared traversal loop
         while (__popc(wq2_step<true, false>(sv, sh, warp, lane, tid, L, pend_est, s.dist, wait_thr, cnt, stack_lim)) >= thr) {}
     }
-    flush_counters(cnt, units, counters);
+    flush_counters(cnt, 0u, counters);
 }
 
 // ---- arbitrary locations (horizon_comp.cpp:828-1094)
@@ -628,13 +781,100 @@ __global__ void k_loc_dist_fix(LocationParams lp, int azim_num, const float4* or
 
 }  // namespace
 
-int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
+static void queue_sections(HorizonParams& p, int tiles_x, int tiles_y) {
+    p.q_tiles_x = tiles_x; p.q_tiles_y = tiles_y; p.q_wi = tiles_x - 2 * p.q_bx;
+    p.q_nA1 = (unsigned int)p.q_by0 * (unsigned int)tiles_x; p.q_nA2 = (unsigned int)(tiles_y - p.q_by1) * (unsigned int)tiles_x;
+    p.q_nA3 = (unsigned int)(p.q_by1 - p.q_by0) * 2u * (unsigned int)p.q_bx;
+    p.q_nI = (unsigned int)(p.q_by1 - p.q_by0) * (unsigned int)p.q_wi;
+    p.q_total = p.q_nA1 + p.q_nA2 + p.q_nA3 + p.q_nI + p.q_tail * (unsigned int)(p.seg_count - 1);
+    // first split tile (interior tile nI - tail) and the end of the interior as GLOBAL block rows of the launch's row range
+    p.q_gb_end = p.q_by1 * p.blk_stride + p.blk_offset;
+    p.q_gb_tail = p.q_gb_end; p.q_tx_tail = 0;
+    if (p.q_tail > 0 && p.q_wi > 0) {
+        const unsigned int first = p.q_nI - p.q_tail;
+        p.q_gb_tail = (p.q_by0 + (int)(first / (unsigned int)p.q_wi)) * p.blk_stride + p.blk_offset;
+        p.q_tx_tail = p.q_bx + (int)(first % (unsigned int)p.q_wi);
+    }
+}
+
+// Memory pool of the segment records, one per device: stream-ordered allocation without synchronisation, and -- unlike
+// the device's default pool -- it keeps its few MB across synchronisation points, so a repeated launch never goes
+// to the operating system (on some boxes that costs tens of milliseconds).
+static cudaMemPool_t seg_pool(int device) {
+    static std::mutex mu;
+    static std::vector<cudaMemPool_t> pools;
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0) return nullptr;
+    if ((size_t)device >= pools.size()) pools.resize((size_t)device + 1, nullptr);
+    if (!pools[device]) {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned; props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice; props.location.id = device;
+        cudaMemPool_t mp = nullptr;
+        if (cudaMemPoolCreate(&mp, &props) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        pools[device] = mp;
+    }
+    return pools[device];
+}
+
+// Queue layout of one launch (see "Queue order and azimuth segments"): band, interior, split tail.
+static void plan_queue(const Scene& s, HorizonParams& p, int grid_ctas) {
+    const DebugOptions& o = debug_options();
+    const int rows = p.row_end - p.row_begin;
+    const int all = (rows + 3) >> 2;
+    const int tiles_y = all > p.blk_offset ? (all - p.blk_offset + p.blk_stride - 1) / p.blk_stride : 0;
+    const int tiles_x = (p.dim_in_1 + 7) >> 3;
+    p.seg_count = 1; p.q_by0 = 0; p.q_by1 = tiles_y; p.q_bx = 0; p.q_tail = 0; p.seg = nullptr;
+    queue_sections(p, tiles_x, tiles_y);
+    if (o.tail_segments == 1 || o.horizon_kernel != 0 || tiles_y <= 0 || tiles_x <= 0) return;
+    const bool forced = o.tail_segments == SEG_COUNT;
+    if (p.azim_num < 4 * SEG_COUNT) return;                 // every segment starts behind azimuth 1 and has a few azimuths
+    const long long warps = (long long)grid_ctas * WQ_NWARPS;
+    if (!forced) {
+        if (p.azim_num < 64) return;
+        // the tail matters when a lane owns few cells; beyond ~40 cells per lane it is below 1 % of the launch
+        if ((long long)tiles_x * tiles_y > 40 * warps) return;
+    }
+    // Band: cells that may see below the table's low limit over the DEM's edge -- closer to the edge than relief / tan(-low).
+    int band_x = 0, band_y = 0;      // DEM cells
+    if (o.tail_band >= 0) band_x = band_y = o.tail_band;
+    else if (p.algorithm == 2) {
+        if (!(p.low < -0.01f)) return;                      // low limit near or above the horizontal: chains clamp anywhere
+        const double reach = (double)(s.hi[2] - s.lo[2]) / tan(-(double)p.low);
+        const double dx = (double)(s.hi[0] - s.lo[0]) / std::max(1, s.W - 1), dy = (double)(s.hi[1] - s.lo[1]) / std::max(1, s.H - 1);
+        if (!(dx > 0.0) || !(dy > 0.0)) return;
+        band_x = (int)std::min(1e9, ceil(reach / dx)); band_y = (int)std::min(1e9, ceil(reach / dy));
+    }
+    // inner-domain rows / columns outside the band: [r0, r1) x [c0, c1)
+    const int r0 = std::max(0, band_y - p.offset_0), r1 = std::min(p.dim_in_0, s.H - band_y - p.offset_0);
+    const int c0 = std::max(0, band_x - p.offset_1), c1 = std::min(p.dim_in_1, s.W - band_x - p.offset_1);
+    // whole 4-row blocks of this launch / whole 8-column tiles inside it
+    const int gb0 = std::max(0, (r0 - p.row_begin + 3) >> 2), gb1 = std::max(0, std::min(all, (r1 - p.row_begin) >> 2));
+    auto local_below = [&](int gb) { return gb > p.blk_offset ? std::min(tiles_y, (gb - p.blk_offset + p.blk_stride - 1) / p.blk_stride) : 0; };   // local blocks with global index < gb
+    const int by0 = local_below(gb0), by1 = std::max(by0, local_below(gb1));
+    const int bx = std::max((c0 + 7) >> 3, tiles_x - (std::max(c1, 0) >> 3));
+    if (by1 <= by0 || 2 * bx >= tiles_x) return;            // no interior
+    const long long interior = (long long)(by1 - by0) * (tiles_x - 2 * bx);
+    // two tiles per resident warp: the split part outlasts the last whole chains (measured on cfg2: one tile per warp
+    // leaves the end to chance, more than two only adds preludes)
+    long long tail = o.tail_tiles >= 0 ? o.tail_tiles : 2 * warps;
+    tail = std::min(tail, interior);
+    if (tail <= 0) return;
+    p.seg_count = SEG_COUNT; p.q_by0 = by0; p.q_by1 = by1; p.q_bx = bx; p.q_tail = (unsigned int)tail;
+    queue_sections(p, tiles_x, tiles_y);
+}
+
+int launch_horizon_gridded(Scene& s, const HorizonParams& p_in, cudaStream_t st) {
+    HorizonParams p = p_in;
     if (p.row_end <= p.row_begin || p.dim_in_1 <= 0) return 0;
     unsigned int* tile_counter = scene_tile_counter(s, st);
     if (!tile_counter) return 1;
     const SceneView sv = s.view();
     const DebugOptions& o = debug_options();
     if (p.hori_q && (p.algorithm != 2 || p.elev_num > 65534)) { set_error("quantised output needs ray_algorithm guess_constant and at most 65534 table entries"); return 1; }
+    p.seg_count = 1; p.q_by0 = 0; p.q_by1 = 0; p.q_bx = 0; p.q_tail = 0; p.seg = nullptr;     // (plan_queue fills them for the production kernel)
     if (o.horizon_kernel == 1 && !p.hori_q) {   // reference-shaped per-lane kernel on the binary BVH (second implementation for the parity tests)
         const int grid = sm_count() * 8;
         switch (p.algorithm) {
@@ -650,14 +890,28 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
 #define HZB_MB 6
 #endif
         constexpr int MB = HZB_MB;   // resident CTAs per SM (80 registers, 26 KB shared memory): the walk is bound by per-warp latency, a sixth CTA is worth 2-7 %
-        if (p.hori_q) {   // quantised output: guess_constant only (checked by the caller)
-            k_horizon_wq6<2, MB, true><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim);
-        } else switch (p.algorithm) {
-            case 0: k_horizon_wq6<0, MB, false><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
-            case 1: k_horizon_wq6<1, MB, false><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
-            default: k_horizon_wq6<2, MB, false><<<sm_count() * MB, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+        const int cps = (o.ctas_per_sm >= 1 && o.ctas_per_sm <= MB) ? o.ctas_per_sm : MB;
+        const int grid = sm_count() * cps;
+        plan_queue(s, p, grid);
+        if (p.seg_count > 1) {
+            // records of the split cells: stream-ordered allocation (no synchronisation, the block returns to the
+            // device's pool behind the fix-up kernel), initialised to SEG_NONE
+            const size_t bytes = (size_t)p.q_tail * 32 * (SEG_COUNT - 1) * sizeof(SegRecord);
+            cudaMemPool_t pool = seg_pool(s.device);
+            if (!pool || cudaMallocFromPoolAsync((void**)&p.seg, bytes, pool, st) != cudaSuccess) {   // no records, no split cells
+                cudaGetLastError();
+                p.seg = nullptr; p.seg_count = 1; p.q_tail = 0; queue_sections(p, p.q_tiles_x, p.q_tiles_y);
+            }
+            else HZB_CUDA(cudaMemsetAsync(p.seg, 0xFF, bytes, st));
         }
-        // cells whose traversal stack was full (none in practice) are recomputed by the binary-BVH walker
+        if (p.hori_q) {   // quantised output: guess_constant only (checked by the caller)
+            k_horizon_wq6<2, MB, true><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim);
+        } else switch (p.algorithm) {
+            case 0: k_horizon_wq6<0, MB, false><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+            case 1: k_horizon_wq6<1, MB, false><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+            default: k_horizon_wq6<2, MB, false><<<grid, WQ_BLOCK, 0, st>>>(sv, p, s.d_counters, tile_counter, w_refill, w_wait, stack_lim); break;
+        }
+        // cells whose traversal stack was full (none in practice) and segments that started from a wrong index are recomputed
         const long long slots = (long long)((p.row_end - p.row_begin + 3) / 4) * 4 * p.dim_in_1;
         const int rgrid = (int)std::min<long long>((slots + HG_THREADS - 1) / HG_THREADS, (long long)sm_count() * 8);
         if (p.hori_q) k_horizon_redo<2, true><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters);
@@ -666,6 +920,7 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p, cudaStream_t st) {
             case 1: k_horizon_redo<1, false><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
             default: k_horizon_redo<2, false><<<rgrid, HG_THREADS, 0, st>>>(sv, p, s.d_counters); break;
         }
+        if (p.seg) cudaFreeAsync(p.seg, st);
     }
     HZB_CUDA(cudaGetLastError());
     return 0;

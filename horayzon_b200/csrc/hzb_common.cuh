@@ -71,6 +71,7 @@ struct Counters {  // device-side accumulators (one struct per scene / terrain)
     unsigned long long rays, node_visits, prim_tests, units, warp_node_visits;
     unsigned long long stack_overflow;     // binary-BVH walker ran out of its 96-entry stack (results invalid: reported as an error)
     unsigned long long fallback_packets;   // packets re-decided by the binary-BVH walker after a full shared-memory stack (informational)
+    unsigned long long segment_tasks, segment_redos;   // azimuth segments >= 1 run as tasks of their own / recomputed by the fix-up pass
 };
 
 // Test-only switches (hzb_debug_option): second implementations and tuning knobs the parity tests
@@ -82,6 +83,10 @@ struct DebugOptions {
     int no_overlap = 0;       // host tier: copy the horizon array after the kernel instead of while it runs
     int stack_limit = 1 << 20; // clamped to WQ_STACK_N; lowered by the tests to force the full-stack fallback
     int horizon_variant = 0;  // A/B experiments inside the production kernel family
+    int ctas_per_sm = 0;      // horizon kernel: resident CTAs per SM of the persistent grid (0: the compiled maximum)
+    int tail_segments = -1;   // azimuth segments per cell in the tail of a launch: -1 automatic (4 where it pays), 1 off, 4 forced
+    int tail_tiles = -1;      // tiles whose cells are split (-1: two per resident warp)
+    int tail_band = -1;       // cells next to the DEM's edge that are never split (-1: from the scene's relief and the table's low limit)
 };
 DebugOptions& debug_options();
 
@@ -134,6 +139,13 @@ struct HorizonTables {  // host copies; built exactly like horizon_comp.cpp:711-
     void make(int azim_num, float dist_km, float acc_deg, float low_deg, bool fill = true);
 };
 
+// One record per (split cell, segment >= 1).  guess: the chain index the segment's prelude assumed at the azimuth in
+// front of the segment (guess_constant), SEG_OK where no assumption is needed, SEG_REDO after a full traversal stack,
+// SEG_NONE (the buffer's initial value) if the task never ran.  casts: reference casts the task counted.
+struct SegRecord { int guess; unsigned int casts; };
+constexpr int SEG_NONE = -1, SEG_REDO = -2, SEG_OK = -3;
+constexpr int SEG_COUNT = 4;     // segments of a split cell (the lane keeps the segment number in two spare bits of its cell word)
+
 struct HorizonParams {
     // tables (device)
     const float* azim_sin; const float* azim_cos;
@@ -157,6 +169,17 @@ struct HorizonParams {
     unsigned int* row_done;  // optional [ceil(rows/4)]: +1 per finished cell slot of that row block, 32 per 8x4 tile (host overlaps D2H)
     volatile unsigned int* row_flags;  // optional, MAPPED HOST memory [ceil(rows/4)]: set to 1 by the lane that completes a row block
     unsigned int row_full;   // cell slots per row block (32 per tile)
+    // Work queue (horizon.cu, "Queue order and azimuth segments"): tiles of the band -- block rows outside [q_by0, q_by1),
+    // tile columns outside [q_bx, tiles_x - q_bx) -- come first, then the interior in row order; the cells of the last
+    // q_tail interior tiles are split into seg_count azimuth segments (one queue entry per tile and segment).
+    int seg_count;           // 1: no segments
+    int q_by0, q_by1, q_bx;
+    unsigned int q_tail;
+    // derived on the host (plan_queue): tile grid of the launch, interior width, section sizes of the queue
+    int q_tiles_x, q_tiles_y, q_wi;
+    unsigned int q_nA1, q_nA2, q_nA3, q_nI, q_total;
+    int q_gb_end, q_gb_tail, q_tx_tail;
+    SegRecord* seg;          // [q_tail * 32 * (seg_count - 1)]: what the fix-up pass needs to know about segment 1.. of a split cell
 };
 
 int parse_algorithm(const char* s);  // -1 if unknown

@@ -62,13 +62,25 @@ HZB_HD float midpoint(float a, float b) { return __fmul_rn(__fadd_rn(a, b), 0.5f
 // ===========================================================================
 struct LaneSM {
     // search state (horizon_comp.cpp:387-498 unrolled into states)
-    int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete
+    int phase;       // 0 idle/no cell, 1 bisect, 2 upward, 3 downward, 4 discrete; 5 / 6: prelude of an azimuth segment (below)
     int k, cur, prev, count, prev_az;   // during a bisection (phase 1) prev / count hold the bits of lim_up / lim_low
     int spec_ie; bool spec_hit;   // packet kernels: table index / result of the cast that travelled with the last one (-1: none)
 };
 
+// Azimuth segments (tail of a launch, horizon.cu).  The guess_constant chain hands the previous azimuth's table
+// index to the next one (:439-441), so a lane that starts in the middle of a cell's chain -- at azimuth k_start
+// -- needs the index the chain holds there.  Every step of the chain moves the index by a multiple of 10 (casts
+// at prev+5+10m, result in the middle of the last hit and the first miss), so the index keeps the residue the
+// first azimuth's bisection gave it, and the chain's value at k_start-1 is the rung of that residue class
+// between the highest hit and the lowest miss.  The PRELUDE finds it without the chain: phase 5 repeats the
+// bisection of azimuth 0 (no output) for the residue, phase 6 bisects the rungs {c0 + 10 j} at azimuth
+// k_start-1.  The result is a GUESS -- hit(elevation) need not be monotone, the table ends clamp -- and is
+// reported through seg_guess; the caller's fix-up pass compares it with the index the preceding segment really
+// produced and recomputes the segment if they differ, so the outputs are the sequential chain's in every case.
+// Prelude casts are not reference casts (the caller does not count them).
+
 template <int ALG, bool PK>
-HZB_HD bool sm_begin_azimuth(const SearchTables& s, LaneSM& m, int& cast_ie, int& lo_ie) {
+HZB_HD bool sm_begin_azimuth(const SearchTables& s, LaneSM& m, int& cast_ie, int& lo_ie, bool prelude = false) {
     // returns true if a cast is required (cast_ie set), false if the azimuth needs none
     const int top = s.elev_num - 1;
     if (ALG == 0) {
@@ -76,7 +88,7 @@ HZB_HD bool sm_begin_azimuth(const SearchTables& s, LaneSM& m, int& cast_ie, int
         if (PK) lo_ie = min(m.cur + 10, top);                   // the next sample, should this one hit
         return true;
     } else if (ALG == 1 || m.k == 0) {
-        m.phase = 1; m.prev = __float_as_int(s.up); m.count = __float_as_int(s.low);
+        m.phase = (ALG == 2 && prelude) ? 5 : 1; m.prev = __float_as_int(s.up); m.count = __float_as_int(s.low);
         m.cur = index_of(s, midpoint(s.up, s.low));
         const float ea = __ldg(s.elev_ang + m.cur);
         if (fmaxf(__fsub_rn(s.up, ea), __fsub_rn(ea, s.low)) > s.acc) { cast_ie = m.cur; return true; }
@@ -99,10 +111,15 @@ HZB_HD bool sm_begin_azimuth(const SearchTables& s, LaneSM& m, int& cast_ie, int
 // result in m.spec_ie / m.spec_hit; when the search then asks for exactly that index the
 // stored result is consumed instead of casting, and counted in extra_rays -- i.e. only
 // when the reference would have cast it.  An unused companion result is dropped.
+// The search ends in front of azimuth k_end (< 0: azim_num).  k_start > 0 (guess_constant only): the lane owns the
+// azimuths [k_start, k_end) of its cell and starts with m.k == 0, m.phase == 0: prelude first (see above);
+// seg_guess receives the chain index the prelude found.
 template <int ALG, bool PK, typename OB>
 HZB_HD bool sm_advance(const SearchTables& s, LaneSM& m, bool have_result, bool hit, OB& ob, int& cast_ie,
-                                           int& lo_ie, unsigned int& extra_rays) {
+                                           int& lo_ie, unsigned int& extra_rays, const int k_start = 0, int k_end = -1,
+                                           int* seg_guess = nullptr) {
     const int top = s.elev_num - 1;
+    if (k_end < 0) k_end = s.azim_num;
     lo_ie = -1;
 #define HZB_SM_CAST(COMPANION)                                                                        \
     do {                                                                                              \
@@ -114,13 +131,13 @@ HZB_HD bool sm_advance(const SearchTables& s, LaneSM& m, bool have_result, bool 
 again:
     while (true) {
         if (!have_result) {  // start of an azimuth
-            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie)) { if (lo_ie == cast_ie) lo_ie = -1; return true; }
+            if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie, k_start > 0)) { if (lo_ie == cast_ie) lo_ie = -1; return true; }
             // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
             hit = false; have_result = true;
             // (emulate loop exit below)
             goto bisect_done;
         }
-        if (m.phase == 1) {
+        if (m.phase == 1 || (ALG == 2 && m.phase == 5)) {
             {
                 const float ea = __ldg(s.elev_ang + m.cur);
                 if (hit) m.count = __float_as_int(ea); else m.prev = __float_as_int(ea);
@@ -130,8 +147,32 @@ again:
                 if (fmaxf(__fsub_rn(lim_up, ea2), __fsub_rn(ea2, lim_low)) > s.acc) { cast_ie = m.cur; return true; }
             }
         bisect_done:
+            if (ALG == 2 && m.phase == 5) {
+                // prelude, second step: rungs c0 + 10 j of the chain's residue class at azimuth k_start-1;
+                // j = m.prev counts as a hit, j = m.count as a miss (virtual rungs below the table / at its top)
+                m.prev_az = (m.cur + 5) % 10;
+                m.prev = -1; m.count = (top - m.prev_az) / 10 + 1;
+                m.phase = 6; m.k = k_start - 1;
+                goto ladder_next;
+            }
             ob.put(m.k, midpoint(__int_as_float(m.prev), __int_as_float(m.count)));   // un-quantised midpoint (:377, :428)
             m.prev_az = m.cur;            // seeds the chain (:429)
+        } else if (ALG == 2 && m.phase == 6) {
+            if (m.cur >= top) hit = false;            // termination rules of the chain
+            if (m.cur == 0) hit = true;
+            if (hit) m.prev = (m.cur - m.prev_az) / 10; else m.count = (m.cur - m.prev_az) / 10;
+        ladder_next:
+            if (m.count - m.prev > 1) {
+                m.cur = m.prev_az + 10 * ((m.prev + m.count) >> 1);
+                cast_ie = m.cur; lo_ie = -1;
+                return true;
+            }
+            {   // the chain's own arithmetic on the bracketing rungs (clamped like :443-447, :472-476)
+                const int lo_i = max(m.prev_az + 10 * m.prev, 0), hi_i = min(m.prev_az + 10 * m.prev + 10, top);
+                m.prev_az = index_of(s, midpoint(__ldg(s.elev_ang + lo_i), __ldg(s.elev_ang + hi_i)));
+                if (seg_guess) *seg_guess = m.prev_az;
+            }
+            // m.k == k_start-1: "azimuth finished" below moves on to the segment's first azimuth
         } else if (m.phase == 2) {
             m.count++;
             if (m.cur == top) hit = false;            // termination rule
@@ -155,7 +196,7 @@ again:
         }
         // azimuth finished
         m.k++; m.spec_ie = -1;
-        if (m.k >= s.azim_num) { m.phase = 0; return false; }
+        if (m.k >= k_end) { m.phase = 0; return false; }
         have_result = false;
     }
 #undef HZB_SM_CAST

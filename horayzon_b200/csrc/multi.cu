@@ -266,6 +266,7 @@ int hzb_horizon_gridded_multi(const float* vert_grid, int dem_dim_0, int dem_dim
             if (hzb_scene_stats(scenes[r], &st) == 0) {
                 total.rays += st.rays; total.node_visits += st.node_visits; total.prim_tests += st.prim_tests; total.units += st.units;
                 total.fallback_packets += st.fallback_packets;
+                total.segment_tasks += st.segment_tasks; total.segment_redos += st.segment_redos;
                 total.num_prims = st.num_prims; total.num_nodes = st.num_nodes; total.bvh_bytes = st.bvh_bytes;
                 total.t_h2d = std::max(total.t_h2d, st.t_h2d); total.t_build = std::max(total.t_build, st.t_build);
             } else if (ok) { ok = false; first_err = hzb_last_error(); }

@@ -24,7 +24,8 @@ class Stats(ctypes.Structure):
                 ("t_h2d", ctypes.c_double), ("t_build", ctypes.c_double), ("t_trace", ctypes.c_double),
                 ("t_d2h", ctypes.c_double), ("t_total", ctypes.c_double),
                 ("num_prims", ctypes.c_ulonglong), ("num_nodes", ctypes.c_ulonglong),
-                ("bvh_bytes", ctypes.c_ulonglong), ("fallback_packets", ctypes.c_ulonglong)]
+                ("bvh_bytes", ctypes.c_ulonglong), ("fallback_packets", ctypes.c_ulonglong),
+                ("segment_tasks", ctypes.c_ulonglong), ("segment_redos", ctypes.c_ulonglong)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

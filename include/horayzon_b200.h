@@ -54,6 +54,8 @@ typedef struct hzb_stats {
     unsigned long long num_nodes;   /* wide-BVH nodes */
     unsigned long long bvh_bytes;   /* bytes of the traversal structure in HBM */
     unsigned long long fallback_packets; /* packets re-decided by the binary-BVH walker after a full traversal stack */
+    unsigned long long segment_tasks;    /* azimuth segments >= 1 of split cells the horizon kernel ran (tail of a launch) */
+    unsigned long long segment_redos;    /* ... of which the fix-up pass recomputed (start index not the chain's) */
 } hzb_stats;
 int hzb_get_stats(hzb_stats* out);
 

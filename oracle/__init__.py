@@ -397,3 +397,22 @@ def selftest_state_machine(vert_grid, dem_dim_0, dem_dim_1, offset_0, offset_1, 
                                        ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
     return int(bad), a.value, b.value, c.value
 
+
+
+def selftest_segments(vert_grid, dem_dim_0, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, azim_num, dist_search,
+                      hori_acc=0.25, elev_ang_low_lim=-15.0, ray_org_elev=0.01, ray_algorithm="guess_constant",
+                      segments=4, tilted=True):
+    """The PRODUCT's state machine in azimuth-segment mode (csrc/hzb_search.cuh) on the oracle's casts: every
+    segment of every cell runs as a task of its own.  Returns (cells whose verified segments differ from the chain,
+    reference casts, segment tasks, prelude guesses that missed the chain's index, prelude casts)."""
+    L = lib()
+    L.orc_selftest_segments.restype = ctypes.c_longlong
+    a = ctypes.c_longlong(0)
+    st = (ctypes.c_longlong * 3)()
+    vg = np.ascontiguousarray(vert_grid, dtype=np.float32)
+    bad = L.orc_selftest_segments(_p(vg, _f32p), int(dem_dim_0), int(dem_dim_1), int(offset_0), int(offset_1),
+                                  int(dim_in_0), int(dim_in_1), int(azim_num), ctypes.c_float(dist_search),
+                                  ctypes.c_float(hori_acc), ctypes.c_float(elev_ang_low_lim),
+                                  ctypes.c_float(ray_org_elev), ray_algorithm.encode(), int(segments), int(bool(tilted)),
+                                  ctypes.byref(a), st)
+    return int(bad), a.value, int(st[0]), int(st[1]), int(st[2])

@@ -1211,18 +1211,19 @@ struct HostOut { float* out; inline void put(int k, float v) { out[k] = v; } inl
 
 template <int ALG>
 static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_grid, int W, int off0, int off1, int ny, int nx,
-                          float lift, int refuse_every, long long* casts_ref, long long* casts_sm, long long* companions_used) {
-    long long bad = 0, cr = 0, cs = 0, cu = 0;
+                          float lift, int refuse_every, long long* casts_ref, long long* casts_sm, long long* companions_used,
+                          int segments = 1, long long* seg_stats = nullptr, int tilted = 1) {
+    long long bad = 0, cr = 0, cs = 0, cu = 0, st_tasks = 0, sm_miss = 0, sp = 0;
     hzb::SearchTables st;
     st.azim_sin = T.as.data(); st.azim_cos = T.ac.data(); st.elev_ang = T.ea.data(); st.elev_sin = T.es.data();
     st.elev_cos = T.ec.data(); st.azim_num = T.azim_num; st.elev_num = T.elev_num;
     st.acc = T.acc; st.low = T.low; st.up = T.up; st.dist = T.dist; st.step = (double)T.acc / 5.0;
-#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : bad, cr, cs, cu)
+#pragma omp parallel for collapse(2) schedule(dynamic, 4) reduction(+ : bad, cr, cs, cu, st_tasks, sm_miss, sp)
     for (int i = 0; i < ny; ++i)
         for (int j = 0; j < nx; ++j) {
             const float* vp = vert_grid + 3 * ((size_t)(i + off0) * W + (j + off1));
             // a slightly tilted, rotated frame per cell so that all nine matrix entries matter
-            const float tx = 0.02f * (float)((i * 7 + j * 3) % 11 - 5) / 5.f, ty = 0.015f * (float)((i * 5 + j) % 7 - 3) / 3.f;
+            const float tx = tilted ? 0.02f * (float)((i * 7 + j * 3) % 11 - 5) / 5.f : 0.f, ty = tilted ? 0.015f * (float)((i * 5 + j) % 7 - 3) / 3.f : 0.f;
             const float nl = sqrtf(tx * tx + ty * ty + 1.f);
             const V3 nrm = {tx / nl, ty / nl, 1.f / nl};
             V3 nth = {0.05f, 1.f, 0.f};
@@ -1260,13 +1261,60 @@ static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_gr
                 m.spec_ie = two ? lo : -1;
                 have_result = true;
             }
-            const bool same = memcmp(ref.data(), got.data(), sizeof(float) * T.azim_num) == 0 && rays == cast.rays && dir_bad == 0;
+            bool same = memcmp(ref.data(), got.data(), sizeof(float) * T.azim_num) == 0 && rays == cast.rays && dir_bad == 0;
+            // Azimuth segments (hzb_search.cuh): segment s = 1 .. segments-1 of the chain run as a task of its own --
+            // prelude, then the azimuths [k_s, k_e).  Where the prelude's guess equals the chain's index at k_s - 1 the
+            // task's outputs must be the chain's; where it does not, the product's fix-up pass recomputes the segment
+            // (counted in seg_miss).  Prelude casts are counted in seg_pre.
+            for (int sg = 1; sg < segments && same; ++sg) {
+                const int k_s = (int)((long long)sg * T.azim_num / segments), k_e = (int)((long long)(sg + 1) * T.azim_num / segments);
+                if (k_s < 2 || k_e <= k_s) continue;
+                std::vector<float> seg(T.azim_num, -999.f);
+                hzb::LaneSM q; q.phase = 0; q.k = (ALG == 2) ? 0 : k_s; q.cur = q.prev = q.count = q.prev_az = 0; q.spec_ie = -1; q.spec_hit = false;
+                HostOut sob{seg.data()};
+                bool hr = false, h1 = false, h2 = false; int guess = -1; long long pre = 0;
+                while (true) {
+                    int ie = 0, lo = -1; unsigned int extra = 0;
+                    q.spec_hit = h2;
+                    const bool need = hzb::sm_advance<ALG, true, HostOut>(st, q, hr, h1, sob, ie, lo, extra, (ALG == 2) ? k_s : 0, k_e, &guess);
+                    if (!need) break;
+                    if (q.phase >= 5) ++pre;
+                    const hzb::F3 pd = hzb::ray_dir(st, pf, ie, q.k);
+                    h1 = sc.occluded({pf.org.x, pf.org.y, pf.org.z}, {pd.x, pd.y, pd.z}, T.dist, false);
+                    const bool two = lo >= 0;
+                    if (two) { const hzb::F3 pl = hzb::ray_dir(st, pf, lo, q.k); h2 = sc.occluded({pf.org.x, pf.org.y, pf.org.z}, {pl.x, pl.y, pl.z}, T.dist, false); }
+                    else h2 = h1;
+                    q.spec_ie = two ? lo : -1;
+                    hr = true;
+                }
+                sp += pre; ++st_tasks;
+                if (ALG == 2 && (guess < 0 || T.ea[guess] != ref[k_s - 1])) { ++sm_miss; continue; }
+                if (memcmp(ref.data() + k_s, seg.data() + k_s, sizeof(float) * (k_e - k_s)) != 0) same = false;
+                for (int k = 0; k < T.azim_num; ++k) if ((k < k_s || k >= k_e) && seg[k] != -999.f) same = false;    // wrote outside its segment
+            }
             bad += same ? 0 : 1; cr += (long long)cast.rays; cs += (long long)rays; cu += (long long)used;
         }
     *casts_ref = cr; *casts_sm = cs; *companions_used = cu;
+    if (seg_stats) { seg_stats[0] = st_tasks; seg_stats[1] = sm_miss; seg_stats[2] = sp; }
     return bad;
 }
 }  // namespace
+
+// the same with azimuth segments: seg_stats = {segment tasks run, prelude guesses that missed the chain's index, prelude casts};
+// the cells are rows [row_begin, row_begin + dim_in_0) of the inner domain; tilted = 0: planar frames (the bench workloads)
+extern "C" long long orc_selftest_segments(const float* vert_grid, int dem_dim_0, int dem_dim_1, int offset_0, int offset_1,
+                                           int dim_in_0, int dim_in_1, int azim_num, float dist_search, float hori_acc,
+                                           float elev_ang_low_lim, float ray_org_elev, const char* ray_algorithm,
+                                           int segments, int tilted, long long* casts_ref, long long* seg_stats) {
+    const int alg = algo_id(ray_algorithm);
+    if (alg < 0 || segments < 1) return -1;
+    Scene sc; sc.add_grid(vert_grid, dem_dim_0, dem_dim_1); sc.build();
+    Tables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim);
+    long long cs = 0, cu = 0;
+    if (alg == 0) return sm_cells<0>(sc, T, vert_grid, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, ray_org_elev, 0, casts_ref, &cs, &cu, segments, seg_stats, tilted);
+    if (alg == 1) return sm_cells<1>(sc, T, vert_grid, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, ray_org_elev, 0, casts_ref, &cs, &cu, segments, seg_stats, tilted);
+    return sm_cells<2>(sc, T, vert_grid, dem_dim_1, offset_0, offset_1, dim_in_0, dim_in_1, ray_org_elev, 0, casts_ref, &cs, &cu, segments, seg_stats, tilted);
+}
 
 extern "C" long long orc_selftest_state_machine(const float* vert_grid, int dem_dim_0, int dem_dim_1, int offset_0, int offset_1,
                                                 int dim_in_0, int dim_in_1, int azim_num, float dist_search, float hori_acc,

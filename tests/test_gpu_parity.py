@@ -78,6 +78,61 @@ def test_horizon_kernel_variants_agree(mods, dbg, opts, alg):
         assert st["fallback_packets"] == 0 and st["rays"] == rays
 
 
+@pytest.mark.parametrize("alg", ["guess_constant", "binary_search", "discrete_sampling"])
+@pytest.mark.parametrize("extra", [{}, {"stack_limit": 3}])
+def test_azimuth_segments_everywhere(mods, dbg, alg, extra):
+    """Tail splitting forced onto EVERY cell, rim included (no band): segments 1..3 of every cell run as tasks of their
+    own.  cfg1's rim cells look out over the DEM's edge, where the chain is clamped at the table's low end and the
+    prelude's assumption fails, so the fix-up pass has real work: the outputs must still be the oracle's bits and --
+    without the full-stack fallback -- the cast counter the reference's."""
+    hb, oracle = mods
+    dbg("tail_segments", 4); dbg("tail_band", 0); dbg("tail_tiles", 1 << 30)
+    for k, v in extra.items():
+        dbg(k, v)
+    c, args = _cfg(hb, "cfg1")
+    h_gpu, _ = hb.horizon.horizon_gridded(*args, azim_num=c["azim_num"], ray_algorithm=alg)
+    st = hb.resident.last_stats()
+    h_cpu, _, rays = oracle.horizon_gridded(*args, azim_num=c["azim_num"], ray_algorithm=alg, return_rays=True)
+    _assert_same(h_gpu, h_cpu, "segments " + alg)
+    print("\nsegments %s %s: tasks %d, recomputed %d, fallback packets %d" % (alg, extra, st["segment_tasks"], st["segment_redos"], st["fallback_packets"]))
+    assert st["segment_tasks"] > 0.5 * 3 * c["ny"] * c["nx"]          # (the outermost tile ring is band by construction)
+    assert st["units"] == c["ny"] * c["nx"] * c["azim_num"]
+    if alg != "guess_constant" and not extra:
+        assert st["segment_redos"] == 0
+    if not extra:
+        assert st["fallback_packets"] == 0 and st["rays"] == rays, "cast counter differs from the oracle's"
+
+
+def test_azimuth_segments_layouts_and_quantised(mods, dbg):
+    """Split cells with a mask, the azimuth-first layout, the 16-bit output and a sharded, packed launch."""
+    hb, oracle = mods
+    import torch
+    c, args = _cfg(hb, "cfg2", n=161)
+    K = 72
+    mask = np.ones((c["ny"], c["nx"]), np.uint8); mask[::7, ::5] = 0
+    ref, _ = hb.horizon.horizon_gridded(*args, azim_num=K, mask=mask, hori_fill=-1.0)
+    dbg("tail_segments", 4); dbg("tail_band", 0); dbg("tail_tiles", 1 << 30)
+    a, _ = hb.horizon.horizon_gridded(*args, azim_num=K, mask=mask, hori_fill=-1.0)
+    assert hb.resident.last_stats()["segment_tasks"] > 0
+    assert np.array_equal(a, ref)
+    b, _ = hb.horizon.horizon_gridded(*args, azim_num=K, mask=mask, hori_fill=-1.0, azim_first=True)
+    assert np.array_equal(np.moveaxis(b, 0, 2), ref)
+    idx, first, table = hb.horizon.horizon_gridded_quantised(*args, azim_num=K, mask=mask, hori_fill=-1.0)[:3]
+    assert np.array_equal(hb.horizon.dequantise(idx, first, table), ref)
+    dev = torch.device("cuda:0")
+    sc = hb.resident.Scene(c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"])
+    vn = torch.from_numpy(c["vec_norm"]).to(dev); vno = torch.from_numpy(c["vec_north"]).to(dev); mk = torch.from_numpy(mask).to(dev)
+    for world in (2, 3):
+        per = hb.sharding.padded_block_rows(c["ny"], world)
+        gathered = torch.full((world * per, c["nx"], K), float("nan"), device=dev)
+        for r in range(world):
+            sc.horizon_gridded_sharded(vn, vno, mk, c["offset_0"], c["offset_1"], gathered[r * per:(r + 1) * per], r, world, K,
+                                       packed=True, dist_search=c["dist_search"], hori_fill=-1.0)
+        torch.cuda.synchronize()
+        assert np.array_equal(hb.sharding.unpack_blocks(gathered, c["ny"], world).cpu().numpy(), ref), "sharded x%d" % world
+    assert sc.stats()["segment_tasks"] > 0
+
+
 def test_shadow_kernel_variants_agree(mods, dbg):
     hb, oracle = mods
     vg, n, rim, tilt, norm, enl, elev, mask = _terrain_inputs(hb)
