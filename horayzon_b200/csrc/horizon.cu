@@ -334,12 +334,13 @@ __device__ __forceinline__ int seg_begin(const HorizonParams& p, int n) { return
 __device__ __forceinline__ int cell_row(unsigned int w) { return (int)((w >> 16) & 0x7FFFu); }
 __device__ __forceinline__ int cell_col(unsigned int w) { return (int)(w & 0x7FFFu); }
 __device__ __forceinline__ int cell_seg(unsigned int w) { return (int)(((w >> 15) & 1u) | ((w >> 30) & 2u)); }
-// record of (cell of a split tile, segment n >= 1)
+// record of (cell of a split tile, segment n >= 1); n == SEG_COUNT: the cell's shared record (guess = the index the
+// bisection of azimuth 0 ended with, published by the lane that owns segment 0)
 __device__ __forceinline__ SegRecord* seg_record(const HorizonParams& p, int ci, int cj, int n) {
     const int gb = (ci - p.row_begin) >> 2, lb = (gb - p.blk_offset) / p.blk_stride;
     const int tt = tail_tile(p, lb, cj >> 3);
     const int in_tile = (((ci - p.row_begin) & 3) << 3) | (cj & 7);
-    return p.seg + ((size_t)tt * 32 + in_tile) * (SEG_COUNT - 1) + (n - 1);
+    return p.seg + ((size_t)tt * 32 + in_tile) * SEG_COUNT + (n - 1);
 }
 // cell slots (one per task) of local block row lb: what publish_cell counts up to
 __device__ __forceinline__ unsigned int row_slots(const HorizonParams& p, int lb) {
@@ -553,7 +554,8 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
             const int seg_n = cell_seg(my_cell);
             // end of the lane's azimuths: the segment's end, or azim_num for a whole chain (the cell word has no room for
             // "segment 0 of a split cell": that is read off the cell's place in the queue)
-            const int k_end = (seg_n > 0 || cell_is_split(p, cell_row(my_cell), cell_col(my_cell))) ? seg_begin(p, seg_n + 1) : p.azim_num;
+            const bool split = seg_n > 0 || cell_is_split(p, cell_row(my_cell), cell_col(my_cell));
+            const int k_end = split ? seg_begin(p, seg_n + 1) : p.azim_num;
             m.spec_hit = L.hit2;
             if (L.node == WQ_OVF) {   // the packet's stack was full: the cell (or segment) is left to the fix-up kernel (same results)
                 L.node = WQ_NONE;
@@ -562,10 +564,12 @@ __global__ void __launch_bounds__(WQ_BLOCK, MINB) k_horizon_wq6(SceneView sv, Ho
                 atomicAdd(&counters->fallback_packets, 1ull);
                 need_ray = false;
             } else {
-                int seg_guess = -1;
+                int seg_guess = -1, r0_known = -1;
+                if (ALG == 2 && seg_n > 0 && !have_result && m.phase == 0)      // first step of the task: has the head of the chain reported yet?
+                    r0_known = *(volatile int*)&seg_record(p, cell_row(my_cell), cell_col(my_cell), SEG_COUNT)->guess;
                 need_ray = sm_advance<ALG, true, OB>(s, m, have_result, L.hit1, ob, ie, lo_ie, extra,
-                                                     (ALG == 2 && seg_n > 0) ? seg_begin(p, seg_n) : 0, k_end, &seg_guess);
-                if (seg_guess >= 0) seg_record(p, cell_row(my_cell), cell_col(my_cell), seg_n)->guess = seg_guess;
+                                                     (ALG == 2 && seg_n > 0) ? seg_begin(p, seg_n) : 0, k_end, &seg_guess, r0_known);
+                if (seg_guess >= 0 && split) seg_record(p, cell_row(my_cell), cell_col(my_cell), seg_n > 0 ? seg_n : SEG_COUNT)->guess = seg_guess;
                 cnt.rays += extra + ((need_ray && m.phase < 5) ? 1u : 0u);      // prelude casts are not reference casts
                 if (!need_ray && seg_n > 0) seg_record(p, cell_row(my_cell), cell_col(my_cell), seg_n)->casts += cnt.rays;
             }
@@ -896,7 +900,7 @@ int launch_horizon_gridded(Scene& s, const HorizonParams& p_in, cudaStream_t st)
         if (p.seg_count > 1) {
             // records of the split cells: stream-ordered allocation (no synchronisation, the block returns to the
             // device's pool behind the fix-up kernel), initialised to SEG_NONE
-            const size_t bytes = (size_t)p.q_tail * 32 * (SEG_COUNT - 1) * sizeof(SegRecord);
+            const size_t bytes = (size_t)p.q_tail * 32 * SEG_COUNT * sizeof(SegRecord);
             cudaMemPool_t pool = seg_pool(s.device);
             if (!pool || cudaMallocFromPoolAsync((void**)&p.seg, bytes, pool, st) != cudaSuccess) {   // no records, no split cells
                 cudaGetLastError();

@@ -179,7 +179,8 @@ struct HorizonParams {
     int q_tiles_x, q_tiles_y, q_wi;
     unsigned int q_nA1, q_nA2, q_nA3, q_nI, q_total;
     int q_gb_end, q_gb_tail, q_tx_tail;
-    SegRecord* seg;          // [q_tail * 32 * (seg_count - 1)]: what the fix-up pass needs to know about segment 1.. of a split cell
+    SegRecord* seg;          // [q_tail * 32][SEG_COUNT]: per split cell, what the fix-up pass needs to know about segments 1.. (records
+                             // 0 .. SEG_COUNT-2) and the index azimuth 0's bisection ended with (guess of the last record)
 };
 
 int parse_algorithm(const char* s);  // -1 if unknown

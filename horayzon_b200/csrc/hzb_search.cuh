@@ -113,11 +113,13 @@ HZB_HD bool sm_begin_azimuth(const SearchTables& s, LaneSM& m, int& cast_ie, int
 // when the reference would have cast it.  An unused companion result is dropped.
 // The search ends in front of azimuth k_end (< 0: azim_num).  k_start > 0 (guess_constant only): the lane owns the
 // azimuths [k_start, k_end) of its cell and starts with m.k == 0, m.phase == 0: prelude first (see above);
-// seg_guess receives the chain index the prelude found.
+// seg_guess receives the chain index the prelude found.  r0_known >= 0: the index the bisection of azimuth 0 ended
+// with is already known (the lane that owns the head of the chain reports it through seg_guess, k_start == 0), so
+// the prelude skips its first step.
 template <int ALG, bool PK, typename OB>
 HZB_HD bool sm_advance(const SearchTables& s, LaneSM& m, bool have_result, bool hit, OB& ob, int& cast_ie,
                                            int& lo_ie, unsigned int& extra_rays, const int k_start = 0, int k_end = -1,
-                                           int* seg_guess = nullptr) {
+                                           int* seg_guess = nullptr, const int r0_known = -1) {
     const int top = s.elev_num - 1;
     if (k_end < 0) k_end = s.azim_num;
     lo_ie = -1;
@@ -131,6 +133,7 @@ HZB_HD bool sm_advance(const SearchTables& s, LaneSM& m, bool have_result, bool 
 again:
     while (true) {
         if (!have_result) {  // start of an azimuth
+            if (ALG == 2 && k_start > 0 && m.k == 0 && r0_known >= 0) { m.phase = 5; m.cur = r0_known; have_result = true; goto bisect_done; }
             if (sm_begin_azimuth<ALG, PK>(s, m, cast_ie, lo_ie, k_start > 0)) { if (lo_ie == cast_ie) lo_ie = -1; return true; }
             // bisect needed no cast at all: fall through to "azimuth finished" with phase 1
             hit = false; have_result = true;
@@ -157,6 +160,7 @@ again:
             }
             ob.put(m.k, midpoint(__int_as_float(m.prev), __int_as_float(m.count)));   // un-quantised midpoint (:377, :428)
             m.prev_az = m.cur;            // seeds the chain (:429)
+            if (ALG == 2 && seg_guess) *seg_guess = m.cur;     // (the head of a split chain tells the other segments)
         } else if (ALG == 2 && m.phase == 6) {
             if (m.cur >= top) hit = false;            // termination rules of the chain
             if (m.cur == 0) hit = true;

@@ -1242,10 +1242,11 @@ static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_gr
             HostOut ob{got.data()};
             bool have_result = false, hit1 = false, hit2 = false;
             unsigned long long rays = 0, used = 0, asked = 0;
+            int r0_head = -1;     // what the head of the chain reports to the other segments (guess_constant)
             while (true) {
                 int ie = 0, lo = -1; unsigned int extra = 0;
                 m.spec_hit = hit2;
-                const bool need = hzb::sm_advance<ALG, true, HostOut>(st, m, have_result, hit1, ob, ie, lo, extra);
+                const bool need = hzb::sm_advance<ALG, true, HostOut>(st, m, have_result, hit1, ob, ie, lo, extra, 0, -1, &r0_head);
                 rays += extra + (need ? 1u : 0u); used += extra;
                 if (!need) break;
                 // the ray comes from the PRODUCT's frame / direction arithmetic and must carry the oracle's bits
@@ -1276,7 +1277,8 @@ static long long sm_cells(const Scene& sc, const Tables& T, const float* vert_gr
                 while (true) {
                     int ie = 0, lo = -1; unsigned int extra = 0;
                     q.spec_hit = h2;
-                    const bool need = hzb::sm_advance<ALG, true, HostOut>(st, q, hr, h1, sob, ie, lo, extra, (ALG == 2) ? k_s : 0, k_e, &guess);
+                    const bool need = hzb::sm_advance<ALG, true, HostOut>(st, q, hr, h1, sob, ie, lo, extra, (ALG == 2) ? k_s : 0, k_e, &guess,
+                                                                          ((i + j + sg) & 1) ? r0_head : -1);    // every other task skips the first step of the prelude
                     if (!need) break;
                     if (q.phase >= 5) ++pre;
                     const hzb::F3 pd = hzb::ray_dir(st, pf, ie, q.k);

@@ -338,6 +338,33 @@ def test_product_state_machine_on_the_cpu(alg):
 
 
 
+@pytest.mark.parametrize("alg", ["guess_constant", "binary_search", "discrete_sampling"])
+def test_azimuth_segments_on_the_cpu(alg):
+    """Azimuth segments (the tail of a launch, csrc/horizon.cu): segment 1.. of every cell runs as a task of its own
+    through the product's state machine -- prelude, then its azimuths -- on the oracle's casts, half of the tasks with
+    the head's bisection result handed over.  A task whose prelude found the chain's index must reproduce the chain bit
+    for bit and write nothing outside its segment; where it did not find it (the chain was clamped at the table's low
+    end on its way: cells that look out over the DEM's edge) the product's fix-up pass recomputes, which the GPU suite
+    covers.  Away from the edge the assumption must hold for (nearly) every task."""
+    c = syn.make_config("cfg1", n=72)
+    bad, ref, tasks, missed, pre = oracle.selftest_segments(c["vert_grid"], 72, 72, c["offset_0"], c["offset_1"], c["ny"], c["nx"], 40,
+                                                            c["dist_search"], ray_algorithm=alg, segments=4)
+    assert bad == 0 and tasks == 3 * c["ny"] * c["nx"]
+    if alg == "guess_constant":
+        assert 0 < pre < 20 * tasks and missed <= 0.01 * tasks
+    else:
+        assert pre == 0 and missed == 0          # independent azimuths: no prelude, nothing to assume
+    # the rim of a steep DEM, low limit close to the horizontal: chains are clamped all the time, most guesses miss,
+    # verified segments must still be exact
+    x, y, z = syn.sinusoid_dem(40, 40, 5.0, 300.0, 140.0, 5, 3)
+    vg = syn.rearrange_pad_buffer(x, y, z)
+    bad, ref, tasks, missed, pre = oracle.selftest_segments(vg, 40, 40, 1, 1, 38, 38, 32, 0.3, hori_acc=0.5, elev_ang_low_lim=-2.0,
+                                                            ray_algorithm=alg, segments=4)
+    assert bad == 0 and tasks > 0
+    if alg == "guess_constant":
+        assert missed > 0
+
+
 def test_parity_sensitivity_to_the_rounding_of_the_triangle_test():
     """The ray path is 'parity unpinned' (Embree absent).  What CAN be measured: how many outputs depend on the
     rounding of the triangle test at all.  The oracle with the specified fp32 Pluecker arithmetic against the same
