@@ -706,11 +706,15 @@ def run_ours(args):
                          "kernel_ms_ranks": {"min": mn[1], "mean": mean[1], "max": mx[1]},
                          "algorithmic_bytes_per_unit": algo_bytes_per_unit,
                          "note": "compulsory bytes only (output store + per-cell inputs); the traversal is bound by "
-                                 "instruction issue with the BVH served from L1/L2, see DESIGN.md"},
+                                 "per-warp latency / instruction issue with the BVH served from L1/L2, see DESIGN.md"},
             "counters": {"casts_per_unit": rays / units_step,
                          "nodes_per_cast": sm[3] / max(sm[2], 1.0), "prims_per_cast": sm[4] / max(sm[2], 1.0)},
             "bvh": {"prims": int(after["num_prims"]), "bytes": int(after["bvh_bytes"]), "build_s": after["t_build"],
                     "h2d_s": after["t_h2d"]},
+            # tail of every launch: the last tiles' azimuth chains run as four segment tasks each;
+            # "recomputed" = segments the fix-up pass had to redo because their start index was not the chain's (rank 0)
+            "tail_segments": {"tasks_per_step": int(after["segment_tasks"] - before["segment_tasks"]) // args.steps,
+                              "recomputed": int(after["segment_redos"] - before["segment_redos"])},
         }
         if gather_check:
             line["gather_check"] = gather_check

@@ -293,7 +293,7 @@ int hzb_debug_option(const char* name, int value) {
     return 1;
 }
 // Release the idle pooled memory of this process (device blocks of the host tier, page-locked output blocks).
-void hzb_trim(void) { pool_trim(); host_block_trim(); }
+void hzb_trim(void) { pool_trim(); host_block_trim(); seg_pool_trim(); }
 void* hzb_host_alloc(size_t bytes) { if (require_device()) return nullptr; return host_block_alloc(bytes); }
 void hzb_host_free(void* p) { host_block_free(p); }
 

@@ -804,9 +804,15 @@ static void queue_sections(HorizonParams& p, int tiles_x, int tiles_y) {
 // Memory pool of the segment records, one per device: stream-ordered allocation without synchronisation, and -- unlike
 // the device's default pool -- it keeps its few MB across synchronisation points, so a repeated launch never goes
 // to the operating system (on some boxes that costs tens of milliseconds).
+static std::mutex g_seg_mu;
+static std::vector<cudaMemPool_t> g_seg_pools;
+void seg_pool_trim() {      // hzb_trim(): give the idle blocks back
+    std::lock_guard<std::mutex> lk(g_seg_mu);
+    for (cudaMemPool_t mp : g_seg_pools) if (mp) cudaMemPoolTrimTo(mp, 0);
+}
 static cudaMemPool_t seg_pool(int device) {
-    static std::mutex mu;
-    static std::vector<cudaMemPool_t> pools;
+    std::mutex& mu = g_seg_mu;
+    std::vector<cudaMemPool_t>& pools = g_seg_pools;
     std::lock_guard<std::mutex> lk(mu);
     if (device < 0) return nullptr;
     if ((size_t)device >= pools.size()) pools.resize((size_t)device + 1, nullptr);
