@@ -20,6 +20,7 @@
 #include "hzb_wq.cuh"
 #include "hzb_wq2.cuh"
 #include "hzb_search.cuh"
+#include "hzb_queue.cuh"
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -297,61 +298,7 @@ __device__ __forceinline__ int local_blocks(const HorizonParams& p, int rows) {
 //        [interior tiles in row order, whole chains] [the last q_tail interior tiles x SEG_COUNT segments, segment-major]
 // (rows still complete in order for the host tier's overlapped copy: the interior is the last part of every row).
 // ---------------------------------------------------------------------------
-// queue entry q -> tile (ty, tx) and task: seg 0 = the whole chain, 1 + n = azimuth segment n
-__device__ __forceinline__ void queue_decode(const HorizonParams& p, unsigned int q, int& ty, int& tx, int& seg) {
-    seg = 0;
-    if (q < p.q_nA1) { ty = (int)(q / p.q_tiles_x); tx = (int)(q % p.q_tiles_x); return; }
-    q -= p.q_nA1;
-    if (q < p.q_nA2) { ty = p.q_by1 + (int)(q / p.q_tiles_x); tx = (int)(q % p.q_tiles_x); return; }
-    q -= p.q_nA2;
-    if (q < p.q_nA3) {
-        const int w2 = 2 * p.q_bx, c = (int)(q % w2);
-        ty = p.q_by0 + (int)(q / w2); tx = c < p.q_bx ? c : p.q_tiles_x - w2 + c;
-        return;
-    }
-    q -= p.q_nA3;
-    unsigned int b = q;
-    if (q >= p.q_nI - p.q_tail) {
-        const unsigned int u = q - (p.q_nI - p.q_tail);
-        seg = 1 + (int)(u / p.q_tail); b = p.q_nI - p.q_tail + u % p.q_tail;
-    }
-    ty = p.q_by0 + (int)(b / p.q_wi); tx = p.q_bx + (int)(b % p.q_wi);
-}
-// index of tile (local block row lb, tile column tx) among the split tiles, or -1
-__device__ __forceinline__ int tail_tile(const HorizonParams& p, int lb, int tx) {
-    if (p.seg_count <= 1 || lb < p.q_by0 || lb >= p.q_by1 || tx < p.q_bx || tx >= p.q_tiles_x - p.q_bx) return -1;
-    const int b = (lb - p.q_by0) * p.q_wi + (tx - p.q_bx);
-    return b - (int)(p.q_nI - p.q_tail);      // < 0: interior, not split
-}
-// does cell (ci, cj) belong to a split tile?  (no division: compared as global block rows, host-prepared bounds)
-__device__ __forceinline__ bool cell_is_split(const HorizonParams& p, int ci, int cj) {
-    const int gb = (ci - p.row_begin) >> 2, tx = cj >> 3;
-    return p.seg_count > 1 && tx >= p.q_bx && tx < p.q_tiles_x - p.q_bx && gb < p.q_gb_end &&
-           (gb > p.q_gb_tail || (gb == p.q_gb_tail && tx >= p.q_tx_tail));
-}
-__device__ __forceinline__ int seg_begin(const HorizonParams& p, int n) { return (int)(((long long)n * p.azim_num) / SEG_COUNT); }
-// the lane's cell word: row << 16 | column (both <= 32767, horizon.pyx:149-151) with the segment number in bits 15 and 31
-__device__ __forceinline__ int cell_row(unsigned int w) { return (int)((w >> 16) & 0x7FFFu); }
-__device__ __forceinline__ int cell_col(unsigned int w) { return (int)(w & 0x7FFFu); }
-__device__ __forceinline__ int cell_seg(unsigned int w) { return (int)(((w >> 15) & 1u) | ((w >> 30) & 2u)); }
-// record of (cell of a split tile, segment n >= 1); n == SEG_COUNT: the cell's shared record (guess = the index the
-// bisection of azimuth 0 ended with, published by the lane that owns segment 0)
-__device__ __forceinline__ SegRecord* seg_record(const HorizonParams& p, int ci, int cj, int n) {
-    const int gb = (ci - p.row_begin) >> 2, lb = (gb - p.blk_offset) / p.blk_stride;
-    const int tt = tail_tile(p, lb, cj >> 3);
-    const int in_tile = (((ci - p.row_begin) & 3) << 3) | (cj & 7);
-    return p.seg + ((size_t)tt * 32 + in_tile) * SEG_COUNT + (n - 1);
-}
-// cell slots (one per task) of local block row lb: what publish_cell counts up to
-__device__ __forceinline__ unsigned int row_slots(const HorizonParams& p, int lb) {
-    unsigned int n = p.row_full;
-    if (p.seg_count > 1 && lb >= p.q_by0 && lb < p.q_by1) {
-        const long long over = (long long)(lb - p.q_by0 + 1) * p.q_wi - (long long)(p.q_nI - p.q_tail);
-        const long long split = over < 0 ? 0 : (over > p.q_wi ? p.q_wi : over);
-        n += (unsigned int)split * 32u * (unsigned int)(p.seg_count - 1);
-    }
-    return n;
-}
+__device__ __forceinline__ SegRecord* seg_record(const HorizonParams& p, int ci, int cj, int n) { return p.seg + seg_record_index(p, ci, cj, n); }
 
 constexpr int HG_THREADS = 128;
 
@@ -784,22 +731,6 @@ __global__ void k_loc_dist_fix(LocationParams lp, int azim_num, const float4* or
 }
 
 }  // namespace
-
-static void queue_sections(HorizonParams& p, int tiles_x, int tiles_y) {
-    p.q_tiles_x = tiles_x; p.q_tiles_y = tiles_y; p.q_wi = tiles_x - 2 * p.q_bx;
-    p.q_nA1 = (unsigned int)p.q_by0 * (unsigned int)tiles_x; p.q_nA2 = (unsigned int)(tiles_y - p.q_by1) * (unsigned int)tiles_x;
-    p.q_nA3 = (unsigned int)(p.q_by1 - p.q_by0) * 2u * (unsigned int)p.q_bx;
-    p.q_nI = (unsigned int)(p.q_by1 - p.q_by0) * (unsigned int)p.q_wi;
-    p.q_total = p.q_nA1 + p.q_nA2 + p.q_nA3 + p.q_nI + p.q_tail * (unsigned int)(p.seg_count - 1);
-    // first split tile (interior tile nI - tail) and the end of the interior as GLOBAL block rows of the launch's row range
-    p.q_gb_end = p.q_by1 * p.blk_stride + p.blk_offset;
-    p.q_gb_tail = p.q_gb_end; p.q_tx_tail = 0;
-    if (p.q_tail > 0 && p.q_wi > 0) {
-        const unsigned int first = p.q_nI - p.q_tail;
-        p.q_gb_tail = (p.q_by0 + (int)(first / (unsigned int)p.q_wi)) * p.blk_stride + p.blk_offset;
-        p.q_tx_tail = p.q_bx + (int)(first % (unsigned int)p.q_wi);
-    }
-}
 
 // Memory pool of the segment records, one per device: stream-ordered allocation without synchronisation, and -- unlike
 // the device's default pool -- it keeps its few MB across synchronisation points, so a repeated launch never goes

@@ -6,6 +6,7 @@
 #include <vector>
 #include "../../include/horayzon_b200.h"
 #include "hzb_hd.cuh"
+#include "hzb_queue.cuh"
 
 namespace hzb {
 
@@ -138,13 +139,6 @@ struct HorizonTables {  // host copies; built exactly like horizon_comp.cpp:711-
     std::vector<float> azim_sin, azim_cos, elev_ang, elev_sin, elev_cos;
     void make(int azim_num, float dist_km, float acc_deg, float low_deg, bool fill = true);
 };
-
-// One record per (split cell, segment >= 1).  guess: the chain index the segment's prelude assumed at the azimuth in
-// front of the segment (guess_constant), SEG_OK where no assumption is needed, SEG_REDO after a full traversal stack,
-// SEG_NONE (the buffer's initial value) if the task never ran.  casts: reference casts the task counted.
-struct SegRecord { int guess; unsigned int casts; };
-constexpr int SEG_NONE = -1, SEG_REDO = -2, SEG_OK = -3;
-constexpr int SEG_COUNT = 4;     // segments of a split cell (the lane keeps the segment number in two spare bits of its cell word)
 
 struct HorizonParams {
     // tables (device)

@@ -31,7 +31,8 @@ def build(force=False):
             os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_search.cuh"),
             os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_tri.cuh"),
             os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_box.cuh"),
-            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_hd.cuh")]
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_hd.cuh"),
+            os.path.join(os.path.dirname(_HERE), "horayzon_b200", "csrc", "hzb_queue.cuh")]
     if (force or not os.path.exists(_SO)
             or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs if os.path.exists(f))):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libhzb_oracle.so"],
@@ -416,3 +417,11 @@ def selftest_segments(vert_grid, dem_dim_0, dem_dim_1, offset_0, offset_1, dim_i
                                   ctypes.c_float(ray_org_elev), ray_algorithm.encode(), int(segments), int(bool(tilted)),
                                   ctypes.byref(a), st)
     return int(bad), a.value, int(st[0]), int(st[1]), int(st[2])
+
+
+def selftest_queue(seed=1, iters=2000):
+    """Enumerate the PRODUCT's work queue (csrc/hzb_queue.cuh, host build) for random launch geometries; returns the
+    number of violations (tiles / segments not covered exactly once, predicates that disagree with the enumeration)."""
+    L = lib()
+    L.orc_selftest_queue.restype = ctypes.c_longlong
+    return int(L.orc_selftest_queue(ctypes.c_ulonglong(seed), ctypes.c_longlong(iters)))

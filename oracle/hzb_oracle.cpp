@@ -58,6 +58,7 @@
 
 // the PRODUCT's search state machine, compiled for the host (unit under test of orc_selftest_state_machine)
 #include "../horayzon_b200/csrc/hzb_search.cuh"
+#include "../horayzon_b200/csrc/hzb_queue.cuh"
 #include "../horayzon_b200/csrc/hzb_tri.cuh"
 #include "../horayzon_b200/csrc/hzb_box.cuh"
 
@@ -1197,6 +1198,83 @@ long long orc_selftest_folded_slab(unsigned long long seed, long long n, int pad
     return bad;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// The product's work-queue arithmetic (horayzon_b200/csrc/hzb_queue.cuh, the source the CUDA kernels compile) on the
+// CPU: for random launch geometries -- tile grid, block sharding, band, number of split tiles -- the whole queue is
+// enumerated.  Every tile must come up exactly once as a whole-chain task or exactly once per azimuth segment, whole
+// chains before segments, the interior in row order; the split-tile predicates the lanes and the fix-up kernel use
+// (tail_tile, cell_is_split), the record indices and the per-row task counts the host tier waits for must all agree
+// with the enumeration.  Returns the number of violations.  Test infrastructure only.
+// ---------------------------------------------------------------------------
+namespace {
+struct QueueP {     // the queue fields of HorizonParams
+    int seg_count, q_by0, q_by1, q_bx; unsigned int q_tail;
+    int q_tiles_x, q_tiles_y, q_wi; unsigned int q_nA1, q_nA2, q_nA3, q_nI, q_total;
+    int q_gb_end, q_gb_tail, q_tx_tail;
+    int row_begin, blk_stride, blk_offset, azim_num; unsigned int row_full;
+};
+}
+extern "C" long long orc_selftest_queue(unsigned long long seed, long long iters) {
+    Rng R{seed};
+    long long bad = 0;
+    for (long long it = 0; it < iters; ++it) {
+        QueueP p{};
+        const int tiles_x = 1 + (int)(R.next() % 24), tiles_y = 1 + (int)(R.next() % 24);
+        p.blk_stride = 1 + (int)(R.next() % 4); p.blk_offset = (int)(R.next() % p.blk_stride); p.row_begin = 4 * (int)(R.next() % 3);
+        p.azim_num = 16 + (int)(R.next() % 400); p.row_full = (unsigned int)tiles_x * 32u;
+        p.q_by0 = (int)(R.next() % (tiles_y + 1)); p.q_by1 = p.q_by0 + (int)(R.next() % (tiles_y - p.q_by0 + 1));
+        p.q_bx = (int)(R.next() % (tiles_x / 2 + 1));
+        const long long interior = (long long)(p.q_by1 - p.q_by0) * (tiles_x - 2 * p.q_bx);
+        p.q_tail = interior > 0 ? (unsigned int)(R.next() % (interior + 1)) : 0u;
+        if (it % 7 == 0) p.q_tail = (unsigned int)std::max(0ll, interior);
+        p.seg_count = p.q_tail > 0 ? hzb::SEG_COUNT : 1;
+        hzb::queue_sections(p, tiles_x, tiles_y);
+        std::vector<int> whole(tiles_x * tiles_y, 0), segs(tiles_x * tiles_y * hzb::SEG_COUNT, 0), per_row(tiles_y, 0);
+        bool seen_seg = false; int last_interior = -1;
+        for (unsigned int q = 0; q < p.q_total; ++q) {
+            int ty = -1, tx = -1, task = -1;
+            hzb::queue_decode(p, q, ty, tx, task);
+            if (ty < 0 || ty >= tiles_y || tx < 0 || tx >= tiles_x || task < 0 || task > hzb::SEG_COUNT) { ++bad; continue; }
+            per_row[ty]++;
+            if (task == 0) { whole[ty * tiles_x + tx]++; if (seen_seg) ++bad; }
+            else { segs[(ty * tiles_x + tx) * hzb::SEG_COUNT + task - 1]++; seen_seg = true; }
+            const bool in_interior = ty >= p.q_by0 && ty < p.q_by1 && tx >= p.q_bx && tx < tiles_x - p.q_bx;
+            if (task == 0 && in_interior) { const int b = ty * tiles_x + tx; if (b < last_interior) ++bad; last_interior = b; }
+        }
+        std::vector<int> rec_seen((size_t)p.q_tail * 32 * hzb::SEG_COUNT, 0), tt_seen(p.q_tail, 0);
+        for (int ty = 0; ty < tiles_y; ++ty) {
+            if (hzb::row_slots(p, ty) != 32u * (unsigned int)per_row[ty]) ++bad;
+            for (int tx = 0; tx < tiles_x; ++tx) {
+                const int tt = hzb::tail_tile(p, ty, tx);
+                const bool split = tt >= 0;
+                if (split) { if (tt >= (int)p.q_tail) { ++bad; continue; } tt_seen[tt]++; }
+                if (whole[ty * tiles_x + tx] != (split ? 0 : 1)) ++bad;
+                for (int n = 0; n < hzb::SEG_COUNT; ++n) if (segs[(ty * tiles_x + tx) * hzb::SEG_COUNT + n] != (split ? 1 : 0)) ++bad;
+                for (int r = 0; r < 4; ++r) for (int c = 0; c < 8; c += 7) {
+                    const int ci = p.row_begin + (ty * p.blk_stride + p.blk_offset) * 4 + r, cj = tx * 8 + c;
+                    if (hzb::cell_is_split(p, ci, cj) != split) ++bad;
+                    unsigned int w = ((unsigned int)ci << 16) | (unsigned int)cj;
+                    if (hzb::cell_row(w) != ci || hzb::cell_col(w) != cj || hzb::cell_seg(w) != 0) ++bad;
+                    if (split) for (int n = 1; n <= hzb::SEG_COUNT; ++n) {
+                        const size_t ri = hzb::seg_record_index(p, ci, cj, n);
+                        if (ri >= rec_seen.size()) ++bad; else rec_seen[ri]++;
+                    }
+                }
+            }
+        }
+        for (int v : tt_seen) if (v != 1) ++bad;
+        for (size_t i = 0; i < rec_seen.size(); ++i) {      // rows 0..3 x columns {0, 7} of every split tile were enumerated
+            const int in_tile = (int)((i / hzb::SEG_COUNT) % 32);
+            if (rec_seen[i] != (((in_tile & 7) == 0 || (in_tile & 7) == 7) ? 1 : 0)) ++bad;
+        }
+        for (int n = 0; n <= hzb::SEG_COUNT; ++n) {          // segment bounds partition the azimuths, every segment starts behind azimuth 1
+            const int k = hzb::seg_begin(p, n);
+            if ((n == 0 && k != 0) || (n == hzb::SEG_COUNT && k != p.azim_num) || (n > 0 && k <= hzb::seg_begin(p, n - 1)) || (n == 1 && k < 2)) ++bad;
+        }
+    }
+    return bad;
+}
 
 // ---------------------------------------------------------------------------
 // The product's search state machine (horayzon_b200/csrc/hzb_search.cuh, the source the CUDA

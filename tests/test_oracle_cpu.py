@@ -365,6 +365,14 @@ def test_azimuth_segments_on_the_cpu(alg):
         assert missed > 0
 
 
+def test_queue_order_covers_every_task_once():
+    """The work queue of a horizon launch (csrc/hzb_queue.cuh, the kernels' own source built for the host): band tiles
+    first, interior in row order, the last tiles once per azimuth segment -- enumerated for 4000 random geometries
+    (tile grids, block sharding, bands, tail sizes incl. none / everything).  Every task exactly once, whole chains
+    before segments, and the predicates the lanes, the fix-up kernel and the host tier's row counters use agree."""
+    assert oracle.selftest_queue(seed=11, iters=4000) == 0
+
+
 def test_parity_sensitivity_to_the_rounding_of_the_triangle_test():
     """The ray path is 'parity unpinned' (Embree absent).  What CAN be measured: how many outputs depend on the
     rounding of the triangle test at all.  The oracle with the specified fp32 Pluecker arithmetic against the same
