@@ -772,6 +772,7 @@ static void plan_queue(const Scene& s, HorizonParams& p, int grid_ctas) {
     if (o.tail_segments == 1 || o.horizon_kernel != 0 || tiles_y <= 0 || tiles_x <= 0) return;
     const bool forced = o.tail_segments == SEG_COUNT;
     if (p.azim_num < 4 * SEG_COUNT) return;                 // every segment starts behind azimuth 1 and has a few azimuths
+    if (p.elev_num < 32) return;                            // the prelude bisects rungs 10 table entries apart: not worth it (or defined) on a tiny table
     const long long warps = (long long)grid_ctas * WQ_NWARPS;
     if (!forced) {
         if (p.azim_num < 64) return;
