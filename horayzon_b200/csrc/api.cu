@@ -284,7 +284,6 @@ int hzb_debug_option(const char* name, int value) {
     if (!strcmp(name, "wwait")) { o.wwait = value; return 0; }
     if (!strcmp(name, "no_overlap")) { o.no_overlap = value; return 0; }
     if (!strcmp(name, "stack_limit")) { o.stack_limit = value; return 0; }
-    if (!strcmp(name, "horizon_variant")) { o.horizon_variant = value; return 0; }
     if (!strcmp(name, "ctas_per_sm")) { o.ctas_per_sm = value; return 0; }
     if (!strcmp(name, "tail_segments")) { o.tail_segments = value; return 0; }
     if (!strcmp(name, "tail_tiles")) { o.tail_tiles = value; return 0; }

@@ -83,7 +83,6 @@ struct DebugOptions {
     int wrefill = 24, wwait = 2;
     int no_overlap = 0;       // host tier: copy the horizon array after the kernel instead of while it runs
     int stack_limit = 1 << 20; // clamped to WQ_STACK_N; lowered by the tests to force the full-stack fallback
-    int horizon_variant = 0;  // A/B experiments inside the production kernel family
     int ctas_per_sm = 0;      // horizon kernel: resident CTAs per SM of the persistent grid (0: the compiled maximum)
     int tail_segments = -1;   // azimuth segments per cell in the tail of a launch: -1 automatic (4 where it pays), 1 off, 4 forced
     int tail_tiles = -1;      // tiles whose cells are split (-1: two per resident warp)

@@ -77,8 +77,9 @@ void hzb_host_free(void* p);
 void hzb_trim(void);
 /* Test-only switches: second implementations ("horizon_kernel" 1, "shadow_kernel" 1/2: reference-shaped
  * per-lane kernels on the binary BVH / nearest-first order), tuning knobs ("wrefill", "wwait"),
- * "no_overlap", "stack_limit" (forces the full-stack fallback), "reset".  Production code never
- * calls it; no environment variable selects a kernel. */
+ * "no_overlap", "stack_limit" (forces the full-stack fallback), "tail_segments" / "tail_tiles" /
+ * "tail_band" (azimuth segments in the tail of a horizon launch: off, forced, everywhere),
+ * "ctas_per_sm", "reset".  Production code never calls it; no environment variable selects a kernel. */
 int hzb_debug_option(const char* name, int value);
 
 /* --------------------------------------------------------------- host tier */
