@@ -262,7 +262,10 @@ __device__ __forceinline__ void flush_counters(LaneCounters& cnt, unsigned int u
 // block's counter goes up, and the lane that completes the block raises the block's flag in mapped host
 // memory -- the host tier polls those flags and copies finished blocks while the kernel is still running.
 __device__ __forceinline__ void publish_cell(const HorizonParams& p, int blk, unsigned int slots) {
-    __threadfence_system();
+    // device scope is enough for the cell's outputs: they are read by the copy engine (through L2) after the host has
+    // seen the block's flag, and the flag is written behind a system-scope fence by the lane that saw every other
+    // lane's (fenced) arrival
+    __threadfence();
     if (atomicAdd(p.row_done + blk, 1u) == slots - 1u && p.row_flags) {
         __threadfence_system();
         p.row_flags[blk] = 1u;
