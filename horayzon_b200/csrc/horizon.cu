@@ -796,10 +796,11 @@ static void plan_queue(const Scene& s, HorizonParams& p, int grid_ctas) {
     const int r0 = std::max(0, band_y - p.offset_0), r1 = std::min(p.dim_in_0, s.H - band_y - p.offset_0);
     const int c0 = std::max(0, band_x - p.offset_1), c1 = std::min(p.dim_in_1, s.W - band_x - p.offset_1);
     // whole 4-row blocks of this launch / whole 8-column tiles inside it
-    const int gb0 = std::max(0, (r0 - p.row_begin + 3) >> 2), gb1 = std::max(0, std::min(all, (r1 - p.row_begin) >> 2));
+    // (a partial last block / tile only holds cells beyond the domain's end: it counts as inside when the band does not cut there)
+    const int gb0 = std::max(0, (r0 - p.row_begin + 3) >> 2), gb1 = r1 >= p.row_end ? all : std::max(0, std::min(all, (r1 - p.row_begin) >> 2));
     auto local_below = [&](int gb) { return gb > p.blk_offset ? std::min(tiles_y, (gb - p.blk_offset + p.blk_stride - 1) / p.blk_stride) : 0; };   // local blocks with global index < gb
     const int by0 = local_below(gb0), by1 = std::max(by0, local_below(gb1));
-    const int bx = std::max((c0 + 7) >> 3, tiles_x - (std::max(c1, 0) >> 3));
+    const int bx = std::max((c0 + 7) >> 3, c1 >= p.dim_in_1 ? 0 : tiles_x - (std::max(c1, 0) >> 3));
     if (by1 <= by0 || 2 * bx >= tiles_x) return;            // no interior
     const long long interior = (long long)(by1 - by0) * (tiles_x - 2 * bx);
     // two tiles per resident warp: the split part outlasts the last whole chains (measured on cfg2: one tile per warp
@@ -810,6 +811,9 @@ static void plan_queue(const Scene& s, HorizonParams& p, int grid_ctas) {
     p.seg_count = SEG_COUNT; p.q_by0 = by0; p.q_by1 = by1; p.q_bx = bx; p.q_tail = (unsigned int)tail;
     queue_sections(p, tiles_x, tiles_y);
 }
+
+// host-only view of plan_queue for the CPU suite (hzb_plan_queue, api.cu)
+void plan_queue_host(const Scene& s, HorizonParams& p, int grid_ctas) { plan_queue(s, p, grid_ctas); }
 
 int launch_horizon_gridded(Scene& s, const HorizonParams& p_in, cudaStream_t st) {
     HorizonParams p = p_in;

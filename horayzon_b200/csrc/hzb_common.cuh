@@ -187,6 +187,7 @@ struct LocationParams {
 };
 int launch_horizon_locations(Scene& s, const HorizonParams& p, const LocationParams& lp, cudaStream_t st);
 int scene_tables(Scene& s, int azim_num, float dist_km, float acc_deg, float low_deg, HorizonParams& p, cudaStream_t st);
+void plan_queue_host(const Scene& s, HorizonParams& p, int grid_ctas);   // queue layout of a launch (no device needed)
 void seg_pool_trim();      // releases the idle memory of the segment-record pools (hzb_trim)
 unsigned int* scene_tile_counter(Scene& s, cudaStream_t st);   // fresh (zeroed on `st`) work-queue counter for one launch
 constexpr unsigned int HZB_TILE_SLOTS = 64;

@@ -75,6 +75,14 @@ void hzb_host_free(void* p);
 /* Additive: release the idle pooled memory of this process (device blocks the host tier keeps
  * between calls, at most 6 GB; the one idle page-locked output block, at most 4 GB). */
 void hzb_trim(void);
+/* Additive, pure host code (no device needed; for test suites): the work-queue layout the horizon kernel would use for a
+ * launch (band along the DEM's edge first, interior in row order, the last tiles as azimuth segments; DESIGN.md
+ * section 5).  lo / hi: bounds of the DEM vertices (3 floats each); resident_ctas: CTAs of the persistent grid.
+ * out[0..6] = segments per split cell (1: no split), first / end local block row and tile-column margin of the interior,
+ * split tiles, queue entries, tiles of the launch. */
+int hzb_plan_queue(int dem_dim_0, int dem_dim_1, const float* lo, const float* hi, int offset_0, int offset_1, int dim_in_0,
+                   int dim_in_1, int row_begin, int row_end, int shard_rank, int shard_count, int azim_num, float hori_acc,
+                   float elev_ang_low_lim, const char* ray_algorithm, int resident_ctas, long long* out);
 /* Test-only switches: second implementations ("horizon_kernel" 1, "shadow_kernel" 1/2: reference-shaped
  * per-lane kernels on the binary BVH / nearest-first order), tuning knobs ("wrefill", "wwait"),
  * "no_overlap", "stack_limit" (forces the full-stack fallback), "tail_segments" / "tail_tiles" /

@@ -268,3 +268,44 @@ def test_round2_additive_api_validation():
     assert resident.lib().hzb_debug_option(b"no_such_option", 1) != 0
     assert resident.lib().hzb_shard_rows(1199, 0, 8) == 152 and resident.lib().hzb_shard_rows(1199, 7, 8) == 148
     assert sum(resident.lib().hzb_shard_rows(1199, r, 8) for r in range(8)) == 1200
+
+
+def _plan(H, W, lo, hi, off0, off1, ny, nx, r0, r1, rank, world, K, acc=0.25, low=-15.0, alg="guess_constant", ctas=148 * 6):
+    L = resident.lib()
+    out = (ctypes.c_longlong * 7)()
+    lo_a, hi_a = (ctypes.c_float * 3)(*lo), (ctypes.c_float * 3)(*hi)
+    rc = L.hzb_plan_queue(H, W, lo_a, hi_a, off0, off1, ny, nx, r0, r1, rank, world, K, ctypes.c_float(acc), ctypes.c_float(low),
+                          alg.encode(), ctas, out)
+    assert rc == 0
+    return dict(zip(("seg", "by0", "by1", "bx", "tail", "total", "tiles"), [int(v) for v in out]))
+
+
+def test_queue_plan_of_the_bench_workloads(built):
+    """The host-side queue layout (hzb_plan_queue: pure host code): which launches get a split tail, and where the band
+    along the DEM's edge ends (cells closer to the edge than relief / tan(-low limit) may see below the elevation table
+    and are never split)."""
+    # cfg2: 1201 x 1201 at 90 m, relief ~3.6 km -> band ~150 cells; one GPU and one of eight interleaved shards
+    lo, hi = (0.0, 0.0, -1800.0), (108000.0, 108000.0, 1800.0)
+    p1 = _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360)
+    band = int(np.ceil(3600.0 / np.tan(np.deg2rad(15.0)) / 90.0))
+    assert p1["seg"] == 4 and p1["tail"] == 2 * 148 * 6 * 4
+    assert p1["by0"] == (band - 1 + 3) // 4 and p1["bx"] == (band - 1 + 7) // 8
+    assert p1["tiles"] == 150 * 300 and p1["total"] == p1["tiles"] + 3 * p1["tail"]
+    p8 = [_plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, r, 8, 360) for r in range(8)]
+    assert all(p["seg"] == 4 for p in p8)
+    assert sum(p["tiles"] for p in p8) == p1["tiles"]
+    assert sum(p["by1"] - p["by0"] for p in p8) == p1["by1"] - p1["by0"]      # the shards' interiors partition the interior
+    assert all(p["tail"] == (p["by1"] - p["by0"]) * (150 - 2 * p["bx"]) for p in p8)      # at N = 8 the whole interior is split
+    # the north-star workload on one GPU: 40+ cells per lane, the tail is noise -> whole chains only
+    lo4, hi4 = (0.0, 0.0, -790.0), (11998.0, 11998.0, 790.0)
+    assert _plan(6000, 6000, lo4, hi4, 1, 1, 5998, 5998, 0, 5998, 0, 1, 360)["seg"] == 1
+    # inner domain far from the DEM's edge (the reference's usual set-up): no band at all
+    far = _plan(1201, 1201, lo, hi, 300, 300, 601, 601, 0, 601, 0, 1, 360)
+    assert far["seg"] == 4 and far["by0"] == 0 and far["bx"] == 0 and far["by1"] == (601 + 3) // 4
+    # few azimuths, tiny elevation table, low limit above the horizontal (guess_constant): never split
+    assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 36)["seg"] == 1
+    assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, acc=30.0)["seg"] == 1
+    assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, low=5.0)["seg"] == 1
+    # independent azimuths need no band
+    ind = _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, alg="binary_search")
+    assert ind["seg"] == 4 and ind["by0"] == 0 and ind["bx"] == 0
