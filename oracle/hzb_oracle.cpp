@@ -39,6 +39,12 @@
 // from the stable geometric normal).  Operation order and fused-multiply-add
 // placement are fixed in tri_hit() below and documented in DESIGN.md; the CUDA
 // product implements the same specification independently.
+// For the CPU TIMING legs of bench.py only (orc_set_fast_traversal) pure grid
+// scenes also get an implicit 4-ary hierarchy over the quads whose four child
+// boxes are tested per SSE step (Scene::occluded_fast): the same decisions --
+// boxes only cull -- three to seven times faster, so that the reported CPU
+// baseline is not held back by the plain walker.  Every parity check keeps the
+// plain binary-BVH walker; tests/test_oracle_cpu.py pins fast == plain.
 //
 // Deviation shared by oracle and product: where the
 // reference would loop forever (still "hit" at the top table index, still
@@ -55,6 +61,7 @@
 #include <string>
 #include <vector>
 #include <omp.h>
+#include <immintrin.h>
 
 // the PRODUCT's search state machine, compiled for the host (unit under test of orc_selftest_state_machine)
 #include "../horayzon_b200/csrc/hzb_search.cuh"
@@ -150,6 +157,8 @@ static inline bool tri_hit_exact(const Tri& T, V3 O, V3 D, float tfar, float* t_
 // and grid (horizon_comp.cpp:140-151, 163-171, 178-183).
 // ---------------------------------------------------------------------------
 struct BNode { float lo[3], hi[3]; int left, right, first, count; };
+static bool g_fast_traversal = false;      // orc_set_fast_traversal: scenes built while it is on also get the 4-ary grid hierarchy, casts use it
+static inline bool g_fast_traversal_fwd() { return g_fast_traversal; }
 
 struct Scene {
     std::vector<Tri> tris;
@@ -159,8 +168,18 @@ struct Scene {
     float pad = 0.f;
     double build_s = 0.0;
     int node_count = 0;
+    // Fast any-hit traversal for pure grid scenes (the CPU timing legs of bench.py; orc_set_fast_traversal): an implicit
+    // 4-ary hierarchy over the grid quads -- level 0 = one quad, a node of level l covers 2^l x 2^l quads -- with the
+    // boxes of the four children of a node stored side by side, so that one step tests four boxes with SSE.  Same
+    // padding and slack as the binary BVH; a cast is still the OR of tri_hit over the triangles whose boxes the ray
+    // meets, i.e. the same decision (tests/test_oracle_cpu.py::test_fast_traversal_equals_plain).
+    int gH = 0, gW = 0;                        // vertices of the grid (0: none)
+    struct Level { int nh = 0, nw = 0, ph = 0, pw = 0; std::vector<float> p[6]; };    // nodes nh x nw in groups of four per parent (ph x pw); p: lo xyz, hi xyz
+    std::vector<Level> lv;
+    bool fast_ready = false;
 
     void add_grid(const float* vg, int H, int W) {
+        if (tris.empty()) { gH = H; gW = W; } else gH = gW = 0;      // (grid first and only once: quad q = triangles 2q, 2q+1)
         auto P = [&](int i, int j) {
             const float* p = vg + 3 * ((size_t)i * W + j);
             return V3{p[0], p[1], p[2]};
@@ -261,6 +280,92 @@ struct Scene {
 #pragma omp parallel for schedule(static)
         for (long long k = 0; k < (long long)n; ++k) ltris[k] = tris[order[k]];
         build_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (g_fast_traversal_fwd()) build_fast();
+    }
+
+    void build_fast() {
+        fast_ready = false; lv.clear();
+        if (gH < 2 || gW < 2 || tris.size() != (size_t)2 * (gH - 1) * (gW - 1)) return;      // grid only (no TIN)
+        auto t0 = std::chrono::steady_clock::now();
+        int nh = gH - 1, nw = gW - 1;
+        while (true) {
+            Level L; L.nh = nh; L.nw = nw; L.ph = (nh + 1) / 2; L.pw = (nw + 1) / 2;
+            const size_t n = (size_t)L.ph * L.pw * 4;
+            for (int a = 0; a < 3; ++a) { L.p[a].assign(n, INFINITY); L.p[3 + a].assign(n, -INFINITY); }
+            lv.push_back(std::move(L));
+            if (nh == 1 && nw == 1) break;
+            nh = (nh + 1) / 2; nw = (nw + 1) / 2;
+        }
+        auto slot = [](const Level& L, int I, int J) { return (((size_t)(I >> 1) * L.pw + (J >> 1)) << 2) | (size_t)(((I & 1) << 1) | (J & 1)); };
+        {
+            Level& L = lv[0];
+            const int qw = gW - 1;
+#pragma omp parallel for schedule(static)
+            for (int i = 0; i < L.nh; ++i)
+                for (int j = 0; j < L.nw; ++j) {
+                    float lo[3], hi[3], l2[3], h2[3];
+                    const size_t q = (size_t)i * qw + j;
+                    tri_box(tris[2 * q], lo, hi); tri_box(tris[2 * q + 1], l2, h2);
+                    const size_t k = slot(L, i, j);
+                    for (int a = 0; a < 3; ++a) { L.p[a][k] = fminf(lo[a], l2[a]) - pad; L.p[3 + a][k] = fmaxf(hi[a], h2[a]) + pad; }
+                }
+        }
+        for (size_t l = 1; l < lv.size(); ++l) {
+            Level& L = lv[l]; const Level& C = lv[l - 1];
+#pragma omp parallel for schedule(static)
+            for (int I = 0; I < L.nh; ++I)
+                for (int J = 0; J < L.nw; ++J) {
+                    const size_t g = ((size_t)I * C.pw + J) << 2, k = slot(L, I, J);      // C.pw == L.nw
+                    for (int a = 0; a < 3; ++a) {
+                        float lo = INFINITY, hi = -INFINITY;
+                        for (int c = 0; c < 4; ++c) { lo = fminf(lo, C.p[a][g + c]); hi = fmaxf(hi, C.p[3 + a][g + c]); }
+                        L.p[a][k] = lo; L.p[3 + a][k] = hi;
+                    }
+                }
+        }
+        fast_ready = true;
+        build_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    // any-hit over the implicit hierarchy: a stack entry is a node (level L >= 1, I, J) whose four children (level L-1) are tested at once
+    bool occluded_fast(V3 O, V3 D, float tfar) const {
+        float inv[3]; safe_inv(D, inv);
+        const __m128 ox = _mm_set1_ps(O.x), oy = _mm_set1_ps(O.y), oz = _mm_set1_ps(O.z);
+        const __m128 ix = _mm_set1_ps(inv[0]), iy = _mm_set1_ps(inv[1]), iz = _mm_set1_ps(inv[2]);
+        const __m128 zero = _mm_setzero_ps(), far = _mm_set1_ps(tfar), slack = _mm_set1_ps(1.000001f);
+        uint64_t stack[160]; int sp = 0;
+        stack[sp++] = (uint64_t)lv.size() << 32;        // the virtual parent of the single top node
+        const int qw = gW - 1;
+        float t;
+        while (sp) {
+            const uint64_t e = stack[--sp];
+            const int Lp = (int)(e >> 32), I = (int)((e >> 16) & 0xFFFFu), J = (int)(e & 0xFFFFu);
+            const Level& C = lv[Lp - 1];
+            const size_t g = ((size_t)I * C.pw + J) << 2;
+            const __m128 lx = _mm_loadu_ps(&C.p[0][g]), ly = _mm_loadu_ps(&C.p[1][g]), lz = _mm_loadu_ps(&C.p[2][g]);
+            const __m128 hx = _mm_loadu_ps(&C.p[3][g]), hy = _mm_loadu_ps(&C.p[4][g]), hz = _mm_loadu_ps(&C.p[5][g]);
+            const __m128 ax = _mm_mul_ps(_mm_sub_ps(lx, ox), ix), bx = _mm_mul_ps(_mm_sub_ps(hx, ox), ix);
+            const __m128 ay = _mm_mul_ps(_mm_sub_ps(ly, oy), iy), by = _mm_mul_ps(_mm_sub_ps(hy, oy), iy);
+            const __m128 az = _mm_mul_ps(_mm_sub_ps(lz, oz), iz), bz = _mm_mul_ps(_mm_sub_ps(hz, oz), iz);
+            const __m128 t0 = _mm_max_ps(_mm_max_ps(zero, _mm_min_ps(ax, bx)), _mm_max_ps(_mm_min_ps(ay, by), _mm_min_ps(az, bz)));
+            const __m128 t1 = _mm_min_ps(_mm_min_ps(far, _mm_max_ps(ax, bx)), _mm_min_ps(_mm_max_ps(ay, by), _mm_max_ps(az, bz)));
+            int m = _mm_movemask_ps(_mm_and_ps(_mm_cmple_ps(t0, _mm_mul_ps(t1, slack)), _mm_cmple_ps(lx, hx)));     // (lx > hx: no such node)
+            if (!m) continue;
+            if (Lp == 1) {          // children are quads: two triangles each
+                for (int c = 0; c < 4; ++c) if (m & (1 << c)) {
+                    const size_t q = (size_t)(2 * I + (c >> 1)) * qw + (size_t)(2 * J + (c & 1));
+                    if (tri_hit(tris[2 * q], O, D, tfar, &t) || tri_hit(tris[2 * q + 1], O, D, tfar, &t)) return true;
+                }
+            } else {                // push the hit children, the nearest one last
+                alignas(16) float tn[4]; _mm_store_ps(tn, t0);
+                int ord[4], n = 0;
+                for (int c = 0; c < 4; ++c) if (m & (1 << c)) { int k = n++; while (k > 0 && tn[ord[k - 1]] < tn[c]) { ord[k] = ord[k - 1]; --k; } ord[k] = c; }
+                for (int k = 0; k < n; ++k) {
+                    const int c = ord[k];
+                    stack[sp++] = ((uint64_t)(Lp - 1) << 32) | ((uint64_t)(2 * I + (c >> 1)) << 16) | (uint64_t)(2 * J + (c & 1));
+                }
+            }
+        }
+        return false;
     }
 
     static inline bool slab(const BNode& nd, V3 O, const float* inv, float tfar, float* tnear) {
@@ -289,6 +394,7 @@ struct Scene {
             for (const Tri& T : tris) if (tri_hit(T, O, D, tfar, &t)) return true;
             return false;
         }
+        if (fast_ready && g_fast_traversal_fwd()) return occluded_fast(O, D, tfar);
         if (nodes.empty()) return false;
         float inv[3]; safe_inv(D, inv);
         float tn;
@@ -553,6 +659,9 @@ extern "C" {
 
 void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 void orc_set_exact_predicate(int on) { g_exact_predicate = on != 0; }
+// Fast any-hit traversal for pure grid scenes (see Scene::occluded_fast): used by the CPU TIMING legs of bench.py, so that
+// the reported CPU baseline is not held back by the plain binary-BVH walker; the parity checks keep the plain walker.
+void orc_set_fast_traversal(int on) { g_fast_traversal = on != 0; }
 
 // horizon_gridded_comp (horizon_comp.cpp:629-822); argument order as horizon_comp.h:8-20
 int orc_horizon_gridded(const float* vert_grid, int dem_dim_0, int dem_dim_1,

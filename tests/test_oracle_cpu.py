@@ -365,6 +365,45 @@ def test_azimuth_segments_on_the_cpu(alg):
         assert missed > 0
 
 
+def test_fast_traversal_equals_plain():
+    """The oracle's fast any-hit traversal (implicit 4-ary hierarchy over the grid quads, four boxes per SSE step; used by
+    the CPU TIMING legs of bench.py) against its plain binary-BVH walker (used by every parity check): identical horizon
+    arrays and cast counts for all three algorithms and odd grid sizes (partial groups), and identical shadow codes
+    (casts with tfar = inf)."""
+    try:
+        for name, n, K, alg in (("cfg1", None, 36, "guess_constant"), ("cfg1", 77, 20, "binary_search"),
+                                ("cfg1", 50, 12, "discrete_sampling"), ("cfg2", 131, 48, "guess_constant"),
+                                ("cfg4p", 97, 40, "guess_constant")):
+            c = syn.make_config(name, n)
+            args = (c["vert_grid"], c["dem_dim_0"], c["dem_dim_1"], c["vec_norm"], c["vec_north"], c["offset_0"], c["offset_1"],
+                    c["dist_search"])
+            oracle.set_fast_traversal(False)
+            h0, _, r0 = oracle.horizon_gridded(*args, azim_num=K, ray_algorithm=alg, return_rays=True)
+            oracle.set_fast_traversal(True)
+            h1, _, r1 = oracle.horizon_gridded(*args, azim_num=K, ray_algorithm=alg, return_rays=True)
+            assert np.array_equal(h0, h1) and r0 == r1, (name, n, alg)
+        # shadow codes: one any-hit ray per cell towards the sun
+        n, rim = 101, 10
+        x, y, z = syn.sinusoid_dem(n, n, 50.0, 400.0, 4000.0, 5, 4)
+        tilt = syn.tilt_vectors(x, y, z, rim)
+        norm, _ = syn.planar_frames(n - 2 * rim, n - 2 * rim)
+        enl = (1.0 / (norm * tilt).sum(axis=2)).astype(np.float32)
+        elev = np.ascontiguousarray(z[rim:-rim, rim:-rim]); mask = np.ones(elev.shape, np.uint8)
+        vg = syn.rearrange_pad_buffer(x, y, z)
+        codes = []
+        for fast in (False, True):
+            oracle.set_fast_traversal(fast)
+            t = oracle.Terrain()
+            t.initialise(vg, n, n, rim, rim, tilt, norm, enl, elev, mask)
+            out = []
+            for sun in syn.sun_positions_diurnal(6):
+                b = np.empty(mask.shape, np.uint8); t.shadow(sun, b); out.append(b)
+            codes.append(np.stack(out))
+        assert np.array_equal(codes[0], codes[1]) and len(np.unique(codes[0])) > 1
+    finally:
+        oracle.set_fast_traversal(False)
+
+
 def test_queue_order_covers_every_task_once():
     """The work queue of a horizon launch (csrc/hzb_queue.cuh, the kernels' own source built for the host): band tiles
     first, interior in row order, the last tiles once per azimuth segment -- enumerated for 4000 random geometries
