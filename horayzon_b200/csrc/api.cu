@@ -295,16 +295,16 @@ int hzb_debug_option(const char* name, int value) {
 // for a launch -- see horizon.cu, "Queue order and azimuth segments".  out[0..6] = segments per split cell (1: none), first /
 // end local block row and tile-column margin of the interior, split tiles, queue entries, tiles of the launch.
 int hzb_plan_queue(int dem_dim_0, int dem_dim_1, const float* lo, const float* hi, int offset_0, int offset_1, int dim_in_0,
-                   int dim_in_1, int row_begin, int row_end, int shard_rank, int shard_count, int azim_num, float hori_acc,
-                   float elev_ang_low_lim, const char* ray_algorithm, int resident_ctas, long long* out) {
+                   int dim_in_1, int row_begin, int row_end, int shard_rank, int shard_count, int azim_num, float dist_search,
+                   float hori_acc, float elev_ang_low_lim, const char* ray_algorithm, int resident_ctas, long long* out) {
     if (!lo || !hi || !out || !ray_algorithm) { set_error("null argument"); return 1; }
     const int alg = parse_algorithm(ray_algorithm);
     if (alg < 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) { set_error("invalid argument"); return 1; }
     Scene s; s.H = dem_dim_0; s.W = dem_dim_1;
     for (int a = 0; a < 3; ++a) { s.lo[a] = lo[a]; s.hi[a] = hi[a]; }
-    HorizonTables T; T.make(azim_num, 1.0f, hori_acc, elev_ang_low_lim, false);
+    HorizonTables T; T.make(azim_num, dist_search, hori_acc, elev_ang_low_lim, false);
     HorizonParams p{};
-    p.algorithm = alg; p.azim_num = azim_num; p.elev_num = T.elev_num; p.low = T.low;
+    p.algorithm = alg; p.azim_num = azim_num; p.elev_num = T.elev_num; p.low = T.low; p.dist = T.dist;
     p.offset_0 = offset_0; p.offset_1 = offset_1; p.dim_in_0 = dim_in_0; p.dim_in_1 = dim_in_1; p.row_begin = row_begin; p.row_end = row_end;
     p.blk_stride = shard_count; p.blk_offset = shard_rank; p.row_full = (unsigned int)((dim_in_1 + 7) / 8) * 32u;
     plan_queue_host(s, p, resident_ctas);

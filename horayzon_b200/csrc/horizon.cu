@@ -788,6 +788,9 @@ static void plan_queue(const Scene& s, HorizonParams& p, int grid_ctas) {
     else if (p.algorithm == 2) {
         if (!(p.low < -0.01f)) return;                      // low limit near or above the horizontal: chains clamp anywhere
         const double reach = (double)(s.hi[2] - s.lo[2]) / tan(-(double)p.low);
+        // a cell could also lose sight of all terrain above the low limit INSIDE the DEM if the search distance were
+        // shorter than that reach (a slope falling steeper than the low limit all the way to dist_search): no split then
+        if (!(reach < (double)p.dist)) return;
         const double dx = (double)(s.hi[0] - s.lo[0]) / std::max(1, s.W - 1), dy = (double)(s.hi[1] - s.lo[1]) / std::max(1, s.H - 1);
         if (!(dx > 0.0) || !(dy > 0.0)) return;
         band_x = (int)std::min(1e9, ceil(reach / dx)); band_y = (int)std::min(1e9, ceil(reach / dy));

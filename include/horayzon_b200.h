@@ -81,8 +81,8 @@ void hzb_trim(void);
  * out[0..6] = segments per split cell (1: no split), first / end local block row and tile-column margin of the interior,
  * split tiles, queue entries, tiles of the launch. */
 int hzb_plan_queue(int dem_dim_0, int dem_dim_1, const float* lo, const float* hi, int offset_0, int offset_1, int dim_in_0,
-                   int dim_in_1, int row_begin, int row_end, int shard_rank, int shard_count, int azim_num, float hori_acc,
-                   float elev_ang_low_lim, const char* ray_algorithm, int resident_ctas, long long* out);
+                   int dim_in_1, int row_begin, int row_end, int shard_rank, int shard_count, int azim_num, float dist_search,
+                   float hori_acc, float elev_ang_low_lim, const char* ray_algorithm, int resident_ctas, long long* out);
 /* Test-only switches: second implementations ("horizon_kernel" 1, "shadow_kernel" 1/2: reference-shaped
  * per-lane kernels on the binary BVH / nearest-first order), tuning knobs ("wrefill", "wwait"),
  * "no_overlap", "stack_limit" (forces the full-stack fallback), "tail_segments" / "tail_tiles" /

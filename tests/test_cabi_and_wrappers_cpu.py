@@ -270,12 +270,12 @@ def test_round2_additive_api_validation():
     assert sum(resident.lib().hzb_shard_rows(1199, r, 8) for r in range(8)) == 1200
 
 
-def _plan(H, W, lo, hi, off0, off1, ny, nx, r0, r1, rank, world, K, acc=0.25, low=-15.0, alg="guess_constant", ctas=148 * 6):
+def _plan(H, W, lo, hi, off0, off1, ny, nx, r0, r1, rank, world, K, acc=0.25, low=-15.0, alg="guess_constant", ctas=148 * 6, dist=50.0):
     L = resident.lib()
     out = (ctypes.c_longlong * 7)()
     lo_a, hi_a = (ctypes.c_float * 3)(*lo), (ctypes.c_float * 3)(*hi)
-    rc = L.hzb_plan_queue(H, W, lo_a, hi_a, off0, off1, ny, nx, r0, r1, rank, world, K, ctypes.c_float(acc), ctypes.c_float(low),
-                          alg.encode(), ctas, out)
+    rc = L.hzb_plan_queue(H, W, lo_a, hi_a, off0, off1, ny, nx, r0, r1, rank, world, K, ctypes.c_float(dist), ctypes.c_float(acc),
+                          ctypes.c_float(low), alg.encode(), ctas, out)
     assert rc == 0
     return dict(zip(("seg", "by0", "by1", "bx", "tail", "total", "tiles"), [int(v) for v in out]))
 
@@ -298,7 +298,7 @@ def test_queue_plan_of_the_bench_workloads(built):
     assert all(p["tail"] == (p["by1"] - p["by0"]) * (150 - 2 * p["bx"]) for p in p8)      # at N = 8 the whole interior is split
     # the north-star workload on one GPU: 40+ cells per lane, the tail is noise -> whole chains only
     lo4, hi4 = (0.0, 0.0, -790.0), (11998.0, 11998.0, 790.0)
-    assert _plan(6000, 6000, lo4, hi4, 1, 1, 5998, 5998, 0, 5998, 0, 1, 360)["seg"] == 1
+    assert _plan(6000, 6000, lo4, hi4, 1, 1, 5998, 5998, 0, 5998, 0, 1, 360, dist=12.0)["seg"] == 1
     # inner domain far from the DEM's edge (the reference's usual set-up): no band at all
     far = _plan(1201, 1201, lo, hi, 300, 300, 601, 601, 0, 601, 0, 1, 360)
     assert far["seg"] == 4 and far["by0"] == 0 and far["bx"] == 0 and far["by1"] == (601 + 3) // 4
@@ -306,6 +306,9 @@ def test_queue_plan_of_the_bench_workloads(built):
     assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 36)["seg"] == 1
     assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, acc=30.0)["seg"] == 1
     assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, low=5.0)["seg"] == 1
+    # search distance shorter than relief / tan(-low limit): a slope may fall below the table all the way -> never split
+    assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, dist=10.0)["seg"] == 1
+    assert _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, dist=14.0)["seg"] == 4
     # independent azimuths need no band
     ind = _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, alg="binary_search")
     assert ind["seg"] == 4 and ind["by0"] == 0 and ind["bx"] == 0
