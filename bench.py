@@ -35,8 +35,12 @@ configs[1]).  Default workload: cfg2 = 1201 x 1201 synthetic DEM x 360 azimuths
   parity_sensitivity : (N = 1) share of outputs that depend on the rounding of the triangle test.
   --impl reference : the reference's CPU path.  Embree/TBB cannot be installed
           here, so this arm times the CPU oracle (reference-algorithm restatement,
-          NOT Embree; OpenMP over rows where the reference uses TBB) on a
-          stratified row sample of the same workload, on all host cores.
+          NOT Embree; OpenMP over rows where the reference uses TBB; for the timing
+          legs with its SSE traversal of a 4-ary quad hierarchy, pinned bit for bit
+          to the plain walker the parity checks use) on a stratified row sample of
+          the same workload, on all host cores.
+  tail_segments : azimuth-segment tasks per step in the tail of the horizon launch
+           and how many the fix-up pass had to recompute.
 """
 import argparse
 import importlib.util
