@@ -188,8 +188,16 @@ class OracleSampler:
             self.oracle.set_fast_traversal(False)
         return h, self.oracle.last_timing()[1]
 
+    def run_plain(self, rows):
+        """The same rows with the oracle's plain binary-BVH walker (what the parity checks use; reported beside the baseline)."""
+        c = self.c
+        self.scene.horizon_rows(rows, c["vec_norm"], c["vec_north"], c["offset_0"], c["offset_1"], c["dist_search"],
+                                azim_num=self.K, hori_acc=HORI_ACC, ray_algorithm=ALGORITHM)
+        return self.oracle.last_timing()[1]
+
     def size_sample(self, target_s):
         probe = stratified_rows(self.c["ny"], 4)
+        self.plain_value = len(probe) * self.c["nx"] * self.K / max(self.run_plain(probe), 1e-9)
         _, t = self.run(probe)
         n = int(max(4, round(target_s / max(t / len(probe), 1e-4))))
         return stratified_rows(self.c["ny"], n)
@@ -198,6 +206,7 @@ class OracleSampler:
         _, t = self.run(rows)
         units = len(rows) * self.c["nx"] * self.K
         return {"value": units / t, "unit": UNIT, "cores": self.cores, "kind": "port", "rows": len(rows),
+                "plain_walker_value": getattr(self, "plain_value", None),      # 4 probe rows with the oracle's plain binary-BVH walker
                 "sample": "%d inner rows spread evenly over all %d (%d units), ray tracing %.2f s, BVH build %.2f s excluded; "
                           "CPU oracle = reference-algorithm restatement with OpenMP over rows and an SSE 4-wide traversal of a "
                           "quad hierarchy, NOT Embree+TBB (not installable)"
