@@ -10,6 +10,9 @@
 //
 //   k_horizon_wq6      production: search state machine + two-ray packet warp-queue
 //                      traversal of the compressed 4-wide BVH (hzb_wq2.cuh)
+//                      ("Queue order and azimuth segments" below: band first, the last tiles' chains split)
+//   k_horizon_redo     fix-up pass behind every production launch: cells whose traversal stack was full,
+//                      azimuth segments that started from a wrong chain index (normally neither)
 //   k_horizon_gridded  reference-shaped per-lane kernel on the binary BVH: the second,
 //                      structurally different implementation the full-size parity test
 //                      compares the production kernel with (hzb_debug_option, test only)
@@ -287,7 +290,9 @@ __device__ __forceinline__ int local_blocks(const HorizonParams& p, int rows) {
 // of the queue is therefore made of shorter tasks: the cells of the last q_tail tiles are split into SEG_COUNT
 // azimuth SEGMENTS, each a queue entry of its own.  Segment 0 is the head of the chain; a later segment does not know
 // the chain's index at its first azimuth and starts with the prelude of hzb_search.cuh, which finds it from the
-// residue class the chain keeps (two bisections, ~16 casts).  That value is an assumption -- it is wrong when the
+// residue class the chain keeps (one bisection over the rungs of that class, ~8 single-ray casts; the class comes
+// from the bisection of azimuth 0, which the lane that owns the head publishes -- a segment that starts before that
+// repeats it, ~7 casts).  That value is an assumption -- it is wrong when the
 // chain ran into the lower end of the elevation table on its way (horizon below the table's low limit, i.e. cells
 // that look out over the DEM's edge: the index is clamped there and the residue changes) -- so every segment
 // records it, and the fix-up kernel (k_horizon_redo, behind every launch) compares it with the index the preceding
