@@ -312,3 +312,22 @@ def test_queue_plan_of_the_bench_workloads(built):
     # independent azimuths need no band
     ind = _plan(1201, 1201, lo, hi, 1, 1, 1199, 1199, 0, 1199, 0, 1, 360, alg="binary_search")
     assert ind["seg"] == 4 and ind["by0"] == 0 and ind["bx"] == 0
+
+
+def test_ctypes_stats_struct_matches_the_header(built, tmp_path):
+    """resident.Stats (ctypes) must have the size and field offsets of hzb_stats in include/horayzon_b200.h: the library
+    writes the struct through the pointer the binding hands it."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc unavailable")
+    fields = [n for n, _ in resident.Stats._fields_]
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "horayzon_b200.h"\nint main(void){printf("%zu", sizeof(hzb_stats));'
+                   + "".join('printf(" %%zu", offsetof(hzb_stats, %s));' % f for f in fields) + "return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    vals = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert vals[0] == ctypes.sizeof(resident.Stats)
+    assert vals[1:] == [getattr(resident.Stats, f).offset for f in fields]
